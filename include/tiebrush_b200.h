@@ -1,0 +1,170 @@
+/*
+ * tiebrush_b200.h — C ABI of the B200-native TieBrush / TieCov hot path.
+ *
+ * The reference (alevar/tiebrush) has no plugin or FFI surface: its two tools are monolithic main()s.
+ * The seam this library sits behind is the pair of call sites inside the two hot loops
+ * (SURVEY.md §8b):
+ *
+ *   tiebrush:  TInputFiles::next()                      src/tmerge.cpp:331-344   (k-way merge)
+ *              passes_options()                         src/tiebrush.cpp:532-541 (filters)
+ *              addPData() / flushPData()                src/tiebrush.cpp:477-530 (collapse, YC/YX/YD)
+ *   tiecov:    bundle logic                             src/tiecov.cpp:443-481
+ *              addCov() / flushCoverage(FILE*)          src/tiecov.cpp:194-241
+ *              addJunction() / flushJuncs()             src/tiecov.cpp:100-120
+ *
+ * Everything crossing the boundary is a plain pointer + size. No torch / STL types.
+ * Arrays are struct-of-arrays; `on_device` says whether the per-record arrays are host pointers
+ * (the library stages them through pinned memory and copies on its stream) or device pointers
+ * (already resident in HBM; no copy). Small descriptor arrays (run_off, file_merged) are always
+ * host memory.
+ *
+ * Error convention mirrors the reference's GError (gclib/GBase.cpp:31-53): a call returns non-zero,
+ * tb_last_error() gives the message, the caller prints it to stderr and exits 1.
+ * There is NO CPU fallback anywhere behind this ABI: without a CUDA device tb_create() fails.
+ */
+#ifndef TIEBRUSH_B200_H_
+#define TIEBRUSH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* merge strategy: enum TMrgStrategy, src/tiebrush.cpp:82-87 */
+#define TB_MODE_CIGAR 0 /* default: same CIGAR            (cmpCigar     :306-312) */
+#define TB_MODE_FULL  1 /* -L/--full: same CIGAR and MD   (cmpFull      :285-304) */
+#define TB_MODE_CLIP  2 /* -P/--clip: CIGAR w/o end S ops (cmpCigarClip :314-332) */
+#define TB_MODE_EXON  3 /* -E/--exon: same exon chain     (cmpExons     :334-345) */
+
+/* keep_bits: struct Options, src/tiebrush.cpp:89-98 */
+#define TB_KEEP_SUPP      1 /* -S / --keep-supp      keep flag 0x800 */
+#define TB_KEEP_SECONDARY 2 /* --keep-secondary      keep flag 0x100 */
+#define TB_KEEP_UNMAP     4 /* -M / --keep-unmap     (reference aborts on real unmapped reads; rejected here) */
+#define TB_STORE_FRAC     8 /* --store-frac          YC += 1/NH (not implemented on device yet: tb_create fails) */
+
+#define TB_NO_MAX_NH 0x7fffffff /* Options.max_nh default MAX_INT */
+
+typedef struct tb_ctx tb_ctx;
+
+/* One collapse window: every record, of every input file, whose (tid,start) lies in the window.
+ * FILE-MAJOR layout: records of input file f (command-line order = sample index, tmerge.h:26
+ * `fidx`) occupy [run_off[f], run_off[f+1]) and appear in file order, i.e. coordinate-sorted by pos;
+ * the index inside the run is the record's order in its file. The device performs the k-way merge
+ * (tmerge.cpp:331-344) itself from these sorted runs.
+ * A window must hold ALL records of each (tid,start) it touches, for every file — including records
+ * the filters will drop: they still delay the records queued behind them. */
+typedef struct {
+  int64_t  n;              /* records in the window (< 2^31)                                   */
+  int32_t  n_files;        /* k                                                                */
+  int32_t  tid;            /* reference id shared by all records (bam1_core_t.tid)             */
+  const int64_t* run_off;  /* [n_files+1], HOST memory                                         */
+  const uint8_t* file_merged; /* [n_files] HOST; 1 = file made by TieBrush (tbMerged,
+                                 tmerge.cpp:69-77); NULL = none                                */
+  /* per-record arrays, length n */
+  const int32_t*  pos;     /* bam1_core_t.pos, 0-based                                         */
+  const uint16_t* flag;    /* bam1_core_t.flag                                                 */
+  const uint8_t*  mapq;    /* bam1_core_t.qual                                                 */
+  const uint8_t*  strand;  /* GSamRecord::spliceStrand() result: '+', '-' or '.' (GSam.cpp:464) */
+  const uint16_t* nh;      /* NH tag, 0 when absent, saturated at 65535 (tiebrush.cpp:537)      */
+  const uint32_t* cig_off; /* [n+1] word offsets into `cigar`; n_cigar = cig_off[i+1]-cig_off[i] */
+  const uint32_t* cigar;   /* packed BAM CIGAR words (len<<4|op), arena of cig_off[n] words      */
+  const uint32_t* md_off;  /* TB_MODE_FULL only, [n+1] byte offsets into `md`; a record with     */
+  const uint8_t*  md;      /*   md_off[i+1]==md_off[i] has NO MD tag, else bytes incl. the NUL    */
+  const uint64_t* qhash;   /* collapse_same (-A) only: 64-bit hash of QNAME, else NULL           */
+  const float*    yc_in;   /* records of merged files: YC tag as float (0 = absent); else NULL   */
+  const int32_t*  yx_in;   /*   YX tag (1 when absent)                                           */
+  const int32_t*  yd_in;   /*   YD tag (0 when absent)                                           */
+  int32_t  on_device;      /* 0: arrays above are host pointers; 1: device pointers              */
+} tb_soa_in;
+
+/* Collapsed groups of one window in FINAL OUTPUT ORDER (flushPData order, tiebrush.cpp:501-530).
+ * The caller keeps the raw records of the window, and for group g writes record rep_index[g]
+ * with tags YC:f=yc[g], YX=yx[g] and, when yd[g]>0, YD=yd[g] (else YD removed). */
+typedef struct {
+  int64_t   capacity;   /* in : entries the arrays below can hold (n is always enough)          */
+  int64_t   n_groups;   /* out: groups written (outCounter)                                      */
+  int64_t   n_kept;     /* out: records that passed the filters (inCounter, tiebrush.cpp:573)    */
+  uint32_t* rep_index;  /* out: window index of the representative record                        */
+  float*    yc;         /* out: (float)accYC — bam_aux_update_float writes type 'f'              */
+  uint32_t* yx;         /* out: popcount(samples)+accYX                                          */
+  int32_t*  yd;         /* out: max upstream bundle extent, 0 = no tag                           */
+  int32_t   on_device;  /* 0: host arrays; 1: device arrays                                      */
+} tb_groups_out;
+
+/* One coverage window: records of a coordinate-sorted (collapsed or raw) stream, unmapped records
+ * already dropped (tiecov.cpp:436-438). A window must hold whole bundles (tiecov.cpp:443). */
+typedef struct {
+  int64_t  n;
+  const int32_t*  tid;     /* non-decreasing                                                   */
+  const int32_t*  pos;     /* 0-based, non-decreasing within a tid                             */
+  const float*    yc;      /* YC tag through bam_aux2f, 1.0 when absent (tiecov.cpp:482-485)    */
+  const uint8_t*  strand;  /* spliceStrand(): '+','-','.' (only used for junctions)             */
+  const uint32_t* cig_off; /* [n+1]                                                             */
+  const uint32_t* cigar;
+  int32_t  on_device;
+} tc_soa_in;
+
+/* bedGraph runs, in file order: "chr\tstart0\tend0\t%.3f" (tiecov.cpp:226-241) */
+typedef struct {
+  int64_t  capacity;
+  int64_t  n_runs;     /* out */
+  int32_t* tid;
+  int32_t* start0;     /* 0-based inclusive */
+  int32_t* end0;       /* 0-based exclusive */
+  double*  value;
+  int32_t  on_device;
+} tc_runs_out;
+
+/* junctions in print order (tid,start,end,strand char); print as
+ * "chr\t(start-1)\tend\tJUNC%08d\t%.3f\t%c" (tiecov.cpp:91-95) */
+typedef struct {
+  int64_t  capacity;
+  int64_t  n_juncs;    /* out */
+  int32_t* tid;
+  int32_t* start;      /* exon[i-1].end+1, 1-based */
+  int32_t* end;        /* exon[i].start-1          */
+  uint8_t* strand;
+  double*  value;
+  int32_t  on_device;
+} tc_juncs_out;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+/* replaces the globals `options`, `mrgStrategy` (tiebrush.cpp:89-100). Returns NULL on failure;
+ * tb_last_error(NULL) then holds the reason. */
+tb_ctx* tb_create(int device, int n_samples, int mode, uint32_t flag_mask /* -F */,
+                  int max_nh /* -N */, int min_qual /* -Q */, int keep_bits, int collapse_same /* -A */);
+void        tb_destroy(tb_ctx*);
+const char* tb_last_error(tb_ctx*);
+
+/* Use an externally created CUDA stream (cudaStream_t passed as void*); NULL restores the context's
+ * own stream. Lets a caller time calls with its own events. */
+int   tb_set_stream(tb_ctx*, void* cuda_stream);
+void* tb_get_stream(tb_ctx*);
+int   tb_sync(tb_ctx*);
+
+/* ---- tiebrush: merge + collapse of one window --------------------------------------------- */
+/* replaces TInputFiles::next + passes_options + addPData + flushPData for the window */
+int tb_collapse_window(tb_ctx*, const tb_soa_in* in, tb_groups_out* out);
+
+/* ---- tiecov: coverage, junctions, bedgraph runs of one window ------------------------------ */
+/* replaces addCov + flushCoverage + addJunction + flushJuncs; runs / juncs may each be NULL
+ * (tiecov without -c / without -j). Returns 2 and an error naming the record for CIGAR ops the
+ * reference aborts on (tiecov.cpp:219-220). */
+int tc_coverage_window(tb_ctx*, const tc_soa_in* in, tc_runs_out* runs, tc_juncs_out* juncs);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* Kernels launched by this library since the context was created (for bench.py's gpu_launches). */
+int64_t tb_launch_count(tb_ctx*);
+/* Device time in ms of the dominant kernel of the last call, measured with CUDA events on the
+ * launching stream: which=0 collapse tile kernel, which=1 coverage accumulate kernel.
+ * Enabled by tb_set_profiling(ctx,1); costs two event records per call. */
+int   tb_set_profiling(tb_ctx*, int on);
+float tb_last_kernel_ms(tb_ctx*, int which);
+
+const char* tb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIEBRUSH_B200_H_ */
