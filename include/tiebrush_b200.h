@@ -76,6 +76,9 @@ typedef struct {
   const int32_t*  yx_in;   /*   YX tag (1 when absent)                                           */
   const int32_t*  yd_in;   /*   YD tag (0 when absent)                                           */
   int32_t  on_device;      /* 0: arrays above are host pointers; 1: device pointers              */
+  int64_t  n_cig;          /* words in `cigar` (== cig_off[n]); the packer knows it, the device need not sync */
+  int64_t  n_md;           /* bytes in `md` (== md_off[n]), 0 when unused                         */
+  int32_t  pos_lo, pos_hi; /* every record has pos in [pos_lo, pos_hi): the window the packer cut  */
 } tb_soa_in;
 
 /* Collapsed groups of one window in FINAL OUTPUT ORDER (flushPData order, tiebrush.cpp:501-530).
@@ -103,6 +106,7 @@ typedef struct {
   const uint32_t* cig_off; /* [n+1]                                                             */
   const uint32_t* cigar;
   int32_t  on_device;
+  int64_t  n_cig;          /* words in `cigar` (== cig_off[n]) */
 } tc_soa_in;
 
 /* bedGraph runs, in file order: "chr\tstart0\tend0\t%.3f" (tiecov.cpp:226-241) */

@@ -18,7 +18,8 @@ class _In(C.Structure):
                 ("file_merged", C.c_void_p), ("pos", C.c_void_p), ("flag", C.c_void_p), ("mapq", C.c_void_p),
                 ("strand", C.c_void_p), ("nh", C.c_void_p), ("cig_off", C.c_void_p), ("cigar", C.c_void_p),
                 ("md_off", C.c_void_p), ("md", C.c_void_p), ("qhash", C.c_void_p), ("yc_in", C.c_void_p),
-                ("yx_in", C.c_void_p), ("yd_in", C.c_void_p), ("on_device", C.c_int32)]
+                ("yx_in", C.c_void_p), ("yd_in", C.c_void_p), ("on_device", C.c_int32),
+                ("n_cig", C.c_int64), ("n_md", C.c_int64), ("pos_lo", C.c_int32), ("pos_hi", C.c_int32)]
 
 
 class _Out(C.Structure):
@@ -33,7 +34,7 @@ class _Opts(C.Structure):
 
 class _CovIn(C.Structure):
     _fields_ = [("n", C.c_int64), ("tid", C.c_void_p), ("pos", C.c_void_p), ("yc", C.c_void_p), ("strand", C.c_void_p),
-                ("cig_off", C.c_void_p), ("cigar", C.c_void_p), ("on_device", C.c_int32)]
+                ("cig_off", C.c_void_p), ("cigar", C.c_void_p), ("on_device", C.c_int32), ("n_cig", C.c_int64)]
 
 
 class _Runs(C.Structure):
@@ -91,7 +92,8 @@ def collapse(cols: dict, run_off, tid=0, mode=0, flag_mask=0, max_nh=0x7FFFFFFF,
     yx_in = _c(cols["yx_in"], np.int32) if (fm is not None and "yx_in" in cols) else None
     yd_in = _c(cols["yd_in"], np.int32) if (fm is not None and "yd_in" in cols) else None
     sin = _In(n, k, tid, _p(run_off), _p(fm), _p(a["pos"]), _p(a["flag"]), _p(a["mapq"]), _p(a["strand"]), _p(a["nh"]),
-              _p(a["cig_off"]), _p(a["cigar"]), _p(md_off), _p(md), _p(qh), _p(yc_in), _p(yx_in), _p(yd_in), 0)
+              _p(a["cig_off"]), _p(a["cigar"]), _p(md_off), _p(md), _p(qh), _p(yc_in), _p(yx_in), _p(yd_in), 0,
+              int(a["cig_off"][-1]) if n else 0, int(md_off[-1]) if n else 0, 0, 0)
     cap = max(n, 1)
     rep = np.zeros(cap, np.uint32); yc = np.zeros(cap, np.float32); yx = np.zeros(cap, np.uint32); yd = np.zeros(cap, np.int32)
     out = _Out(cap, 0, 0, _p(rep), _p(yc), _p(yx), _p(yd), 0)
@@ -108,7 +110,7 @@ def coverage(cols: dict, want_runs=True, want_juncs=True, cap_runs=None):
     n = len(cols["pos"])
     a = dict(tid=_c(cols["tid"], np.int32), pos=_c(cols["pos"], np.int32), yc=_c(cols["yc"], np.float32),
              strand=_c(cols["strand"], np.uint8), cig_off=_c(cols["cig_off"], np.uint32), cigar=_c(cols["cigar"], np.uint32))
-    cin = _CovIn(n, _p(a["tid"]), _p(a["pos"]), _p(a["yc"]), _p(a["strand"]), _p(a["cig_off"]), _p(a["cigar"]), 0)
+    cin = _CovIn(n, _p(a["tid"]), _p(a["pos"]), _p(a["yc"]), _p(a["strand"]), _p(a["cig_off"]), _p(a["cigar"]), 0, int(a["cig_off"][-1]) if n else 0)
     ncig = int(a["cig_off"][-1]) if n else 0
     capr = cap_runs if cap_runs is not None else 2 * ncig + 16
     capj = ncig + 16

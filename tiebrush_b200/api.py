@@ -1,0 +1,173 @@
+"""Host-side Python mirror of the hot-path interface, one level above the C ABI.
+
+`Context` plays the role of the reference's global option state (struct Options / mrgStrategy,
+src/tiebrush.cpp:89-100); `collapse_window` stands where main()'s loop calls TInputFiles::next +
+passes_options + addPData + flushPData (tiebrush.cpp:570-592) and `coverage_window` where tiecov's
+loop calls addCov / flushCoverage / addJunction / flushJuncs (tiecov.cpp:435-528).
+
+Column dicts use the tiebrush_b200.sam.to_columns layout. Values may be numpy arrays (host path:
+the library copies host<->device inside the call) or torch CUDA tensors (device-resident path)."""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+from . import _lib
+
+NO_MAX_NH = 0x7FFFFFFF
+
+
+class TieBrushError(RuntimeError):
+    pass
+
+
+def _is_torch(a):
+    return hasattr(a, "data_ptr")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+def _host(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class Context:
+    def __init__(self, device=0, n_samples=1, mode=0, flag_mask=0, max_nh=NO_MAX_NH, min_qual=-1, keep_bits=0, collapse_same=0):
+        self.lib = _lib.load()
+        self.h = self.lib.tb_create(device, n_samples, mode, flag_mask, max_nh, min_qual, keep_bits, collapse_same)
+        if not self.h:
+            raise TieBrushError(self.lib.tb_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _err(self):
+        return self.lib.tb_last_error(self.h).decode()
+
+    def set_stream(self, cuda_stream_ptr):
+        self.lib.tb_set_stream(self.h, cuda_stream_ptr)
+
+    def set_profiling(self, on=True):
+        self.lib.tb_set_profiling(self.h, int(on))
+
+    def last_kernel_ms(self, which):
+        return float(self.lib.tb_last_kernel_ms(self.h, which))
+
+    def launch_count(self):
+        return int(self.lib.tb_launch_count(self.h))
+
+    # ------------------------------------------------------------------------------------------
+    def collapse_window(self, cols, run_off, tid=0, file_merged=None, pos_range=None, out=None):
+        """One window of tiebrush. Returns dict(rep_index, yc, yx, yd, n_kept, n_groups)."""
+        dev = _is_torch(cols["pos"])
+        n = int(cols["pos"].shape[0])
+        run_off = _host(run_off, np.int64)
+        k = len(run_off) - 1
+        keep = []  # keep converted arrays alive
+
+        def col(name, dt):
+            a = cols.get(name)
+            if a is None:
+                return None
+            if not dev:
+                a = _host(a, dt)
+            keep.append(a)
+            return a
+
+        pos, flag, mapq = col("pos", np.int32), col("flag", np.uint16), col("mapq", np.uint8)
+        strand, nh = col("strand", np.uint8), col("nh", np.uint16)
+        cig_off, cigar = col("cig_off", np.uint32), col("cigar", np.uint32)
+        md_off, md = col("md_off", np.uint32), col("md", np.uint8)
+        qh = col("qhash", np.uint64)
+        fm = _host(file_merged, np.uint8) if file_merged is not None else None
+        yc_in = col("yc_in", np.float32) if fm is not None else None
+        yx_in = col("yx_in", np.int32) if fm is not None else None
+        yd_in = col("yd_in", np.int32) if fm is not None else None
+        n_cig = int(cols["n_cig"]) if "n_cig" in cols else (int(cig_off[-1]) if n else 0)
+        n_md = int(cols["n_md"]) if "n_md" in cols else (int(md_off[-1]) if (md_off is not None and n) else 0)
+        if pos_range is None:
+            if dev:
+                raise ValueError("pos_range=(lo,hi) is required for device-resident windows")
+            pos_range = (int(pos.min()), int(pos.max()) + 1) if n else (0, 0)
+        sin = _lib.SoaIn(n, k, tid, _ptr(run_off), _ptr(fm), _ptr(pos), _ptr(flag), _ptr(mapq), _ptr(strand), _ptr(nh),
+                         _ptr(cig_off), _ptr(cigar), _ptr(md_off), _ptr(md), _ptr(qh), _ptr(yc_in), _ptr(yx_in), _ptr(yd_in),
+                         1 if dev else 0, n_cig, n_md, pos_range[0], pos_range[1])
+        cap = max(n, 1)
+        if out is None:
+            if dev:
+                import torch
+                d = cols["pos"].device
+                out = dict(rep_index=torch.empty(cap, dtype=torch.int32, device=d), yc=torch.empty(cap, dtype=torch.float32, device=d),
+                           yx=torch.empty(cap, dtype=torch.int32, device=d), yd=torch.empty(cap, dtype=torch.int32, device=d))
+            else:
+                out = dict(rep_index=np.empty(cap, np.uint32), yc=np.empty(cap, np.float32), yx=np.empty(cap, np.uint32), yd=np.empty(cap, np.int32))
+        o = _lib.GroupsOut(int(out["rep_index"].shape[0]), 0, 0, _ptr(out["rep_index"]), _ptr(out["yc"]), _ptr(out["yx"]), _ptr(out["yd"]),
+                           1 if _is_torch(out["rep_index"]) else 0)
+        rc = self.lib.tb_collapse_window(self.h, C.byref(sin), C.byref(o))
+        if rc != 0:
+            raise TieBrushError(self._err())
+        g = int(o.n_groups)
+        return dict(rep_index=out["rep_index"][:g], yc=out["yc"][:g], yx=out["yx"][:g], yd=out["yd"][:g], n_kept=int(o.n_kept), n_groups=g)
+
+    # ------------------------------------------------------------------------------------------
+    def coverage_window(self, cols, want_runs=True, want_juncs=True, cap_runs=None, cap_juncs=None, out=None):
+        """One window of tiecov -c/-j. Returns dict(runs=(tid,start0,end0,value), juncs=(tid,start,end,strand,value))."""
+        dev = _is_torch(cols["pos"])
+        n = int(cols["pos"].shape[0])
+        keep = []
+
+        def col(name, dt):
+            a = cols[name]
+            if not dev:
+                a = _host(a, dt)
+            keep.append(a)
+            return a
+
+        tid, pos, yc = col("tid", np.int32), col("pos", np.int32), col("yc", np.float32)
+        strand, cig_off, cigar = col("strand", np.uint8), col("cig_off", np.uint32), col("cigar", np.uint32)
+        n_cig = int(cols["n_cig"]) if "n_cig" in cols else (int(cig_off[-1]) if n else 0)
+        cin = _lib.CovIn(n, _ptr(tid), _ptr(pos), _ptr(yc), _ptr(strand), _ptr(cig_off), _ptr(cigar), 1 if dev else 0, n_cig)
+        capr = cap_runs if cap_runs is not None else 2 * n_cig + 16
+        capj = cap_juncs if cap_juncs is not None else n_cig + 16
+        if out is None:
+            if dev:
+                import torch
+                d = cols["pos"].device
+                i32 = lambda m: torch.empty(m, dtype=torch.int32, device=d)
+                out = dict(r_tid=i32(capr), r_start=i32(capr), r_end=i32(capr), r_val=torch.empty(capr, dtype=torch.float64, device=d),
+                           j_tid=i32(capj), j_start=i32(capj), j_end=i32(capj), j_strand=torch.empty(capj, dtype=torch.uint8, device=d),
+                           j_val=torch.empty(capj, dtype=torch.float64, device=d))
+            else:
+                out = dict(r_tid=np.empty(capr, np.int32), r_start=np.empty(capr, np.int32), r_end=np.empty(capr, np.int32), r_val=np.empty(capr, np.float64),
+                           j_tid=np.empty(capj, np.int32), j_start=np.empty(capj, np.int32), j_end=np.empty(capj, np.int32),
+                           j_strand=np.empty(capj, np.uint8), j_val=np.empty(capj, np.float64))
+        odev = 1 if _is_torch(out["r_tid"]) else 0
+        runs = _lib.RunsOut(int(out["r_tid"].shape[0]), 0, _ptr(out["r_tid"]), _ptr(out["r_start"]), _ptr(out["r_end"]), _ptr(out["r_val"]), odev)
+        juncs = _lib.JuncsOut(int(out["j_tid"].shape[0]), 0, _ptr(out["j_tid"]), _ptr(out["j_start"]), _ptr(out["j_end"]), _ptr(out["j_strand"]),
+                              _ptr(out["j_val"]), odev)
+        rc = self.lib.tc_coverage_window(self.h, C.byref(cin), C.byref(runs) if want_runs else None, C.byref(juncs) if want_juncs else None)
+        if rc == 2:
+            raise ValueError(self._err())
+        if rc != 0:
+            raise TieBrushError(self._err())
+        r, j = int(runs.n_runs), int(juncs.n_juncs)
+        return dict(runs=(out["r_tid"][:r], out["r_start"][:r], out["r_end"][:r], out["r_val"][:r]),
+                    juncs=(out["j_tid"][:j], out["j_start"][:j], out["j_end"][:j], out["j_strand"][:j], out["j_val"][:j]),
+                    n_runs=r, n_juncs=j)

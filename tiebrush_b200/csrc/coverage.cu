@@ -1,0 +1,508 @@
+// coverage.cu — tiecov's hot path on the device (reference src/tiecov.cpp:62-120, 194-241, 435-528).
+//
+//   K6  bundle breaks   : prefix-max of (tid,end) over the record stream; a record opens a bundle iff its
+//                         tid differs from, or its start exceeds, the running max end   (tiecov.cpp:443)
+//   K7  coverage        : difference array over BUNDLE-COMPACTED coordinates (gaps between bundles are
+//                         skipped; one sentinel cell closes each bundle), +w at every M-block start and
+//                         -w one past its end, 64-bit fixed-point atomics                (addCov :194-223)
+//   K8  bedgraph runs   : scan of the difference array -> change points -> stream compaction of the
+//                         non-zero-depth runs; runs never join across bundles     (flushCoverage :226-241)
+//   K9  junctions       : intron (start,end,strand) keys reduced in a device hash table (fingerprint CAS,
+//                         min/max verified, so exactness never rests on the hash), then radix-sorted
+//                         into print order                                   (addJunction/flushJuncs :100-120)
+//
+// Weights: YC is float32 on disk; the reference accumulates doubles. Here every weight is
+// converted once to 2^-20 fixed point (exact for all integer-valued YC and for dyadic fractions) and
+// summed in int64, which equals the reference's double sum whenever that sum is exact.
+#include "tb_common.cuh"
+
+namespace {
+
+constexpr double COV_FX_SCALE = 1048576.0;
+
+enum {  // workspace slots in ctx->buf
+  CB_KEY = 0,     // u64 [n]   (tid<<32 | end1)
+  CB_PM,          // u64 [n]   exclusive prefix max of CB_KEY
+  CB_BID,         // u32 [n]   bundle id per record
+  CB_BSTART,      // i32 [n]   bundle start (1-based)   (indexed by bundle)
+  CB_BEND,        // i32 [n]
+  CB_BTID,        // i32 [n]
+  CB_BBASE,       // i64 [n+1] compact base offset per bundle
+  CB_AGG,         // scan aggregates (max of all uses)
+  CB_STATUS,      // i64 [16]  device status block
+  CB_DIFF,        // i64 [L]
+  CB_CPPOS,       // i64 [Kmax]
+  CB_CPDEPTH,     // i64 [Kmax]
+  CB_JTAG,        // u64 [JCAP]
+  CB_JKMIN,       // u64 [JCAP]
+  CB_JKMAX,       // u64 [JCAP]
+  CB_JTID,        // i32 [2*JCAP] (min, max)
+  CB_JVAL,        // i64 [JCAP]
+  CB_JKEYS,       // u64 [J] compacted
+  CB_JIDX,        // u32 [J]
+  CB_JKEYS2,      // u64 [J]
+  CB_JIDX2,       // u32 [J]
+  CB_RSTABLE,     // radix sort table
+  CB_RSAGG,
+  CB_TIDKEYS,     // u64 [J]
+  CB_TIDKEYS2,
+  CB_COUNT_
+};
+
+// status block layout (int64 each)
+enum { ST_ERRIDX = 0, ST_NBUNDLES, ST_DENSE_LEN, ST_NCHANGE, ST_NRUNS, ST_NJUNC, ST_JOVERFLOW, ST_JCOLLISION, ST_RUNOVERFLOW, ST_INEXACT, ST_N_ };
+
+struct CovIn {
+  int64_t n;
+  const int32_t* tid; const int32_t* pos; const float* yc; const uint8_t* strand;
+  const uint32_t* cig_off; const uint32_t* cigar;
+};
+
+// ---- K6a: per-record end coordinate + op validation ---------------------------------------------
+__global__ void __launch_bounds__(256) cov_key_kernel(CovIn in, int check_ops, unsigned long long* __restrict__ key,
+                                                      long long* __restrict__ status) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= in.n) return;
+  uint32_t c0 = in.cig_off[i], c1 = in.cig_off[i + 1];
+  int l = 0;
+  bool bad = check_ops && (c1 - c0 >= 256u);  // tiecov.cpp:198 uint8_t loop counter never terminates
+  for (uint32_t c = c0; c < c1; ++c) {
+    uint32_t w = in.cigar[c];
+    uint32_t op = w & 0xf, len = w >> 4;
+    if (op == TB_OP_M || op == TB_OP_D || op == TB_OP_N || op == TB_OP_EQ || op == TB_OP_X) l += (int)len;
+    if (check_ops && !(op == TB_OP_M || op == TB_OP_I || op == TB_OP_D || op == TB_OP_N || op == TB_OP_S)) bad = true;
+  }
+  if (bad) atomicMin((unsigned long long*)&status[ST_ERRIDX], (unsigned long long)i);
+  uint32_t end1 = (uint32_t)(in.pos[i] + l);
+  key[i] = ((unsigned long long)(uint32_t)in.tid[i] << 32) | end1;
+  float w = in.yc[i];
+  float sc = w * (float)COV_FX_SCALE;
+  if (sc != truncf(sc)) status[ST_INEXACT] = 1;  // benign race: any writer stores 1
+}
+
+struct KeyIn { const unsigned long long* k; __device__ unsigned long long operator()(int64_t i) const { return k[i]; } };
+struct PmOut { unsigned long long* pm; __device__ void operator()(int64_t i, unsigned long long exc, unsigned long long) const { pm[i] = exc; } };
+
+__device__ __forceinline__ bool cov_is_head(const CovIn& in, const unsigned long long* pm, int64_t i) {
+  if (i == 0) return true;
+  unsigned long long p = pm[i];
+  int ptid = (int)(p >> 32);
+  int pend = (int)(uint32_t)p;
+  return in.tid[i] != ptid || (in.pos[i] + 1) > pend;  // tiecov.cpp:443
+}
+
+struct HeadIn {
+  CovIn in; const unsigned long long* pm;
+  __device__ uint32_t operator()(int64_t i) const { return cov_is_head(in, pm, i) ? 1u : 0u; }
+};
+struct BundleOut {
+  CovIn in; const unsigned long long* pm; const unsigned long long* key;
+  uint32_t* bid; int32_t* bstart; int32_t* bend; int32_t* btid;
+  __device__ void operator()(int64_t i, uint32_t, uint32_t inc) const {
+    uint32_t b = inc - 1;
+    bid[i] = b;
+    if (cov_is_head(in, pm, i)) { bstart[b] = in.pos[i] + 1; btid[b] = in.tid[i]; }
+    if (i == in.n - 1 || cov_is_head(in, pm, i + 1)) {
+      int e = (int)(uint32_t)key[i];
+      unsigned long long p = pm[i];
+      if (i > 0 && (int)(p >> 32) == in.tid[i] && (int)(uint32_t)p > e) e = (int)(uint32_t)p;
+      bend[b] = e;
+    }
+  }
+};
+
+struct BLenIn {
+  const int32_t* bstart; const int32_t* bend; const long long* status;
+  __device__ long long operator()(int64_t b) const {
+    if (b >= status[ST_NBUNDLES]) return 0;
+    long long len = (long long)bend[b] - bstart[b] + 1;
+    if (len < 0) len = 0;
+    return len + 1;  // + sentinel cell one past the bundle end
+  }
+};
+struct BBaseOut { long long* base; __device__ void operator()(int64_t b, long long exc, long long) const { base[b] = exc; } };
+
+__global__ void cov_publish_kernel(const uint32_t* nb_total, const long long* len_total, long long* status) {
+  // nb_total: grand total of the head scan; written before the length scan runs
+  if (nb_total) status[ST_NBUNDLES] = *nb_total;
+  if (len_total) status[ST_DENSE_LEN] = *len_total;
+}
+
+// ---- K7 + K9 insert: one thread per record walks its CIGAR ----------------------------------------
+struct JTable {
+  unsigned long long* tag; unsigned long long* kmin; unsigned long long* kmax; int32_t* tmin; int32_t* tmax; long long* val;
+  uint32_t mask; uint64_t seed;
+};
+
+__device__ __forceinline__ void junc_insert(const JTable& jt, int tid, unsigned long long k64, long long w, long long* status) {
+  unsigned long long tag = tb_mix64(k64 ^ tb_mix64((unsigned long long)(uint32_t)tid + jt.seed));
+  if (tag == 0) tag = 1;
+  uint32_t s = (uint32_t)(tag >> 20) & jt.mask;
+  for (uint32_t probe = 0; probe <= jt.mask; ++probe) {
+    unsigned long long old = atomicCAS(&jt.tag[s], 0ULL, tag);
+    if (old == 0ULL || old == tag) {
+      if (old == 0ULL) atomicAdd((unsigned long long*)&status[ST_NJUNC], 1ULL);
+      atomicAdd((unsigned long long*)&jt.val[s], (unsigned long long)w);
+      atomicMin(&jt.kmin[s], k64); atomicMax(&jt.kmax[s], k64);
+      atomicMin(&jt.tmin[s], tid); atomicMax(&jt.tmax[s], tid);
+      return;
+    }
+    s = (s + 1) & jt.mask;
+  }
+  status[ST_JOVERFLOW] = 1;
+}
+
+__device__ __forceinline__ unsigned strand_code(uint8_t c) { return c == '+' ? 0u : (c == '-' ? 1u : 2u); }  // '+' < '-' < '.'
+__device__ __forceinline__ uint8_t strand_char(unsigned c) { return c == 0 ? '+' : (c == 1 ? '-' : '.'); }
+
+__global__ void __launch_bounds__(256) cov_accumulate_kernel(CovIn in, const uint32_t* __restrict__ bid, const int32_t* __restrict__ bstart,
+                                                             const long long* __restrict__ bbase, long long* __restrict__ diff,
+                                                             int do_cov, int do_junc, JTable jt, long long* __restrict__ status) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= in.n) return;
+  uint32_t c0 = in.cig_off[i], c1 = in.cig_off[i + 1];
+  int pos = in.pos[i];
+  long long w = (long long)rintf(in.yc[i] * (float)COV_FX_SCALE);
+  uint32_t b = bid[i];
+  long long shift = bbase[b] - (long long)bstart[b];  // compact index of 1-based coordinate x is x + shift
+  int tid = in.tid[i];
+  unsigned sc = strand_code(in.strand[i]);
+  // setupCoordinates state (GSam.cpp:351-417) for the junctions
+  int l = 0, exstart = pos, nclosed = 0, last_end = 0;
+  bool intron = false, ins = false;
+  for (uint32_t c = c0; c < c1; ++c) {
+    uint32_t cw = in.cigar[c];
+    uint32_t op = cw & 0xf; int len = (int)(cw >> 4);
+    switch (op) {
+      case TB_OP_M:
+        if (do_cov && len > 0) {
+          long long ci = (long long)(pos + l + 1) + shift;
+          atomicAdd((unsigned long long*)&diff[ci], (unsigned long long)w);
+          atomicAdd((unsigned long long*)&diff[ci + len], (unsigned long long)(-w));
+        }
+        l += len; intron = false; ins = false; break;
+      case TB_OP_EQ: case TB_OP_X: case TB_OP_D:
+        l += len; intron = false; ins = false; break;
+      case TB_OP_N:
+        if (!ins || !intron) {
+          if (do_junc && nclosed > 0) {
+            unsigned long long k64 = ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc;
+            junc_insert(jt, tid, k64, w, status);
+          }
+          last_end = pos + l; nclosed++;
+        }
+        l += len; exstart = pos + l; intron = true; break;
+      case TB_OP_S: case TB_OP_H:
+        intron = false; ins = false; break;
+      case TB_OP_I:
+        ins = true; break;
+      default: break;
+    }
+  }
+  if (do_junc && nclosed > 0) {
+    unsigned long long k64 = ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc;
+    junc_insert(jt, tid, k64, w, status);
+  }
+}
+
+// ---- K8: change points and runs --------------------------------------------------------------------
+struct SumNz { long long sum; long long nz; };
+struct OpSumNz {
+  typedef SumNz T;
+  __host__ __device__ static T identity() { return SumNz{0, 0}; }
+  __host__ __device__ static T combine(T a, T b) { return SumNz{a.sum + b.sum, a.nz + b.nz}; }
+};
+struct DiffIn {
+  const long long* d;
+  __device__ SumNz operator()(int64_t i) const { long long v = d[i]; return SumNz{v, v != 0 ? 1 : 0}; }
+};
+struct ChangeOut {
+  const long long* d; long long* cppos; long long* cpdepth;
+  __device__ void operator()(int64_t i, SumNz exc, SumNz inc) const {
+    if (inc.nz != exc.nz) { cppos[exc.nz] = i; cpdepth[exc.nz] = inc.sum; }
+  }
+};
+
+struct RunValidIn {
+  const long long* cpdepth; const long long* status;
+  __device__ uint32_t operator()(int64_t k) const {
+    long long K = status[ST_NCHANGE];
+    return (k + 1 < K && cpdepth[k] != 0) ? 1u : 0u;
+  }
+};
+struct RunOut {
+  const long long* cppos; const long long* cpdepth; long long* status;
+  const long long* bbase; const int32_t* bstart; const int32_t* btid;
+  int32_t* o_tid; int32_t* o_start; int32_t* o_end; double* o_val; long long capacity;
+  __device__ void operator()(int64_t k, uint32_t exc, uint32_t inc) const {
+    if (inc == exc) return;
+    if ((long long)exc >= capacity) { status[ST_RUNOVERFLOW] = 1; return; }
+    long long c = cppos[k], c2 = cppos[k + 1];
+    long long B = status[ST_NBUNDLES];
+    long long lo = 0, hi = B;  // last bundle with base <= c
+    while (hi - lo > 1) { long long m = (lo + hi) >> 1; if (bbase[m] <= c) lo = m; else hi = m; }
+    long long off = (long long)bstart[lo] - 1 - bbase[lo];
+    o_tid[exc] = btid[lo];
+    o_start[exc] = (int32_t)(c + off);
+    o_end[exc] = (int32_t)(c2 + off);
+    o_val[exc] = (double)cpdepth[k] / COV_FX_SCALE;
+  }
+};
+
+__global__ void cov_store_total_kernel(const SumNz* tot, const uint32_t* nruns, long long* status) {
+  if (tot) status[ST_NCHANGE] = tot->nz;
+  if (nruns) status[ST_NRUNS] = *nruns;
+}
+
+// ---- K9 extraction ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) junc_init_kernel(JTable jt, uint32_t cap) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cap) return;
+  jt.tag[s] = 0; jt.kmin[s] = ~0ULL; jt.kmax[s] = 0; jt.tmin[s] = 0x7fffffff; jt.tmax[s] = -0x7fffffff - 1; jt.val[s] = 0;
+}
+
+__global__ void __launch_bounds__(256) junc_compact_kernel(JTable jt, uint32_t cap, unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx,
+                                                           unsigned long long* __restrict__ counter, long long* __restrict__ status) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cap) return;
+  if (jt.tag[s] == 0) return;
+  if (jt.kmin[s] != jt.kmax[s] || jt.tmin[s] != jt.tmax[s]) status[ST_JCOLLISION] = 1;
+  unsigned long long k = atomicAdd(counter, 1ULL);
+  keys[k] = jt.kmin[s];
+  idx[k] = s;
+}
+
+__global__ void __launch_bounds__(256) junc_tidkey_kernel(JTable jt, const uint32_t* __restrict__ idx, int64_t J, unsigned long long* __restrict__ tkeys) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= J) return;
+  tkeys[k] = (unsigned long long)(uint32_t)jt.tmin[idx[k]];
+}
+
+__global__ void __launch_bounds__(256) junc_emit_kernel(JTable jt, const uint32_t* __restrict__ idx, int64_t J, int32_t* o_tid, int32_t* o_start,
+                                                        int32_t* o_end, uint8_t* o_strand, double* o_val) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= J) return;
+  uint32_t s = idx[k];
+  unsigned long long key = jt.kmin[s];
+  o_tid[k] = jt.tmin[s];
+  o_start[k] = (int32_t)(key >> 33);
+  o_end[k] = (int32_t)((key >> 2) & 0x7fffffffULL);
+  o_strand[k] = strand_char((unsigned)(key & 3));
+  o_val[k] = (double)jt.val[s] / COV_FX_SCALE;
+}
+
+static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+template <class T>
+static int stage_in(tb_ctx* ctx, DevBuf& b, const T* src, size_t count, int on_device, const T** out) {
+  if (on_device || src == nullptr) { *out = src; return 0; }
+  TB_CUDA(b.ensure(count * sizeof(T) + 16));
+  TB_CUDA(cudaMemcpyAsync(b.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *out = (const T*)b.p;
+  return 0;
+}
+
+}  // namespace
+
+int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_juncs_out* juncs) {
+  TB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = hin->n;
+  if (runs) runs->n_runs = 0;
+  if (juncs) juncs->n_juncs = 0;
+  if (n == 0) return 0;
+  if (n >= (1LL << 31)) { ctx->set_error("tc_coverage_window: n=%lld too large for one window", (long long)n); return 1; }
+  const int do_cov = runs != nullptr, do_junc = juncs != nullptr;
+  cudaStream_t st = ctx->stream;
+
+  // ---- inputs on the device ----
+  CovIn in; in.n = n;
+  int64_t ncig = hin->n_cig;
+  if (stage_in(ctx, ctx->in_stage[0], hin->tid, (size_t)n, hin->on_device, &in.tid)) return 1;
+  if (stage_in(ctx, ctx->in_stage[1], hin->pos, (size_t)n, hin->on_device, &in.pos)) return 1;
+  if (stage_in(ctx, ctx->in_stage[2], hin->yc, (size_t)n, hin->on_device, &in.yc)) return 1;
+  if (stage_in(ctx, ctx->in_stage[3], hin->strand, (size_t)n, hin->on_device, &in.strand)) return 1;
+  if (stage_in(ctx, ctx->in_stage[4], hin->cig_off, (size_t)n + 1, hin->on_device, &in.cig_off)) return 1;
+  if (stage_in(ctx, ctx->in_stage[5], hin->cigar, (size_t)ncig, hin->on_device, &in.cigar)) return 1;
+
+  DevBuf* B = ctx->buf;
+  TB_CUDA(B[CB_KEY].ensure(sizeof(uint64_t) * n));
+  TB_CUDA(B[CB_PM].ensure(sizeof(uint64_t) * n));
+  TB_CUDA(B[CB_BID].ensure(sizeof(uint32_t) * n));
+  TB_CUDA(B[CB_BSTART].ensure(sizeof(int32_t) * n));
+  TB_CUDA(B[CB_BEND].ensure(sizeof(int32_t) * n));
+  TB_CUDA(B[CB_BTID].ensure(sizeof(int32_t) * n));
+  TB_CUDA(B[CB_BBASE].ensure(sizeof(int64_t) * (n + 1)));
+  TB_CUDA(B[CB_STATUS].ensure(sizeof(int64_t) * 16));
+  TB_CUDA(ctx->pinned[0].ensure(sizeof(int64_t) * 16));
+  long long* d_status = B[CB_STATUS].as<long long>();
+  long long* h_status = ctx->pinned[0].as<long long>();
+  {
+    long long init[16]; memset(init, 0, sizeof(init)); init[ST_ERRIDX] = -1;  // as u64: max
+    memcpy(h_status, init, sizeof(init));
+    TB_CUDA(cudaMemcpyAsync(d_status, h_status, sizeof(init), cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaStreamSynchronize(st));  // h_status is reused for readback below
+  }
+  unsigned long long* d_key = B[CB_KEY].as<unsigned long long>();
+  unsigned long long* d_pm = B[CB_PM].as<unsigned long long>();
+
+  // ---- K6 ----
+  cov_key_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, do_cov, d_key, d_status);
+  ctx->launches++;
+  size_t agg_bytes = (size_t)(tb_scan_blocks(n > 2 * ncig + 16 ? n : 2 * ncig + 16) + 8) * sizeof(SumNz);
+  TB_CUDA(B[CB_AGG].ensure(agg_bytes));
+  TB_CUDA((tb_device_scan<OpMaxU64>(ctx, KeyIn{d_key}, n, B[CB_AGG].as<unsigned long long>(), PmOut{d_pm})));
+  BundleOut bo{in, d_pm, d_key, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>()};
+  TB_CUDA((tb_device_scan<OpSumU32>(ctx, HeadIn{in, d_pm}, n, B[CB_AGG].as<uint32_t>(), bo)));
+  cov_publish_kernel<<<1, 1, 0, st>>>(B[CB_AGG].as<uint32_t>() + tb_scan_blocks(n), nullptr, d_status);
+  ctx->launches++;
+  TB_CUDA((tb_device_scan<OpSumI64>(ctx, BLenIn{B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(), d_status}, n,
+                                    B[CB_AGG].as<long long>(), BBaseOut{B[CB_BBASE].as<long long>()})));
+  cov_publish_kernel<<<1, 1, 0, st>>>(nullptr, B[CB_AGG].as<long long>() + tb_scan_blocks(n), d_status);
+  ctx->launches++;
+  TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  if (h_status[ST_ERRIDX] != -1) {
+    ctx->set_error("ERROR: unknown opcode in CIGAR of record %lld (tiecov supports only M,I,D,N,S; n_cigar<256)", h_status[ST_ERRIDX]);
+    return 2;
+  }
+  const int64_t L = h_status[ST_DENSE_LEN];
+  {
+    int64_t m = L > n ? L : n; if (2 * ncig + 16 > m) m = 2 * ncig + 16;
+    TB_CUDA(B[CB_AGG].ensure((size_t)(tb_scan_blocks(m) + 8) * sizeof(SumNz)));
+  }
+
+  // ---- junction table ----
+  JTable jt; memset(&jt, 0, sizeof(jt));
+  uint32_t jcap = 1024;
+  if (do_junc) {
+    int64_t want = 2 * ncig; if (want > (1 << 22)) want = 1 << 22;
+    while ((int64_t)jcap < want) jcap <<= 1;
+  }
+  uint64_t seed = 0x9e3779b97f4a7c15ULL;
+  for (int attempt = 0;; ++attempt) {
+    if (do_junc) {
+      TB_CUDA(B[CB_JTAG].ensure(sizeof(uint64_t) * jcap));
+      TB_CUDA(B[CB_JKMIN].ensure(sizeof(uint64_t) * jcap));
+      TB_CUDA(B[CB_JKMAX].ensure(sizeof(uint64_t) * jcap));
+      TB_CUDA(B[CB_JTID].ensure(sizeof(int32_t) * 2 * jcap));
+      TB_CUDA(B[CB_JVAL].ensure(sizeof(int64_t) * jcap));
+      jt.tag = B[CB_JTAG].as<unsigned long long>(); jt.kmin = B[CB_JKMIN].as<unsigned long long>(); jt.kmax = B[CB_JKMAX].as<unsigned long long>();
+      jt.tmin = B[CB_JTID].as<int32_t>(); jt.tmax = jt.tmin + jcap; jt.val = B[CB_JVAL].as<long long>();
+      jt.mask = jcap - 1; jt.seed = seed;
+      junc_init_kernel<<<grid_for(jcap, 256), 256, 0, st>>>(jt, jcap);
+      ctx->launches++;
+    }
+    if (do_cov) {
+      TB_CUDA(B[CB_DIFF].ensure(sizeof(int64_t) * (L + 1)));
+      TB_CUDA(cudaMemsetAsync(B[CB_DIFF].p, 0, sizeof(int64_t) * (L + 1), st));
+    }
+    // ---- K7 (+K9 insert): the dominant kernel ----
+    if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
+    cov_accumulate_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(), B[CB_BBASE].as<long long>(),
+                                                           B[CB_DIFF].as<long long>(), do_cov, do_junc, jt, d_status);
+    ctx->launches++;
+    if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[1], st));
+    if (!do_junc) break;
+    TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    bool overflow = h_status[ST_JOVERFLOW] != 0 || h_status[ST_NJUNC] * 2 > (int64_t)jcap;
+    if (!overflow) break;
+    if (attempt > 8 || jcap >= (1u << 30)) { ctx->set_error("junction table overflow (%lld distinct junctions)", h_status[ST_NJUNC]); return 1; }
+    jcap <<= 2;
+    h_status[ST_JOVERFLOW] = 0; h_status[ST_NJUNC] = 0;
+    TB_CUDA(cudaMemcpyAsync(d_status, h_status, sizeof(int64_t) * 16, cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+  }
+
+  // ---- K8 ----
+  int64_t kmax = 2 * ncig + 16;
+  if (do_cov) {
+    TB_CUDA(B[CB_CPPOS].ensure(sizeof(int64_t) * kmax));
+    TB_CUDA(B[CB_CPDEPTH].ensure(sizeof(int64_t) * kmax));
+    long long* d_diff = B[CB_DIFF].as<long long>();
+    long long* cppos = B[CB_CPPOS].as<long long>();
+    long long* cpdepth = B[CB_CPDEPTH].as<long long>();
+    TB_CUDA((tb_device_scan<OpSumNz>(ctx, DiffIn{d_diff}, L, B[CB_AGG].as<SumNz>(), ChangeOut{d_diff, cppos, cpdepth})));
+    cov_store_total_kernel<<<1, 1, 0, st>>>(B[CB_AGG].as<SumNz>() + tb_scan_blocks(L), nullptr, d_status);
+    ctx->launches++;
+    // output staging
+    int64_t cap = runs->capacity;
+    int32_t *o_tid = runs->tid, *o_start = runs->start0, *o_end = runs->end0; double* o_val = runs->value;
+    int64_t stage_cap = cap < kmax ? cap : kmax;
+    if (!runs->on_device) {
+      TB_CUDA(ctx->out_stage[0].ensure(sizeof(int32_t) * stage_cap)); TB_CUDA(ctx->out_stage[1].ensure(sizeof(int32_t) * stage_cap));
+      TB_CUDA(ctx->out_stage[2].ensure(sizeof(int32_t) * stage_cap)); TB_CUDA(ctx->out_stage[3].ensure(sizeof(double) * stage_cap));
+      o_tid = ctx->out_stage[0].as<int32_t>(); o_start = ctx->out_stage[1].as<int32_t>(); o_end = ctx->out_stage[2].as<int32_t>();
+      o_val = ctx->out_stage[3].as<double>();
+    }
+    RunOut ro{cppos, cpdepth, d_status, B[CB_BBASE].as<long long>(), B[CB_BSTART].as<int32_t>(), B[CB_BTID].as<int32_t>(),
+              o_tid, o_start, o_end, o_val, stage_cap};
+    // the number of change points is only known on the device: scan the upper bound, functor masks the tail
+    TB_CUDA((tb_device_scan<OpSumU32>(ctx, RunValidIn{cpdepth, d_status}, kmax, B[CB_AGG].as<uint32_t>(), ro)));
+    cov_store_total_kernel<<<1, 1, 0, st>>>(nullptr, B[CB_AGG].as<uint32_t>() + tb_scan_blocks(kmax), d_status);
+    ctx->launches++;
+  }
+  TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  if (ctx->profiling) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_ms[1] = ms; }
+  if (do_cov) {
+    if (h_status[ST_RUNOVERFLOW] || h_status[ST_NRUNS] > runs->capacity) {
+      ctx->set_error("tc_coverage_window: runs capacity %lld too small (%lld runs)", (long long)runs->capacity, h_status[ST_NRUNS]);
+      return 1;
+    }
+    runs->n_runs = h_status[ST_NRUNS];
+    if (!runs->on_device && runs->n_runs > 0) {
+      size_t r = (size_t)runs->n_runs;
+      TB_CUDA(cudaMemcpyAsync(runs->tid, ctx->out_stage[0].p, sizeof(int32_t) * r, cudaMemcpyDeviceToHost, st));
+      TB_CUDA(cudaMemcpyAsync(runs->start0, ctx->out_stage[1].p, sizeof(int32_t) * r, cudaMemcpyDeviceToHost, st));
+      TB_CUDA(cudaMemcpyAsync(runs->end0, ctx->out_stage[2].p, sizeof(int32_t) * r, cudaMemcpyDeviceToHost, st));
+      TB_CUDA(cudaMemcpyAsync(runs->value, ctx->out_stage[3].p, sizeof(double) * r, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  // ---- K9 extraction: compact, verify, sort (start,end,strand) then stable by tid ----
+  if (do_junc) {
+    int64_t J = h_status[ST_NJUNC];
+    if (J > juncs->capacity) { ctx->set_error("tc_coverage_window: junction capacity %lld too small (%lld)", (long long)juncs->capacity, (long long)J); return 1; }
+    if (J > 0) {
+      TB_CUDA(B[CB_JKEYS].ensure(sizeof(uint64_t) * J)); TB_CUDA(B[CB_JKEYS2].ensure(sizeof(uint64_t) * J));
+      TB_CUDA(B[CB_JIDX].ensure(sizeof(uint32_t) * J)); TB_CUDA(B[CB_JIDX2].ensure(sizeof(uint32_t) * J));
+      TB_CUDA(B[CB_TIDKEYS].ensure(sizeof(uint64_t) * J)); TB_CUDA(B[CB_TIDKEYS2].ensure(sizeof(uint64_t) * J));
+      TB_CUDA(B[CB_RSTABLE].ensure(sizeof(uint32_t) * tb_radix_table_elems(J)));
+      TB_CUDA(B[CB_RSAGG].ensure(sizeof(uint32_t) * tb_radix_agg_elems(J)));
+      unsigned long long* counter = (unsigned long long*)(d_status + ST_N_);
+      TB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+      junc_compact_kernel<<<grid_for(jcap, 256), 256, 0, st>>>(jt, jcap, B[CB_JKEYS].as<unsigned long long>(), B[CB_JIDX].as<uint32_t>(), counter, d_status);
+      ctx->launches++;
+      uint64_t* rk; uint32_t* rv;
+      TB_CUDA(tb_radix_sort(ctx, B[CB_JKEYS].as<uint64_t>(), B[CB_JIDX].as<uint32_t>(), B[CB_JKEYS2].as<uint64_t>(), B[CB_JIDX2].as<uint32_t>(), J, 0, 64,
+                            B[CB_RSTABLE].as<uint32_t>(), B[CB_RSAGG].as<uint32_t>(), &rk, &rv));
+      // stable second sort by tid (31 significant bits)
+      uint32_t* other_v = (rv == B[CB_JIDX].as<uint32_t>()) ? B[CB_JIDX2].as<uint32_t>() : B[CB_JIDX].as<uint32_t>();
+      junc_tidkey_kernel<<<grid_for(J, 256), 256, 0, st>>>(jt, rv, J, B[CB_TIDKEYS].as<unsigned long long>());
+      ctx->launches++;
+      uint64_t* rk2; uint32_t* rv2;
+      TB_CUDA(tb_radix_sort(ctx, B[CB_TIDKEYS].as<uint64_t>(), rv, B[CB_TIDKEYS2].as<uint64_t>(), other_v, J, 0, 32,
+                            B[CB_RSTABLE].as<uint32_t>(), B[CB_RSAGG].as<uint32_t>(), &rk2, &rv2));
+      int32_t *o_tid = juncs->tid, *o_start = juncs->start, *o_end = juncs->end; uint8_t* o_strand = juncs->strand; double* o_val = juncs->value;
+      if (!juncs->on_device) {
+        TB_CUDA(ctx->out_stage[4].ensure(sizeof(int32_t) * 3 * J)); TB_CUDA(ctx->out_stage[5].ensure(J)); TB_CUDA(ctx->out_stage[6].ensure(sizeof(double) * J));
+        o_tid = ctx->out_stage[4].as<int32_t>(); o_start = o_tid + J; o_end = o_start + J; o_strand = ctx->out_stage[5].as<uint8_t>(); o_val = ctx->out_stage[6].as<double>();
+      }
+      junc_emit_kernel<<<grid_for(J, 256), 256, 0, st>>>(jt, rv2, J, o_tid, o_start, o_end, o_strand, o_val);
+      ctx->launches++;
+      if (!juncs->on_device) {
+        TB_CUDA(cudaMemcpyAsync(juncs->tid, o_tid, sizeof(int32_t) * J, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(cudaMemcpyAsync(juncs->start, o_start, sizeof(int32_t) * J, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(cudaMemcpyAsync(juncs->end, o_end, sizeof(int32_t) * J, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(cudaMemcpyAsync(juncs->strand, o_strand, (size_t)J, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(cudaMemcpyAsync(juncs->value, o_val, sizeof(double) * J, cudaMemcpyDeviceToHost, st));
+      }
+      TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
+    }
+    TB_CUDA(cudaStreamSynchronize(st));
+    if (h_status[ST_JCOLLISION]) { ctx->set_error("junction fingerprint collision (retry with another seed not implemented)"); return 1; }
+    juncs->n_juncs = J;
+  }
+  TB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
