@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the tiebrush merge+collapse hot path (and tiecov coverage) on B200.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` (N>1 under torch.distributed.run, one rank per
+GPU) prints ONE JSON line from rank 0. A step = one pass of the hot path over one synthetic cohort window
+(BASELINE.json configs[1]: 100 RNA-seq samples x 10 M spliced 150-bp reads on chr1, default CIGAR mode)
+with the inputs resident in HBM; `e2e` is the same call through the C ABI with HOST (pinned) buffers, the
+host->device and device->host copies inside the timed region. `--impl reference` times the unmodified
+reference binary (oracle/_ref/tiebrush, single-threaded as shipped) on a bounded sample of the same cohort.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=int, default=int(os.environ.get("TB_BENCH_SAMPLES", 100)))
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("TB_BENCH_READS", 10_000_000)), help="reads per sample")
+    ap.add_argument("--mode", type=int, default=0)
+    ap.add_argument("--cov-records", type=int, default=int(os.environ.get("TB_BENCH_COV", 100_000_000)),
+                    help="records of the secondary tiecov leg (0 = skip)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("TB_BENCH_CPU_SAMPLE", 20_000_000)),
+                    help="records of the cohort fed to the CPU baseline (bounded sample)")
+    ap.add_argument("--ref-reads", type=int, default=int(os.environ.get("TB_BENCH_REF_READS", 20_000)),
+                    help="--impl reference: reads per sample file written as SAM for the reference binary")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_slice_sample(host, run_off, target):
+    """A coordinate slice [lo,hi) of the window holding ~target records: all files, whole positions."""
+    n = len(host["pos"])
+    if target >= n:
+        return host, run_off
+    # pick the cut from the first run's quantile, then slice every run by coordinate
+    frac = target / n
+    r0 = host["pos"][run_off[0]:run_off[1]]
+    hi = int(r0[min(len(r0) - 1, int(len(r0) * frac))])
+    from tiebrush_b200 import sam
+    idx, new_off = [], [0]
+    for f in range(len(run_off) - 1):
+        a, b = int(run_off[f]), int(run_off[f + 1])
+        c = a + int(np.searchsorted(host["pos"][a:b], hi, side="left"))
+        idx.append(np.arange(a, c, dtype=np.int64))
+        new_off.append(new_off[-1] + (c - a))
+    idx = np.concatenate(idx)
+    sub = {k: host[k][idx] for k in ("pos", "flag", "mapq", "strand", "nh")}
+    sub["cig_off"], sub["cigar"] = sam._gather_csr(host["cig_off"], host["cigar"], idx)
+    return sub, np.asarray(new_off, np.int64)
+
+
+def write_sam_files(host, run_off, tmpdir):
+    """Materialise a (small) window as one SAM file per sample for the reference binary."""
+    from tiebrush_b200 import sam
+    paths = []
+    hdr = "@HD\tVN:1.0\tSO:coordinate\n@SQ\tSN:chr1\tLN:248956422\n"
+    for f in range(len(run_off) - 1):
+        a, b = int(run_off[f]), int(run_off[f + 1])
+        lines = [hdr]
+        for i in range(a, b):
+            cig = sam.cigar_str(host["cigar"][host["cig_off"][i]:host["cig_off"][i + 1]])
+            tags = f"NH:i:{int(host['nh'][i])}"
+            s = chr(int(host["strand"][i]))
+            if s != ".":
+                tags += f"\tXS:A:{s}"
+            lines.append(f"s{f}.{i}\t{int(host['flag'][i])}\tchr1\t{int(host['pos'][i]) + 1}\t{int(host['mapq'][i])}\t{cig}\t*\t0\t0\t*\t*\t{tags}\n")
+        p = os.path.join(tmpdir, f"s{f}.sam")
+        with open(p, "w") as fh:
+            fh.write("".join(lines))
+        paths.append(p)
+    return paths
+
+
+def run_reference_arm(args):
+    """Times the UNMODIFIED reference binary (single-threaded, as shipped) on a bounded sample: K steps of
+    `tiebrush -o out.bam s0.sam ... s{k-1}.sam`, wall clock around the process."""
+    from tiebrush_b200 import synth
+    ref = os.path.join(ROOT, "oracle", "_ref", "tiebrush")
+    line = {"impl": "reference", "metric": "alignments_collapsed_per_sec", "unit": "alignments/s", "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "dtype": "u32", "data": "synthetic", "scaling": "weak",
+            "vs_baseline": None}
+    if not os.path.exists(ref):
+        line["unavailable"] = "oracle/_ref/tiebrush not built (needs /root/reference at build time)"
+        print(json.dumps(line)); return
+    cols, run_off, _ = synth.cohort_window(args.samples, args.ref_reads, seed=0, device="cpu")
+    host = synth.to_host(cols)
+    n = len(host["pos"])
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = write_sam_files(host, run_off, tmp)
+        times = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            r = subprocess.run([ref, "-o", os.path.join(tmp, "o.bam")] + paths, capture_output=True, text=True)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                line["unavailable"] = "reference binary failed: " + r.stderr[:200]
+                print(json.dumps(line)); return
+            if it >= args.warmup:
+                times.append(dt)
+    ms = 1000.0 * float(np.mean(times))
+    v = n / (ms / 1000.0)
+    line.update({"value": v, "ms_per_step": ms,
+                 "config": {"workload": f"C2 cohort model (100 samples x 10M reads chr1, default mode); bounded sample: {args.samples} SAM files x {args.ref_reads} reads",
+                            "records_per_step": n},
+                 "cpu_baseline": {"value": v, "unit": "alignments/s", "cores": 1, "kind": "reference",
+                                  "sample": f"{args.samples} files x {args.ref_reads} reads of the C2 cohort model as SAM text, reference tiebrush -O2, 1 thread (the reference is single-threaded)"},
+                 "e2e": {"value": v, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from tiebrush_b200 import api, synth
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    k, reads = args.samples, args.reads
+    n = k * reads
+    # ---- synthetic cohort straight into HBM; rank r owns an independent coordinate shard (weak scaling) ----
+    t_gen = time.perf_counter()
+    cols, run_off, pr = synth.cohort_window(k, reads, seed=rank, device=dev)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    n_cig = cols["n_cig"]
+    stream = torch.cuda.Stream(device=dev)
+    ctx = api.Context(device=local, n_samples=k, mode=args.mode)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_profiling(True)
+    out = dict(rep_index=torch.empty(n, dtype=torch.int32, device=dev), yc=torch.empty(n, dtype=torch.float32, device=dev),
+               yx=torch.empty(n, dtype=torch.int32, device=dev), yd=torch.empty(n, dtype=torch.int32, device=dev))
+
+    def step_dev():
+        return ctx.collapse_window(cols, run_off, pos_range=pr, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res = step_dev()
+    G = res["n_groups"] if args.warmup else 0
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            res = step_dev()
+            kms.append(ctx.last_kernel_ms(0))
+        e1.record(stream)
+    barrier()
+    launches = ctx.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    G = res["n_groups"]
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * n / (ms_step / 1000.0)
+    clocks = sampler
+    # ---- roofline of the dominant kernel (collapse tile kernel) ----
+    peak, peak_src = peaks()
+    cbar = n_cig / n
+    a_col = n * (30 + 4 * cbar) + 12 * G            # SURVEY §8d algorithmic bytes (default mode: m = 0)
+    kernel_ms = float(np.mean(kms))
+    achieved = a_col / (kernel_ms / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": "col_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms, "algorithmic_bytes": a_col,
+                "layout_bytes": n * (14 + 4 * cbar) + 16 * G}
+    line = {"metric": "alignments_collapsed_per_sec", "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"C2: {k} RNA-seq samples x {reads} spliced 150bp reads on chr1, tiebrush mode {args.mode} (0=default CIGAR), one window per GPU",
+                       "records_per_step_per_gpu": n, "groups_out": G, "mean_cigar_ops": cbar, "l2": "inputs (>=20 GB at full size) exceed the 126 MB L2; no flush needed",
+                       "parallelism": f"coordinate shards x{world}, no data-path collective", "gen_seconds": t_gen},
+            "roofline": roofline, "gpu_launches": int(launches)}
+
+    # ---- tiecov leg (secondary): coverage + junctions + bedgraph runs on a collapsed-like stream ----
+    if args.cov_records > 0:
+        cov = synth.coverage_stream(args.cov_records, seed=rank, chroms=1, device=dev)
+        ncov = args.cov_records
+        ocov = None
+        for _ in range(max(1, args.warmup)):
+            r = ctx.coverage_window(cov) if ocov is None else ctx.coverage_window(cov, out=ocov)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cms = []
+        barrier()
+        with torch.cuda.stream(stream):
+            c0.record(stream)
+            for _ in range(args.steps):
+                r = ctx.coverage_window(cov)
+                cms.append(ctx.last_kernel_ms(1))
+            c1.record(stream)
+        barrier()
+        cov_ms = c0.elapsed_time(c1) / args.steps
+        host_cov = None
+        mbases = float(synth.m_bases(cov))
+        a_cov = ncov * (19 + 4 * cov["n_cig"] / ncov) + 16 * r["n_runs"] + 16 * r["n_juncs"]
+        line["tiecov"] = {"metric": "coverage_bases_per_sec", "value": world * mbases / (cov_ms / 1000.0), "unit": "bases/s",
+                          "records_per_sec": world * ncov / (cov_ms / 1000.0), "ms_per_step": cov_ms, "records": ncov, "runs": r["n_runs"], "juncs": r["n_juncs"],
+                          "roofline": {"bound": "hbm", "kernel": "cov_accumulate_kernel", "achieved": a_cov / (np.mean(cms) / 1000.0) / 1e9, "peak": peak,
+                                       "unit": "GB/s", "frac": a_cov / (np.mean(cms) / 1000.0) / 1e9 / peak, "kernel_ms": float(np.mean(cms)), "traffic": None}}
+        del cov
+
+    # ---- end to end through the C ABI with host buffers ----
+    if not args.no_e2e:
+        host = {}
+        h2d = 0
+        for name in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar"):
+            t = cols[name]
+            ht = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            ht.copy_(t)
+            host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32, "flag": np.uint16, "nh": np.uint16}.get(name, ht.numpy().dtype))
+            h2d += ht.numel() * ht.element_size()
+        host["n_cig"] = n_cig
+        cap = max(G + 1024, 1)
+        hout_t = dict(rep_index=torch.empty(cap, dtype=torch.int32, pin_memory=True), yc=torch.empty(cap, dtype=torch.float32, pin_memory=True),
+                      yx=torch.empty(cap, dtype=torch.int32, pin_memory=True), yd=torch.empty(cap, dtype=torch.int32, pin_memory=True))
+        hout = {kk: v.numpy().view(np.uint32) if kk in ("rep_index", "yx") else v.numpy() for kk, v in hout_t.items()}
+        es = max(1, min(args.steps, 3))
+        ctx.collapse_window(host, run_off, pos_range=pr, out=hout)  # warm the staging buffers
+        barrier()
+        t0 = time.perf_counter()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            g0.record(stream)
+            for _ in range(es):
+                r2 = ctx.collapse_window(host, run_off, pos_range=pr, out=hout)
+            g1.record(stream)
+        barrier()
+        e2e_ms = g0.elapsed_time(g1) / es
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        line["e2e"] = {"value": world * n / (e2e_ms / 1000.0), "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(16 * r2["n_groups"] + 128),
+                       "ms_per_step": e2e_ms, "steps": es, "wall_ms_per_step": 1000.0 * (time.perf_counter() - t0) / es}
+    sampler.stop_flag.set(); sampler.join(timeout=3)
+    line["clocks"] = clocks.summary()
+
+    # ---- CPU baseline: the oracle port on a bounded coordinate slice of the same window (rank 0, N=1 only) ----
+    if rank == 0 and world == 1 and args.cpu_sample > 0:
+        from oracle import oracle
+        hostc = synth.to_host({kk: cols[kk] for kk in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar")})
+        sub, sub_off = host_slice_sample(hostc, run_off, args.cpu_sample)
+        t0 = time.perf_counter()
+        ro = oracle.collapse(sub, sub_off, mode=args.mode)
+        dt = time.perf_counter() - t0
+        ns = len(sub["pos"])
+        line["cpu_baseline"] = {"value": ns / dt, "unit": "alignments/s", "cores": 1, "kind": "port",
+                                "sample": f"coordinate slice of the same window: {ns} records of all {k} samples ({dt:.1f} s); C port of the reference algorithm (oracle/tb_oracle.c), no BAM decode"}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

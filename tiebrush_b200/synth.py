@@ -249,3 +249,9 @@ def take_prefix(host, n):
     out["cig_off"] = host["cig_off"][: n + 1].copy()
     out["cigar"] = host["cigar"][: int(out["cig_off"][-1])]
     return out
+
+
+def m_bases(cols):
+    """Sum of CIGAR M-op lengths ("coverage bases") of a torch column dict."""
+    cig = cols["cigar"].to(torch.int64) & 0xFFFFFFFF
+    return int(((cig >> 4) * ((cig & 0xF) == 0)).sum())
