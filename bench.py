@@ -209,12 +209,13 @@ def main():
     barrier()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = []
+    kms, stages = [], []
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(args.steps):
             res = step_dev()
             kms.append(ctx.last_kernel_ms(0))
+            stages.append([ctx.last_kernel_ms(i) for i in (2, 3, 0, 4, 5)])
         e1.record(stream)
     barrier()
     launches = ctx.launch_count() - l0
@@ -242,7 +243,8 @@ def main():
             "config": {"workload": f"C2: {k} RNA-seq samples x {reads} spliced 150bp reads on chr1, tiebrush mode {args.mode} (0=default CIGAR), one window per GPU",
                        "records_per_step_per_gpu": n, "groups_out": G, "mean_cigar_ops": cbar, "l2": "inputs (>=20 GB at full size) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"coordinate shards x{world}, no data-path collective", "gen_seconds": t_gen},
-            "roofline": roofline, "gpu_launches": int(launches)}
+            "roofline": roofline, "gpu_launches": int(launches),
+            "stage_ms": dict(zip(("hist_scan", "slots_offsets", "tile", "compaction", "yd"), [float(x) for x in np.mean(np.asarray(stages), 0)]))}
 
     # ---- tiecov leg (secondary): coverage + junctions + bedgraph runs on a collapsed-like stream ----
     if args.cov_records > 0:

@@ -160,9 +160,12 @@ int tc_coverage_window(tb_ctx*, const tc_soa_in* in, tc_runs_out* runs, tc_juncs
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Kernels launched by this library since the context was created (for bench.py's gpu_launches). */
 int64_t tb_launch_count(tb_ctx*);
-/* Device time in ms of the dominant kernel of the last call, measured with CUDA events on the
- * launching stream: which=0 collapse tile kernel, which=1 coverage accumulate kernel.
- * Enabled by tb_set_profiling(ctx,1); costs two event records per call. */
+/* Device time in ms of one stage of the last call, measured with CUDA events on the launching stream
+ * (enabled by tb_set_profiling(ctx,1)):
+ *   0 collapse tile kernel (dominant)      1 coverage accumulate kernel (dominant)
+ *   2 collapse C1+C2 histogram+scan        3 collapse C3+C4 slots + run offsets
+ *   4 collapse C6 compaction               5 collapse C7 YD chains
+ *   6 coverage K6 bundles                  7 coverage K8 runs      8 coverage K9 junction extraction */
 int   tb_set_profiling(tb_ctx*, int on);
 float tb_last_kernel_ms(tb_ctx*, int which);
 

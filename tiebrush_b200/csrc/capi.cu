@@ -52,7 +52,7 @@ tb_ctx* tb_create(int device, int n_samples, int mode, uint32_t flag_mask, int m
     global_error("tb_create: cudaStreamCreate: %s", cudaGetErrorString(e)); delete ctx; return nullptr;
   }
   ctx->stream = ctx->own_stream;
-  for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 16; ++i) cudaEventCreate(&ctx->ev[i]);
   return ctx;
 }
 
@@ -64,7 +64,7 @@ void tb_destroy(tb_ctx* ctx) {
   for (auto& b : ctx->in_stage) b.release();
   for (auto& b : ctx->out_stage) b.release();
   for (auto& b : ctx->pinned) b.release();
-  for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 16; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -81,7 +81,7 @@ int tb_sync(tb_ctx* ctx) {
 }
 int64_t tb_launch_count(tb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int tb_set_profiling(tb_ctx* ctx, int on) { if (!ctx) return 1; ctx->profiling = on; return 0; }
-float tb_last_kernel_ms(tb_ctx* ctx, int which) { return (ctx && which >= 0 && which < 2) ? ctx->last_ms[which] : 0.f; }
+float tb_last_kernel_ms(tb_ctx* ctx, int which) { return (ctx && which >= 0 && which < 16) ? ctx->last_ms[which] : 0.f; }
 
 int tb_collapse_window(tb_ctx* ctx, const tb_soa_in* in, tb_groups_out* out) {
   if (!ctx) return 1;

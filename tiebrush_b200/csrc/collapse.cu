@@ -476,34 +476,35 @@ __global__ void col_store_total_kernel(const uint32_t* tot, long long* status) {
 // `prev` can never be touched again before they are freed (disjoint, sorted, all ends < r.start), so they are
 // dropped eagerly; results are unchanged.
 // ---------------------------------------------------------------------------------------------------
-constexpr int YD_CAP = 48;
+constexpr int YD_CAP = 64;      // live nodes per list (shared memory); more => CS_YD_OVERFLOW (fails loudly)
+constexpr int YD_MAXEX = 16;    // exons per read staged in shared memory; longer chains are walked from global memory
 struct SegArr {
   int n; uint32_t last_pos; int last_dist;
-  uint32_t st[YD_CAP], en[YD_CAP];
+  uint32_t* st; uint32_t* en;   // YD_CAP entries each (shared memory)
   __device__ void reset() { n = 0; last_pos = 0; last_dist = -1; }
-  __device__ bool erase(int a, int b) {  // remove [a,b)
-    int d = b - a; if (d <= 0) return true;
+  __device__ void erase(int a, int b) {  // remove [a,b)
+    int d = b - a; if (d <= 0) return;
     for (int q = b; q < n; ++q) { st[q - d] = st[q]; en[q - d] = en[q]; }
-    n -= d; return true;
+    n -= d;
   }
   __device__ bool insert(int at, uint32_t s, uint32_t e) {
     if (n >= YD_CAP) return false;
     for (int q = n; q > at; --q) { st[q] = st[q - 1]; en[q] = en[q - 1]; }
     st[at] = s; en[at] = e; ++n; return true;
   }
-  // mergeRead :167-219; returns false on capacity overflow
-  __device__ bool merge(const ColIn& in, uint32_t rec) {
-    ExonIter it; it.init(in.cigar, in.cig_off[rec], in.cig_off[rec + 1], in.pos[rec]);
+  // mergeRead :167-219 over an exon source; returns false on capacity overflow
+  template <class Src>
+  __device__ bool merge(Src& src) {
     int s, e;
     if (n == 0) {
-      while (it.next(s, e)) { if (n >= YD_CAP) return false; st[n] = (uint32_t)s; en[n] = (uint32_t)e; ++n; }
+      while (src.next(s, e)) { if (n >= YD_CAP) return false; st[n] = (uint32_t)s; en[n] = (uint32_t)e; ++n; }
       return true;
     }
     int cur = 0;
-    while (it.next(s, e)) {
+    while (src.next(s, e)) {
       uint32_t es = (uint32_t)s, ee = (uint32_t)e;
       while (cur < n) {
-        if (ee < st[cur]) { if (!insert(cur, es, ee)) return false; ++cur; break; }  // inserted before n; n unchanged (now at cur+1)
+        if (ee < st[cur]) { if (!insert(cur, es, ee)) return false; ++cur; break; }  // inserted before n; n itself is now at cur
         if (es <= en[cur]) {
           if (es < st[cur]) st[cur] = es;
           if (ee > en[cur]) en[cur] = ee;
@@ -522,8 +523,9 @@ struct SegArr {
     return true;
   }
   // processRead :221-250
-  __device__ int process(const ColIn& in, uint32_t rec, uint32_t rstart, bool& ok) {
-    if (last_pos == rstart) { ok = merge(in, rec) && ok; return last_dist; }
+  template <class Src>
+  __device__ int process(Src& src, uint32_t rstart, bool& ok) {
+    if (last_pos == rstart) { ok = merge(src) && ok; return last_dist; }
     int d = 0, prev = -1;
     for (int q = 0; q < n && st[q] < rstart; ++q) prev = q;
     if (prev >= 0) {
@@ -532,64 +534,196 @@ struct SegArr {
       else erase(0, prev);  // eager drop of the inert nodes before prev
     }
     last_pos = rstart; last_dist = d;
-    ok = merge(in, rec) && ok;
+    ok = merge(src) && ok;
     return d;
   }
 };
+struct SmemExons {  // exon source over a staged array
+  const int2* ex; int n, i;
+  __device__ bool next(int& s, int& e) { if (i >= n) return false; s = ex[i].x; e = ex[i].y; ++i; return true; }
+};
 
-__global__ void __launch_bounds__(256) yd_group_key_kernel(ColIn in, const uint32_t* __restrict__ rep, int64_t G, int32_t* __restrict__ gstart,
-                                                          unsigned long long* __restrict__ gkey) {
+// Y1: per-group start / end / strand of the representative
+__global__ void __launch_bounds__(256) yd_group_info_kernel(ColIn in, const uint32_t* __restrict__ rep, int64_t G, int32_t* __restrict__ gstart,
+                                                           int32_t* __restrict__ gend, uint8_t* __restrict__ gstrand) {
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   uint32_t r = rep[g];
-  int pos = in.pos[r];
-  int l = 0;
+  int pos = in.pos[r], l = 0;
   for (uint32_t c = in.cig_off[r]; c < in.cig_off[r + 1]; ++c) {
     uint32_t w = in.cigar[c]; uint32_t op = w & 0xf;
     if (op == TB_OP_M || op == TB_OP_D || op == TB_OP_N || op == TB_OP_EQ || op == TB_OP_X) l += (int)(w >> 4);
   }
   gstart[g] = pos + 1;
-  gkey[g] = (unsigned long long)(uint32_t)(pos + l);  // end, 1-based inclusive
-}
-struct GKeyIn { const unsigned long long* k; __device__ unsigned long long operator()(int64_t i) const { return k[i]; } };
-struct GPmOut { unsigned long long* pm; __device__ void operator()(int64_t i, unsigned long long exc, unsigned long long) const { pm[i] = exc; } };
-struct GHeadIn {
-  const int32_t* gstart; const unsigned long long* pm;
-  __device__ uint32_t operator()(int64_t g) const { return (g == 0 || (unsigned long long)(uint32_t)gstart[g] > pm[g]) ? 1u : 0u; }
-};
-struct GHeadOut {
-  const int32_t* gstart; const unsigned long long* pm; uint32_t* bhead;
-  __device__ void operator()(int64_t g, uint32_t exc, uint32_t inc) const { if (inc != exc) bhead[exc] = (uint32_t)g; }
-};
-__global__ void yd_store_total_kernel(const uint32_t* tot, long long* status, uint32_t* bhead, uint32_t G) {
-  status[CS_NBUNDLES] = *tot; bhead[*tot] = G;
+  gend[g] = pos + l;
+  gstrand[g] = in.strand[r];
 }
 
-__global__ void __launch_bounds__(128) yd_kernel(ColIn in, const uint32_t* __restrict__ rep, const uint32_t* __restrict__ bits, uint32_t W,
-                                                 const int32_t* __restrict__ gstart, const uint32_t* __restrict__ bhead, long long* status,
-                                                 int32_t* __restrict__ yd) {
-  const long long nb = status[CS_NBUNDLES];
-  const long long total = nb * in.k;
-  SegArr fw, rv;
-  for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
-    // consecutive threads take consecutive samples of the same bundle: bitset words are warp-broadcast loads
-    const uint32_t b = (uint32_t)(x / in.k), s = (uint32_t)(x % in.k);
-    const uint32_t g0 = bhead[b], g1 = bhead[b + 1];
-    fw.reset(); rv.reset();
-    bool ok = true;
-    const uint32_t wsel = s >> 5, bsel = 1u << (s & 31);
-    for (uint32_t g = g0; g < g1; ++g) {
-      if (!(bits[(uint64_t)g * W + wsel] & bsel)) continue;
-      uint32_t r = rep[g];
-      uint8_t ts = in.strand[r];
-      uint32_t rstart = (uint32_t)gstart[g];
-      int dmax = 0;
-      if (ts == '+' || ts == '.') { int d = fw.process(in, r, rstart, ok); dmax = max(dmax, d); }
-      if (ts == '-' || ts == '.') { int d = rv.process(in, r, rstart, ok); dmax = max(dmax, d); }
-      if (dmax > 0) atomicMax(&yd[g], dmax);
+// A chain = (sample s, strand list): the groups, in output order, that contain s and whose strand feeds the list
+// ('+','.' -> forward = 0; '-','.' -> reverse = 1). processRead is a sequential state machine along a chain and
+// chains are independent (tiebrush.cpp:512-521), so the device builds every chain's member list with a stable
+// counting scatter (Y2-Y4) and then walks each chain with one warp (Y5).
+constexpr int YD_BLOCK = 1024;
+
+// Y2: members per (block of groups, chain)
+__global__ void __launch_bounds__(128) yd_count_kernel(const uint32_t* __restrict__ bits, uint32_t W, int k, int64_t G, const uint8_t* __restrict__ gstrand,
+                                                      uint32_t* __restrict__ blkcnt, int64_t nblk) {
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= nblk * W) return;
+  const int64_t b = warp / W; const uint32_t w = (uint32_t)(warp % W);
+  const int lane = tb_lane();
+  const int64_t g0 = b * YD_BLOCK, g1 = (g0 + YD_BLOCK < G) ? g0 + YD_BLOCK : G;
+  uint32_t cf = 0, cr = 0;
+  for (int64_t base = g0; base < g1; base += 32) {
+    int64_t g = base + lane;
+    uint32_t word = 0; uint8_t sc = 0;
+    if (g < g1) { word = bits[(uint64_t)g * W + w]; sc = gstrand[g]; }
+    unsigned any = __ballot_sync(0xffffffffu, word != 0);
+    while (any) {
+      int q = __ffs(any) - 1; any &= any - 1;
+      uint32_t wq = __shfl_sync(0xffffffffu, word, q);
+      int sq = __shfl_sync(0xffffffffu, (int)sc, q);
+      if ((wq >> lane) & 1u) { cf += (sq != '-'); cr += (sq != '+'); }
     }
-    if (!ok) status[CS_YD_OVERFLOW] = 1;
   }
+  const int s = (int)(w * 32 + lane);
+  if (s < k) { blkcnt[(b * 2 + 0) * k + s] = cf; blkcnt[(b * 2 + 1) * k + s] = cr; }
+}
+
+// Y3: exclusive prefix over blocks per chain column (in place), then chain base offsets
+__global__ void __launch_bounds__(128) yd_prefix_kernel(uint32_t* __restrict__ blkcnt, int64_t nblk, int k, uint32_t* __restrict__ coltot) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= 2 * k) return;
+  uint32_t run = 0;
+  for (int64_t b = 0; b < nblk; ++b) {
+    uint32_t* p = &blkcnt[b * 2 * k + col];
+    uint32_t v = *p; *p = run; run += v;
+  }
+  coltot[col] = run;
+}
+__global__ void yd_colbase_kernel(const uint32_t* __restrict__ coltot, int k, unsigned long long* __restrict__ colbase) {
+  unsigned long long run = 0;
+  for (int c = 0; c < 2 * k; ++c) { colbase[c] = run; run += coltot[c]; }
+  colbase[2 * k] = run;
+}
+
+// Y4: stable scatter of the group ids into the chain lists
+__global__ void __launch_bounds__(128) yd_scatter_kernel(const uint32_t* __restrict__ bits, uint32_t W, int k, int64_t G, const uint8_t* __restrict__ gstrand,
+                                                        const uint32_t* __restrict__ blkoff, const unsigned long long* __restrict__ colbase, int64_t nblk,
+                                                        uint32_t* __restrict__ chain) {
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= nblk * W) return;
+  const int64_t b = warp / W; const uint32_t w = (uint32_t)(warp % W);
+  const int lane = tb_lane();
+  const int s = (int)(w * 32 + lane);
+  const int64_t g0 = b * YD_BLOCK, g1 = (g0 + YD_BLOCK < G) ? g0 + YD_BLOCK : G;
+  unsigned long long pf = 0, pr = 0;
+  if (s < k) { pf = colbase[s] + blkoff[(b * 2 + 0) * k + s]; pr = colbase[k + s] + blkoff[(b * 2 + 1) * k + s]; }
+  for (int64_t base = g0; base < g1; base += 32) {
+    int64_t g = base + lane;
+    uint32_t word = 0; uint8_t sc = 0;
+    if (g < g1) { word = bits[(uint64_t)g * W + w]; sc = gstrand[g]; }
+    unsigned any = __ballot_sync(0xffffffffu, word != 0);
+    while (any) {
+      int q = __ffs(any) - 1; any &= any - 1;
+      uint32_t wq = __shfl_sync(0xffffffffu, word, q);
+      int sq = __shfl_sync(0xffffffffu, (int)sc, q);
+      if ((wq >> lane) & 1u) {
+        if (sq != '-') chain[pf++] = (uint32_t)(base + q);
+        if (sq != '+') chain[pr++] = (uint32_t)(base + q);
+      }
+    }
+  }
+}
+
+// Y4b: cut every chain where a member starts beyond every earlier end of its chain. There processRead finds only
+// dead nodes (d==0 => clearTo(prev), prev = last node) and leaves exactly the read's own exons: the state no
+// longer depends on history, so the pieces ("sub-chains") are independent. Prefix max of (chain<<32 | end) over
+// the member array is a segmented prefix max because chain ids ascend.
+struct MemberKeyIn {
+  const uint32_t* chain; const int32_t* gend; const unsigned long long* colbase; int nchains;
+  __device__ int chain_of(int64_t i) const {
+    int lo = 0, hi = nchains;  // last c with colbase[c] <= i
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (colbase[mid] <= (unsigned long long)i) lo = mid; else hi = mid; }
+    return lo;
+  }
+  __device__ unsigned long long operator()(int64_t i) const {
+    return ((unsigned long long)(uint32_t)chain_of(i) << 32) | (uint32_t)gend[chain[i]];
+  }
+};
+struct MemberPmOut { unsigned long long* pm; __device__ void operator()(int64_t i, unsigned long long exc, unsigned long long) const { pm[i] = exc; } };
+struct SubHeadIn {
+  MemberKeyIn mk; const int32_t* gstart; const unsigned long long* pm;
+  __device__ uint32_t operator()(int64_t i) const {
+    if (i == 0) return 1u;
+    unsigned long long p = pm[i];
+    int c = mk.chain_of(i);
+    if ((int)(p >> 32) != c) return 1u;                       // first member of its chain
+    return (uint32_t)gstart[mk.chain[i]] > (uint32_t)p ? 1u : 0u;
+  }
+};
+struct SubHeadOut {
+  uint32_t* heads;
+  __device__ void operator()(int64_t i, uint32_t exc, uint32_t inc) const { if (inc != exc) heads[exc] = (uint32_t)i; }
+};
+__global__ void yd_subchain_total_kernel(const uint32_t* tot, uint32_t* heads, uint32_t n_members, unsigned long long* work) {
+  heads[*tot] = n_members; work[0] = 0; work[1] = *tot;
+}
+
+// Y5: persistent warps pull sub-chains from a work counter. Lanes fetch the next 32 members and parse their exon
+// chains into shared memory, lane 0 runs processRead/mergeRead over them, then the lanes publish the distances.
+constexpr int YD_WARPS = 4;
+__global__ void __launch_bounds__(YD_WARPS * 32) yd_chain_kernel(ColIn in, const uint32_t* __restrict__ rep, const int32_t* __restrict__ gstart,
+                                                                const uint32_t* __restrict__ chain, const uint32_t* __restrict__ heads,
+                                                                unsigned long long* work, int32_t* __restrict__ yd, long long* status) {
+  __shared__ int2 s_ex[YD_WARPS][32][YD_MAXEX];
+  __shared__ int s_nex[YD_WARPS][32];
+  __shared__ int s_d[YD_WARPS][32];
+  __shared__ uint32_t s_st[YD_WARPS][YD_CAP], s_en[YD_WARPS][YD_CAP];
+  const int wl = tb_warp(), lane = tb_lane();
+  const unsigned long long nsub = work[1];
+  SegArr L; L.st = s_st[wl]; L.en = s_en[wl];
+  bool ok = true;
+  for (;;) {
+    unsigned long long j = 0;
+    if (lane == 0) j = atomicAdd(&work[0], 1ULL);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j >= nsub) break;
+    const uint32_t c0 = heads[j], c1 = heads[j + 1];
+    L.reset();
+    for (uint32_t base = c0; base < c1; base += 32) {
+      const uint32_t i = base + lane;
+      uint32_t g = 0;
+      if (i < c1) {
+        g = chain[i];
+        const uint32_t r = rep[g];
+        ExonIter it; it.init(in.cigar, in.cig_off[r], in.cig_off[r + 1], gstart[g] - 1);
+        int s, e, ne = 0;
+        while (it.next(s, e)) { if (ne < YD_MAXEX) s_ex[wl][lane][ne] = make_int2(s, e); ++ne; }
+        s_nex[wl][lane] = ne;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const int cnt = (int)((c1 - base) < 32u ? (c1 - base) : 32u);
+        for (int q = 0; q < cnt; ++q) {
+          const int ne = s_nex[wl][q];
+          const int rsq = s_ex[wl][q][0].x;  // the first exon starts at the read start (setupCoordinates)
+          int d;
+          if (ne <= YD_MAXEX) { SmemExons src{s_ex[wl][q], ne, 0}; d = L.process(src, (uint32_t)rsq, ok); }
+          else {
+            const uint32_t gq = chain[base + q], rr = rep[gq];
+            ExonIter it; it.init(in.cigar, in.cig_off[rr], in.cig_off[rr + 1], gstart[gq] - 1);
+            d = L.process(it, (uint32_t)gstart[gq], ok);
+          }
+          s_d[wl][q] = d;
+        }
+      }
+      __syncwarp();
+      if (i < c1) { const int d = s_d[wl][lane]; if (d > 0) atomicMax(&yd[g], d); }
+      __syncwarp();
+    }
+  }
+  if (lane == 0 && !ok) status[CS_YD_OVERFLOW] = 1;
 }
 
 static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -675,12 +809,14 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
   uint32_t* d_hist = B[XB_HIST].as<uint32_t>();
   const long long* d_runoff = B[XB_RUNOFF].as<long long>();
   // ---- C1, C2 ----
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[4], st));
   TB_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * ((size_t)S + 2), st));
   col_hist_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, d_hist, d_status);
   ctx->launches++;
   TB_CUDA((tb_device_scan<OpSumU32>(ctx, HistIn{d_hist}, (int64_t)S + 1, B[XB_AGG].as<uint32_t>(), HistOut{d_hist})));
   const uint32_t* d_P = d_hist;  // P[0..S], P[S] = n
   // ---- C3, C4 ----
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[5], st));
   col_slotpos_kernel<<<grid_for((int64_t)M + 1, 256), 256, 0, st>>>(d_P, S, (uint32_t)n, T, M, B[XB_SLOTPOS].as<uint32_t>());
   uint64_t off_total = ((uint64_t)M + 1) * k;
   col_off_init_kernel<<<grid_for((int64_t)off_total, 256), 256, 0, st>>>(B[XB_OFF].as<uint32_t>(), d_runoff, k, off_total);
@@ -698,12 +834,18 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
   ctx->launches++;
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[1], st));
   // ---- C6 ----
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[6], st));
   TB_CUDA((tb_device_scan<OpSumU32>(ctx, GcIn{tp.gcount}, (int64_t)M, B[XB_AGG].as<uint32_t>(), GcOut{B[XB_GBASE].as<uint32_t>()})));
   col_store_total_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(M), d_status);
   ctx->launches++;
   TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
-  if (ctx->profiling) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_ms[0] = ms; }
+  if (ctx->profiling) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_ms[0] = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ctx->last_ms[2] = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[0]) == cudaSuccess) ctx->last_ms[3] = ms;
+  }
   if (h_status[CS_ERR] == ERR_POS_RANGE) { ctx->set_error("tb_collapse_window: record %lld has pos outside [pos_lo,pos_hi)", h_status[CS_ERRIDX]); return 1; }
   if (h_status[CS_ERR] == ERR_UNSORTED) { ctx->set_error("tb_collapse_window: run not coordinate-sorted at record %lld", h_status[CS_ERRIDX]); return 1; }
   if (h_status[CS_TABLE_OVERFLOW]) { ctx->set_error("tb_collapse_window: more than %u distinct alignments at one start position (group table overflow; multi-pass fallback not implemented)", gcap - (gcap >> 3)); return 1; }
@@ -722,26 +864,51 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
   TB_CUDA(B[XB_BITS].ensure(sizeof(uint32_t) * (size_t)G * W));
   col_compact_kernel<<<M, 128, 0, st>>>(tp, S, B[XB_GBASE].as<uint32_t>(), o_rep, o_yc, o_yx, B[XB_BITS].as<uint32_t>(), G);
   ctx->launches++;
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[7], st));
 
   // ---- C7: YD ----
-  TB_CUDA(B[XB_GSTART].ensure(sizeof(int32_t) * G));
-  TB_CUDA(B[XB_GKEY].ensure(sizeof(uint64_t) * G));
-  TB_CUDA(B[XB_GPM].ensure(sizeof(uint64_t) * G));
-  TB_CUDA(B[XB_BHEAD].ensure(sizeof(uint32_t) * ((size_t)G + 2)));
-  TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks(G) + 8) * sizeof(uint64_t)));
-  TB_CUDA(cudaMemsetAsync(o_yd, 0, sizeof(int32_t) * G, st));
-  yd_group_key_kernel<<<grid_for(G, 256), 256, 0, st>>>(in, o_rep, G, B[XB_GSTART].as<int32_t>(), B[XB_GKEY].as<unsigned long long>());
-  ctx->launches++;
-  TB_CUDA((tb_device_scan<OpMaxU64>(ctx, GKeyIn{B[XB_GKEY].as<unsigned long long>()}, G, B[XB_AGG].as<unsigned long long>(), GPmOut{B[XB_GPM].as<unsigned long long>()})));
-  TB_CUDA((tb_device_scan<OpSumU32>(ctx, GHeadIn{B[XB_GSTART].as<int32_t>(), B[XB_GPM].as<unsigned long long>()}, G, B[XB_AGG].as<uint32_t>(),
-                                    GHeadOut{B[XB_GSTART].as<int32_t>(), B[XB_GPM].as<unsigned long long>(), B[XB_BHEAD].as<uint32_t>()})));
-  yd_store_total_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(G), d_status, B[XB_BHEAD].as<uint32_t>(), (uint32_t)G);
-  ctx->launches++;
   {
-    int blocks = ctx->sm_count * 8;
+    const int64_t nblk = (G + YD_BLOCK - 1) / YD_BLOCK;
+    TB_CUDA(B[XB_GSTART].ensure(sizeof(int32_t) * G));
+    TB_CUDA(B[XB_YD].ensure(sizeof(int32_t) * G));                           // end per group
+    TB_CUDA(B[XB_GKEY].ensure((size_t)G));                                  // strand char per group
+    TB_CUDA(B[XB_GPM].ensure(sizeof(uint32_t) * (size_t)nblk * 2 * k));       // per (block, chain) counts -> offsets
+    TB_CUDA(B[XB_GEND].ensure(sizeof(uint32_t) * 2 * k + sizeof(uint64_t) * (2 * k + 6)));
+    TB_CUDA(cudaMemsetAsync(o_yd, 0, sizeof(int32_t) * G, st));
+    int32_t* gstart = B[XB_GSTART].as<int32_t>(); int32_t* gend = B[XB_YD].as<int32_t>(); uint8_t* gstrand = B[XB_GKEY].as<uint8_t>();
+    uint32_t* blkcnt = B[XB_GPM].as<uint32_t>();
+    unsigned long long* colbase = B[XB_GEND].as<unsigned long long>();
+    unsigned long long* work = colbase + 2 * k + 2;
+    uint32_t* coltot = (uint32_t*)(colbase + 2 * k + 6);
+    const uint32_t* d_bits = B[XB_BITS].as<uint32_t>();
     if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[2], st));
-    yd_kernel<<<blocks, 128, 0, st>>>(in, o_rep, B[XB_BITS].as<uint32_t>(), W, B[XB_GSTART].as<int32_t>(), B[XB_BHEAD].as<uint32_t>(), d_status, o_yd);
-    ctx->launches++;
+    yd_group_info_kernel<<<grid_for(G, 256), 256, 0, st>>>(in, o_rep, G, gstart, gend, gstrand);
+    const int64_t nwarps = nblk * W;
+    yd_count_kernel<<<grid_for(nwarps * 32, 128), 128, 0, st>>>(d_bits, W, k, G, gstrand, blkcnt, nblk);
+    yd_prefix_kernel<<<grid_for(2 * k, 128), 128, 0, st>>>(blkcnt, nblk, k, coltot);
+    yd_colbase_kernel<<<1, 1, 0, st>>>(coltot, k, colbase);
+    ctx->launches += 4;
+    // total chain members (<= 2 x sum of YX) is only known on the device
+    TB_CUDA(cudaMemcpyAsync(h_status, colbase + 2 * k, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    const int64_t n_members = h_status[0];
+    if (n_members >= (1LL << 32)) { ctx->set_error("tb_collapse_window: %lld chain members exceed the 32-bit YD index", (long long)n_members); return 1; }
+    if (n_members > 0) {
+      uint32_t* chain = nullptr; uint32_t* heads = nullptr; unsigned long long* pm = nullptr;
+      TB_CUDA(B[XB_BHEAD].ensure(sizeof(uint32_t) * ((size_t)n_members + 32)));
+      TB_CUDA(B[XB_ST_REP].ensure(sizeof(uint32_t) * ((size_t)n_members + 32)));  // staging is dead by now: reuse
+      TB_CUDA(B[XB_ST_BITS].ensure(sizeof(uint64_t) * ((size_t)n_members + 32)));
+      TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks(n_members) + 8) * sizeof(uint64_t)));
+      chain = B[XB_BHEAD].as<uint32_t>(); heads = B[XB_ST_REP].as<uint32_t>(); pm = B[XB_ST_BITS].as<unsigned long long>();
+      yd_scatter_kernel<<<grid_for(nwarps * 32, 128), 128, 0, st>>>(d_bits, W, k, G, gstrand, blkcnt, colbase, nblk, chain);
+      ctx->launches++;
+      MemberKeyIn mk{chain, gend, colbase, 2 * k};
+      TB_CUDA((tb_device_scan<OpMaxU64>(ctx, mk, n_members, B[XB_AGG].as<unsigned long long>(), MemberPmOut{pm})));
+      TB_CUDA((tb_device_scan<OpSumU32>(ctx, SubHeadIn{mk, gstart, pm}, n_members, B[XB_AGG].as<uint32_t>(), SubHeadOut{heads})));
+      yd_subchain_total_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(n_members), heads, (uint32_t)n_members, work);
+      yd_chain_kernel<<<ctx->sm_count * 12, YD_WARPS * 32, 0, st>>>(in, o_rep, gstart, chain, heads, work, o_yd, d_status);
+      ctx->launches += 2;
+    }
     if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[3], st));
   }
   TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
@@ -752,6 +919,11 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
     TB_CUDA(cudaMemcpyAsync(out->yd, o_yd, sizeof(int32_t) * G, cudaMemcpyDeviceToHost, st));
   }
   TB_CUDA(cudaStreamSynchronize(st));
+  if (ctx->profiling) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) ctx->last_ms[4] = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->last_ms[5] = ms;
+  }
   if (h_status[CS_YD_OVERFLOW]) { ctx->set_error("tb_collapse_window: YD segment list exceeded %d live nodes (spill path not implemented)", YD_CAP); return 1; }
   return 0;
 }

@@ -346,6 +346,7 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
   unsigned long long* d_pm = B[CB_PM].as<unsigned long long>();
 
   // ---- K6 ----
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[8], st));
   cov_key_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, do_cov, d_key, d_status);
   ctx->launches++;
   size_t agg_bytes = (size_t)(tb_scan_blocks(n > 2 * ncig + 16 ? n : 2 * ncig + 16) + 8) * sizeof(SumNz);
@@ -359,6 +360,7 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
                                     B[CB_AGG].as<long long>(), BBaseOut{B[CB_BBASE].as<long long>()})));
   cov_publish_kernel<<<1, 1, 0, st>>>(nullptr, B[CB_AGG].as<long long>() + tb_scan_blocks(n), d_status);
   ctx->launches++;
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[9], st));
   TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
   if (h_status[ST_ERRIDX] != -1) {
@@ -415,6 +417,7 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
   }
 
   // ---- K8 ----
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[10], st));
   int64_t kmax = 2 * ncig + 16;
   if (do_cov) {
     TB_CUDA(B[CB_CPPOS].ensure(sizeof(int64_t) * kmax));
@@ -442,9 +445,15 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     cov_store_total_kernel<<<1, 1, 0, st>>>(nullptr, B[CB_AGG].as<uint32_t>() + tb_scan_blocks(kmax), d_status);
     ctx->launches++;
   }
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[11], st));
   TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
-  if (ctx->profiling) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_ms[1] = ms; }
+  if (ctx->profiling) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_ms[1] = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]) == cudaSuccess) ctx->last_ms[6] = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]) == cudaSuccess) ctx->last_ms[7] = ms;
+  }
   if (do_cov) {
     if (h_status[ST_RUNOVERFLOW] || h_status[ST_NRUNS] > runs->capacity) {
       ctx->set_error("tc_coverage_window: runs capacity %lld too small (%lld runs)", (long long)runs->capacity, h_status[ST_NRUNS]);

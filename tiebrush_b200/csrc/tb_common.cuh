@@ -66,9 +66,9 @@ struct tb_ctx {
   size_t smem_optin = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[16] = {};
   int profiling = 0;
-  float last_ms[2] = {0.f, 0.f};
+  float last_ms[16] = {};   // per-stage device times of the last call (see tb_last_kernel_ms)
   int64_t launches = 0;
   std::string err;
   DevBuf buf[TB_NBUF];   // workspace slots (see the enum in each pipeline)

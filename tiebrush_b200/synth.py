@@ -77,7 +77,7 @@ def sample_reads(tm: TranscriptModel, n_reads: int, seed: int, paired=False, wit
     hi = torch.minimum(cum[:, 1:], (off + READ_LEN)[:, None])
     m = (hi - lo).clamp(min=0)                                  # [n,12] bases of the read in each exon
     e0 = (cum[:, 1:] <= off[:, None]).sum(1)                    # first exon touched
-    pos = tm.ex_start[tx, e0] + (off - cum[tx, e0])             # 1-based start
+    pos = tm.ex_start[tx, e0] + (off - tm.cum[tx, e0])          # 1-based start
     n = n_reads
     idx = (e0[:, None] + torch.arange(MAXBLK, device=dev)[None, :]).clamp(max=11)
     blk = torch.gather(m, 1, idx) * ((e0[:, None] + torch.arange(MAXBLK, device=dev)[None, :]) <= 11)   # [n,MAXBLK]
