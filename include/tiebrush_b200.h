@@ -40,8 +40,8 @@ extern "C" {
 /* keep_bits: struct Options, src/tiebrush.cpp:89-98 */
 #define TB_KEEP_SUPP      1 /* -S / --keep-supp      keep flag 0x800 */
 #define TB_KEEP_SECONDARY 2 /* --keep-secondary      keep flag 0x100 */
-#define TB_KEEP_UNMAP     4 /* -M / --keep-unmap     (reference aborts on real unmapped reads; rejected here) */
-#define TB_STORE_FRAC     8 /* --store-frac          YC += 1/NH (not implemented on device yet: tb_create fails) */
+#define TB_KEEP_UNMAP     4 /* -M / --keep-unmap     (the reference aborts on a real unmapped read; so does tb_collapse_window) */
+#define TB_STORE_FRAC     8 /* --store-frac          YC += 1/NH, summed in double in the reference's arrival order */
 
 #define TB_NO_MAX_NH 0x7fffffff /* Options.max_nh default MAX_INT */
 
@@ -160,11 +160,16 @@ int tc_coverage_window(tb_ctx*, const tc_soa_in* in, tc_runs_out* runs, tc_juncs
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Kernels launched by this library since the context was created (for bench.py's gpu_launches). */
 int64_t tb_launch_count(tb_ctx*);
+/* Front end the last tb_collapse_window call ran: 0 = shared-memory tile path (order-independent grouping),
+ * 1 = ordered path chosen by the options (-F, -A, TieBrush-made inputs, --store-frac: exact emulation of the reference's
+ * per-position sorted-list search in merge order), 2 = ordered path as fallback (a start position with more distinct
+ * alignments than one shared-memory table). */
+int tb_last_path(tb_ctx*);
 /* Device time in ms of one stage of the last call, measured with CUDA events on the launching stream
  * (enabled by tb_set_profiling(ctx,1)):
  *   0 collapse tile kernel (dominant)      1 coverage accumulate kernel (dominant)
  *   2 collapse C1+C2 histogram+scan        3 collapse C3+C4 slots + run offsets
- *   4 collapse C6 compaction               5 collapse C7 YD chains
+ *   4 collapse C6 compaction               5 collapse C7 YD (descriptors, bundles, chains)
  *   6 coverage K6 bundles                  7 coverage K8 runs      8 coverage K9 junction extraction */
 int   tb_set_profiling(tb_ctx*, int on);
 float tb_last_kernel_ms(tb_ctx*, int which);

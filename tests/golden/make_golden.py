@@ -46,6 +46,8 @@ OPTSETS = [
     ("K2SE", ["--keep-secondary", "-S", "-E"], dict(keep_bits=KS | K2, mode=3)),
     ("F2048SK2", ["-F", "2048", "-S", "--keep-secondary"], dict(flag_mask=2048, keep_bits=KS | K2)),
     ("A", ["-A"], dict(collapse_same=1)),
+    ("SF", ["--store-frac", "--keep-secondary"], dict(keep_bits=K2 | 8)),
+    ("SFF16", ["--store-frac", "--keep-secondary", "-F", "16"], dict(keep_bits=K2 | 8, flag_mask=16)),
 ]
 
 

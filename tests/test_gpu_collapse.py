@@ -48,6 +48,87 @@ def test_collapse_synthetic_vs_oracle(mode, n_tx, k, reads):
         assert np.array_equal(np.asarray(got[key]), exp[key]), key
 
 
+def test_collapse_full_mode_synthetic_vs_oracle():
+    """-L (CIGAR + MD) on a synthetic cohort with MD strings."""
+    from oracle import oracle
+    from tiebrush_b200 import synth
+    cols, run_off, pr = synth.cohort_window(10, 20000, seed=9, n_tx=30, device="cpu", with_md=True)
+    host = synth.to_host(cols)
+    host["md_off"], host["md"] = synth.md_columns(cols)
+    got = gpu_collapse(host, run_off, mode=1)
+    exp = oracle.collapse(host, run_off, mode=1)
+    assert got["n_kept"] == exp["n_kept"]
+    for key in ("rep_index", "yc", "yx", "yd"):
+        assert np.array_equal(np.asarray(got[key]), exp[key]), key
+
+
+@pytest.mark.parametrize("opts", [dict(max_nh=1), dict(min_qual=30), dict(max_nh=3, min_qual=1, mode=3), dict(flag_mask=16),
+                                  dict(flag_mask=16, mode=3, max_nh=2), dict(keep_bits=2 | 8)])
+def test_collapse_filters_and_ordered_path_synthetic_vs_oracle(opts):
+    """-N/-Q filters on the tile path; -F and --store-frac on the ordered path (exact list emulation), paired flags."""
+    from oracle import oracle
+    from tiebrush_b200 import api, synth
+    k = 7
+    cols, run_off, pr = synth.cohort_window(k, 15000, seed=11, n_tx=25, device="cpu", paired=True)
+    host = synth.to_host(cols)
+    with api.Context(device=0, n_samples=k, **opts) as ctx:
+        got = ctx.collapse_window(host, run_off)
+        assert ctx.last_path() == (1 if ("flag_mask" in opts or opts.get("keep_bits", 0) & 8) else 0)
+    exp = oracle.collapse(host, run_off, **opts)
+    assert got["n_kept"] == exp["n_kept"]
+    for key in ("rep_index", "yc", "yx", "yd"):
+        assert np.array_equal(np.asarray(got[key]), exp[key]), key
+
+
+def test_collapse_table_overflow_falls_back_to_ordered_path():
+    """One start position with more distinct alignments than a shared-memory table holds: the window is redone by the
+    exact path and still matches the oracle."""
+    from oracle import oracle
+    from tiebrush_b200 import api
+    rng = np.random.default_rng(5)
+    k, per = 3, 4000
+    n = k * per
+    a = rng.integers(1, 400, n); b = rng.integers(1, 400, n)
+    cigar = np.stack([(a << 4) | 0, np.full(n, (1 << 4) | 1), (b << 4) | 0], 1).astype(np.uint32).reshape(-1)
+    pos = np.full(n, 1000, np.int32)
+    pos[:: 7] = 990  # a second, ordinary position in front
+    order = np.concatenate([f * per + np.argsort(pos[f * per:(f + 1) * per], kind="stable") for f in range(k)])
+    cols = dict(pos=pos[order], flag=np.zeros(n, np.uint16), mapq=np.full(n, 60, np.uint8), strand=np.full(n, ord("+"), np.uint8),
+                nh=np.ones(n, np.uint16), cig_off=(np.arange(n + 1) * 3).astype(np.uint32), cigar=cigar.reshape(n, 3)[order].reshape(-1))
+    run_off = np.arange(k + 1, dtype=np.int64) * per
+    with api.Context(device=0, n_samples=k) as ctx:
+        got = ctx.collapse_window(cols, run_off)
+        assert ctx.last_path() == 2
+    exp = oracle.collapse(cols, run_off)
+    assert got["n_groups"] == len(exp["rep_index"]) > 8000
+    for key in ("rep_index", "yc", "yx", "yd"):
+        assert np.array_equal(np.asarray(got[key]), exp[key]), key
+
+
+def test_collapse_pileup_position_single_mode():
+    """A pile-up position (more records than a tile) with few distinct alignments stays on the tile path."""
+    from oracle import oracle
+    from tiebrush_b200 import api
+    rng = np.random.default_rng(6)
+    k, per = 5, 6000
+    n = k * per
+    a = rng.integers(40, 60, n)
+    cigar = np.stack([(a << 4) | 0, np.full(n, (300 << 4) | 3), ((150 - a) << 4) | 0], 1).astype(np.uint32)
+    pos = np.where(rng.random(n) < 0.9, 5000, rng.integers(4000, 6000, n)).astype(np.int32)
+    order = np.concatenate([f * per + np.argsort(pos[f * per:(f + 1) * per], kind="stable") for f in range(k)])
+    cols = dict(pos=pos[order], flag=np.zeros(n, np.uint16), mapq=np.full(n, 60, np.uint8),
+                strand=rng.choice(np.frombuffer(b"+-.", np.uint8), n), nh=np.ones(n, np.uint16),
+                cig_off=(np.arange(n + 1) * 3).astype(np.uint32), cigar=cigar[order].reshape(-1))
+    run_off = np.arange(k + 1, dtype=np.int64) * per
+    with api.Context(device=0, n_samples=k) as ctx:
+        got = ctx.collapse_window(cols, run_off)
+        assert ctx.last_path() == 0
+    exp = oracle.collapse(cols, run_off)
+    assert got["n_kept"] == exp["n_kept"]
+    for key in ("rep_index", "yc", "yx", "yd"):
+        assert np.array_equal(np.asarray(got[key]), exp[key]), key
+
+
 def test_collapse_device_resident_properties():
     """BASELINE-shaped cohort kept in HBM: size-independent properties (sum YC == records kept, reps are
     members with the right position order, YX <= min(k, YC)) plus oracle equality on the host copy."""

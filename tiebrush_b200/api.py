@@ -73,6 +73,10 @@ class Context:
     def launch_count(self):
         return int(self.lib.tb_launch_count(self.h))
 
+    def last_path(self):
+        """0 tile path, 1 ordered path (by options), 2 ordered path (table-overflow fallback)."""
+        return int(self.lib.tb_last_path(self.h))
+
     # ------------------------------------------------------------------------------------------
     def collapse_window(self, cols, run_off, tid=0, file_merged=None, pos_range=None, out=None):
         """One window of tiebrush. Returns dict(rep_index, yc, yx, yd, n_kept, n_groups)."""

@@ -36,7 +36,6 @@ tb_ctx* tb_create(int device, int n_samples, int mode, uint32_t flag_mask, int m
   }
   if (device < 0 || device >= ndev) { global_error("tb_create: device %d out of range (0..%d)", device, ndev - 1); return nullptr; }
   if (mode < 0 || mode > 3) { global_error("tb_create: unknown merge strategy %d", mode); return nullptr; }
-  if (keep_bits & TB_STORE_FRAC) { global_error("tb_create: --store-frac is not implemented on the device path yet"); return nullptr; }
   if (max_nh >= 65535 && max_nh != TB_NO_MAX_NH) { global_error("tb_create: -N %d exceeds the saturating u16 NH column (use < 65535)", max_nh); return nullptr; }
   if (n_samples < 1 || n_samples > 65535) { global_error("tb_create: n_samples %d out of range (1..65535)", n_samples); return nullptr; }
   if ((e = cudaSetDevice(device)) != cudaSuccess) { global_error("tb_create: cudaSetDevice: %s", cudaGetErrorString(e)); return nullptr; }
@@ -80,6 +79,7 @@ int tb_sync(tb_ctx* ctx) {
   return 0;
 }
 int64_t tb_launch_count(tb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int tb_last_path(tb_ctx* ctx) { return ctx ? ctx->last_path : -1; }
 int tb_set_profiling(tb_ctx* ctx, int on) { if (!ctx) return 1; ctx->profiling = on; return 0; }
 float tb_last_kernel_ms(tb_ctx* ctx, int which) { return (ctx && which >= 0 && which < 16) ? ctx->last_ms[which] : 0.f; }
 

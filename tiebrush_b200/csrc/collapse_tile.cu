@@ -1,0 +1,510 @@
+// collapse_tile.cu — fast front end of the collapse: position-partitioned shared-memory hash tiles.
+//
+// Used when grouping is order independent (no -F, no -A, no TieBrush-made inputs, no --store-frac): then the
+// reference's per-position sorted list (src/tiebrush.cpp:438-499) is simply the set of distinct keys in key order,
+// YC is a count, YX a distinct-sample count and the representative is the first member in merge order
+// (src/tmerge.h:28-50; closed form: min over members of (E, fidx, index-in-file)).
+//
+//   slots      slot m = the start positions whose first merged rank P[p] lies in [mT,(m+1)T). Only the LAST position of a
+//              slot can hold >= T records, so a slot is < T records of ordinary positions plus, possibly, one pile-up
+//              position that is processed as a second sub-tile in "single position" mode.
+//   table      every start position owns a private open-addressing region of the shared-memory table, placed at
+//              floor(1.25 * (P[p]-rank0)) and sized >= its record count: regions are laid out in position order, a group
+//              can never overflow its region (groups <= records), and the final order needs sorting only INSIDE a position.
+//   streaming  persistent CTAs pull slots; each warp owns a contiguous range of the slot's file-major record list
+//              (k slices, located by the per-(slot,file) offsets), so loads are coalesced and the per-file running
+//              maximum of `end` that defines the merge order is a warp-local segmented scan with a register carry.
+//              A record probes its region: tag compare in shared memory, then its real key bytes against the owner's
+//              (grouping never rests on the hash). Lanes of one file hitting one group are merged with match_any:
+//              one count atomic, (rarely) one representative atomicMin, (rarely) one sample-bit atomicOr.
+//   epilogue   occupied entries are compacted in region (= position) order, ranked inside their position by
+//              (strand, end, mode key) with the reference's comparator, and written to the staging arrays.
+#include <limits.h>
+#include "collapse_internal.cuh"
+
+namespace {
+
+constexpr unsigned long long EMPTY64 = ~0ULL;
+
+struct TileParams {
+  uint32_t T, M, ecap, W, cap_records;
+  const uint32_t* P; const uint32_t* slotpos; const uint32_t* off;
+  uint32_t* gcount; uint32_t* st_rep; float* st_yc; uint32_t* st_yx; uint32_t* st_bits;
+  long long* status; unsigned int* slot_counter; uint64_t seed;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// C3: first position of every slot: slotpos[m] = first p with P[p] >= m*T
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) col_slotpos_kernel(const uint32_t* __restrict__ P, uint32_t span, uint32_t T, uint32_t M, uint32_t* __restrict__ slotpos) {
+  uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m > M) return;
+  if (m == M) { slotpos[M] = span; return; }
+  const unsigned long long target = (unsigned long long)m * T;  // < n = P[span]
+  uint32_t lo = 0, hi = span;  // first p in [0,span] with P[p] >= target
+  while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if ((unsigned long long)P[mid] >= target) hi = mid; else lo = mid + 1; }
+  slotpos[m] = lo;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C4: off[m][f] = first record of run f that falls in a slot >= m
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) col_off_init_kernel(uint32_t* __restrict__ off, const long long* __restrict__ run_off, int k, uint64_t total) {
+  uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= total) return;
+  int f = (int)(x % (uint64_t)k);
+  off[x] = (uint32_t)run_off[f + 1];
+}
+
+__global__ void __launch_bounds__(256) col_off_kernel(ColIn in, const long long* __restrict__ run_off, const uint32_t* __restrict__ P, uint32_t T,
+                                                      uint32_t* __restrict__ off, long long* __restrict__ status) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= in.n) return;
+  const int32_t p = in.pos[i];
+  const uint32_t rel = (uint32_t)(p - in.pos_lo);
+  if (rel >= in.span) return;  // already reported by C1
+  int64_t sprev = -1;
+  bool first = false;
+  int f = -1;
+  if (i > 0) {
+    const int32_t pp = in.pos[i - 1];
+    if (pp == p) return;                       // same position as the previous record: same slot, and if i starts a run the
+                                               // check below would need f; handle run starts explicitly
+    // different position: either a file boundary or a forward step inside the file
+    int lo = 0, hi = in.k;                     // run containing i: last f with run_off[f] <= i
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (run_off[mid] <= i) lo = mid; else hi = mid; }
+    f = lo;
+    first = (i == run_off[f]);
+    if (!first) {
+      if (pp > p) { status[CS_ERR] = ERR_UNSORTED; atomicMin((unsigned long long*)&status[CS_ERRIDX], (unsigned long long)i); return; }
+      const uint32_t prel = (uint32_t)(pp - in.pos_lo);
+      if (prel >= in.span) return;
+      sprev = (int64_t)(P[prel] / T);
+    }
+  } else { f = 0; while (f + 1 < in.k && run_off[f + 1] <= 0) ++f; first = true; }
+  (void)first;
+  const int64_t scur = (int64_t)(P[rel] / T);
+  for (int64_t s = sprev + 1; s <= scur; ++s) off[(uint64_t)s * in.k + f] = (uint32_t)i;
+}
+
+// a record that starts its run but has the same position as the last record of the previous run was skipped above
+__global__ void __launch_bounds__(128) col_off_heads_kernel(ColIn in, const long long* __restrict__ run_off, const uint32_t* __restrict__ P, uint32_t T,
+                                                            uint32_t* __restrict__ off) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= in.k) return;
+  const int64_t i = run_off[f];
+  if (i >= run_off[f + 1]) return;
+  const uint32_t rel = (uint32_t)(in.pos[i] - in.pos_lo);
+  if (rel >= in.span) return;
+  const int64_t scur = (int64_t)(P[rel] / T);
+  for (int64_t s = 0; s <= scur; ++s) off[(uint64_t)s * in.k + f] = (uint32_t)i;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C5: the tile kernel
+// ---------------------------------------------------------------------------------------------------
+template <int THREADS>
+struct TileSmem {
+  unsigned long long* word;   // [E]  streaming: tag32<<32 | owner record ; epilogue: 64-bit sort key
+  unsigned long long* rep;    // [E]  streaming: min over members of (E-pos)<<32 | record ; epilogue: owner<<32 | rep
+  uint32_t* cnt;              // [E]
+  uint32_t* bits;             // [E*W]
+  uint32_t* a;                // [k]  slice begin of the current sub-tile
+  uint32_t* b;                // [k]  slice end
+  uint32_t* c;                // [k]  scratch (slot-level slice end while a pile-up sub-tile is split off)
+  uint32_t* soff;             // [k+1] exclusive prefix of slice lengths
+  uint16_t* rbase;            // [E]  region base of the entry's position (segment id in the epilogue)
+  uint16_t* occ;              // [E]  compacted entry indices
+};
+
+static size_t tile_smem_bytes(uint32_t k, uint32_t E, uint32_t W) {
+  return (size_t)E * (8 + 8 + 4 + 4 * (size_t)W + 2 + 2) + (size_t)(4 * k + 1) * 4 + 64;
+}
+
+// 64-bit epilogue sort key: strand(2) | ref_len(30) | key length(8, saturated) | first key word, byte order of memcmp (24).
+// It is a monotone prefix of the reference's order (strand, end, mode compare); ties are settled by tb_mode_cmp.
+__device__ unsigned long long tile_sort_key(const ColIn& in, uint32_t o, unsigned sc) {
+  const uint32_t c0 = in.cig_off[o], c1 = in.cig_off[o + 1];
+  const int pos = in.pos[o];
+  uint32_t reflen, len8, w24;
+  if (in.mode == TB_MODE_EXON) {
+    ExonIter it; it.init(in.cigar, c0, c1, pos);
+    int s, e, nex = 0, e0 = 0;
+    while (it.next(s, e)) { if (nex == 0) e0 = e; ++nex; }
+    reflen = (uint32_t)it.l;
+    len8 = nex > 255 ? 255u : (uint32_t)nex;
+    uint32_t d = (uint32_t)(e0 - pos);               // first exon end - pos (its start is pos+1 for every record of the position)
+    w24 = d > 0xffffffu ? 0xffffffu : d;
+  } else {
+    reflen = (uint32_t)tb_ref_len(in.cigar, c0, c1);
+    uint32_t a = c0, b = c1;
+    if (in.mode == TB_MODE_CLIP) tb_clip_range(in.cigar, a, b);
+    const uint32_t nc = b - a;
+    len8 = nc > 255 ? 255u : nc;
+    w24 = nc ? (__byte_perm(in.cigar[a], 0, 0x0123) >> 8) : 0u;
+  }
+  return ((unsigned long long)sc << 62) | ((unsigned long long)(reflen & 0x3fffffffu) << 32) | ((unsigned long long)len8 << 24) | w24;
+}
+
+template <int THREADS>
+__device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem<THREADS>& sm, uint32_t n_sub, uint32_t rankbase, bool single,
+                                 uint64_t outbase, uint32_t* s_scan, volatile uint32_t* s_flags /*[0]=kept [1]=overflow [2]=ngroups*/) {
+  constexpr int NW = THREADS / 32;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t E = tp.ecap, W = tp.W, k = (uint32_t)in.k;
+  // ---- exclusive prefix of the slice lengths ----
+  {
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < k; base += THREADS) {
+      const uint32_t f = base + tid;
+      const uint32_t c = f < k ? sm.b[f] - sm.a[f] : 0u;
+      uint32_t tot;
+      const uint32_t exc = tb_block_exscan<OpSumU32>(c, s_scan, &tot);
+      if (f < k) sm.soff[f] = carry + exc;
+      carry += tot;
+    }
+    if (tid == 0) sm.soff[k] = carry;
+  }
+  uint32_t E_used = single ? E : ((5u * n_sub) >> 2) + 1u;
+  if (E_used > E) E_used = E;
+  for (uint32_t s = tid; s < E_used; s += THREADS) { sm.word[s] = EMPTY64; sm.rep[s] = EMPTY64; sm.cnt[s] = 0; }
+  for (uint32_t s = tid; s < E_used * W; s += THREADS) sm.bits[s] = 0;
+  if (tid == 0) { s_flags[0] = 0; s_flags[1] = 0; s_flags[2] = 0; }
+  __syncthreads();
+
+  // ---- stream this warp's contiguous range of the file-major record list ----
+  const uint32_t j0 = (uint32_t)(((unsigned long long)n_sub * warp) / NW), j1 = (uint32_t)(((unsigned long long)n_sub * (warp + 1)) / NW);
+  uint32_t carry_f = 0xffffffffu; int carry_pos = INT_MIN; int carry_max = 0;
+  uint32_t my_kept = 0;
+  if (j0 < j1) {
+    // look-back: if the range starts inside a (file,position) run, the running maximum of the part before it is needed
+    uint32_t lo = 0, hi = k;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.soff[mid] <= j0) lo = mid; else hi = mid; }
+    const uint32_t f0 = lo;
+    if (j0 > sm.soff[f0]) {
+      const uint32_t slo = sm.a[f0];
+      const uint32_t i0 = slo + (j0 - sm.soff[f0]);
+      const int p = in.pos[i0];
+      if (in.pos[i0 - 1] == p) {
+        int mx = 0;
+        for (uint32_t top = i0; top > slo;) {
+          const bool ok = lane < top - slo;
+          const uint32_t idx = ok ? top - 1 - lane : slo;
+          const bool same = ok && in.pos[idx] == p;
+          const int rl = same ? tb_ref_len(in.cigar, in.cig_off[idx], in.cig_off[idx + 1]) : 0;
+          const unsigned notsame = __ballot_sync(0xffffffffu, !same);
+          const unsigned first = notsame ? (unsigned)(__ffs(notsame) - 1) : 32u;
+          if (lane < first) mx = max(mx, rl);
+          if (first < 32u) break;
+          top -= 32;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        carry_f = f0; carry_pos = p; carry_max = mx;
+      }
+    }
+  }
+  const uint32_t glimit = E - (E >> 3);
+  for (uint32_t jb = j0; jb < j1; jb += 32) {
+    if (single && s_flags[2] > glimit) { s_flags[1] = 1; break; }   // warp-uniform (broadcast read)
+    const uint32_t j = jb + lane;
+    const bool valid = j < j1;
+    uint32_t f = 0xfffffffeu, i = 0; int pos = INT_MIN + 1 + (int)lane, reflen = 0; uint64_t kh = 0; bool pass = false; unsigned sc = 0;
+    if (valid) {
+      uint32_t lo = 0, hi = k;  // last f with soff[f] <= j
+      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.soff[mid] <= j) lo = mid; else hi = mid; }
+      f = lo;
+      i = sm.a[f] + (j - sm.soff[f]);
+      pos = in.pos[i];
+      const uint32_t c0 = in.cig_off[i], c1 = in.cig_off[i + 1];
+      const uint16_t fl = in.flag[i]; const uint8_t mq = in.mapq[i]; const uint16_t nh = in.nh[i];
+      sc = tb_strand_code(in.strand[i]);
+      tb_parse_record(in, i, pos, c0, c1, reflen, kh);
+      pass = tb_passes_options(in, fl, mq, nh);
+    }
+    // segmented inclusive max-scan of ref_len over (file,position) runs == the running max that orders the reference's
+    // priority queue; records the filters drop still take part (they delay the records behind them)
+    uint32_t f_prev = __shfl_up_sync(0xffffffffu, f, 1); int pos_prev = __shfl_up_sync(0xffffffffu, pos, 1);
+    if (lane == 0) { f_prev = carry_f; pos_prev = carry_pos; }
+    int h = (!valid || f != f_prev || pos != pos_prev) ? 1 : 0;
+    int v = valid ? reflen : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v2 = __shfl_up_sync(0xffffffffu, v, d), h2 = __shfl_up_sync(0xffffffffu, h, d);
+      if ((int)lane >= d) { if (!h) v = max(v, v2); h |= h2; }
+    }
+    if (!h) v = max(v, carry_max);
+    const int Erel = v;
+    carry_f = __shfl_sync(0xffffffffu, f, 31); carry_pos = __shfl_sync(0xffffffffu, pos, 31); carry_max = __shfl_sync(0xffffffffu, Erel, 31);
+
+    uint32_t s = 0;
+    if (pass) {
+      ++my_kept;
+      uint32_t base = 0, size = E;
+      if (!single) {
+        const uint32_t rel = (uint32_t)(pos - in.pos_lo);
+        const uint32_t Pa = tp.P[rel] - rankbase, Pb = tp.P[rel + 1] - rankbase;
+        base = (5u * Pa) >> 2; size = ((5u * Pb) >> 2) - base;
+      }
+      const unsigned long long hh = tb_mix64(kh ^ ((unsigned long long)(uint32_t)reflen * 0xD6E8FEB86659FD93ULL) ^ tp.seed);
+      const uint32_t tag = (sc << 30) | (uint32_t)(hh >> 34);
+      s = base + __umulhi((uint32_t)hh, size);
+      const unsigned long long mine = ((unsigned long long)tag << 32) | i;
+      bool placed = false;
+      for (uint32_t t = 0; t < size; ++t) {
+        unsigned long long w = sm.word[s];
+        if (w == EMPTY64) {
+          w = atomicCAS(&sm.word[s], EMPTY64, mine);
+          if (w == EMPTY64) { sm.rbase[s] = (uint16_t)base; atomicAdd((uint32_t*)&s_flags[2], 1u); placed = true; break; }
+        }
+        if ((uint32_t)(w >> 32) == tag) {
+          const uint32_t o = (uint32_t)w;  // owner: compare the real keys (same position by construction, same strand by the tag)
+          if (o == i || tb_mode_cmp(in, i, o) == 0) { placed = true; break; }
+        }
+        if (++s == base + size) s = base;
+      }
+      if (!placed) { s_flags[1] = 1; pass = false; }
+    }
+    // merge the lanes of one file that hit one group: the lowest lane has the smallest (E, index) of them
+    const uint32_t mkey = pass ? (s | (f << 13)) : (0x80000000u | lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, mkey);
+    if (pass && (int)lane == __ffs(peers) - 1) {
+      atomicAdd(&sm.cnt[s], (uint32_t)__popc(peers));
+      const unsigned long long repkey = ((unsigned long long)(uint32_t)Erel << 32) | i;
+      if (repkey < sm.rep[s]) atomicMin(&sm.rep[s], repkey);
+      const uint32_t bi = s * W + (f >> 5), bit = 1u << (f & 31);
+      if (!(sm.bits[bi] & bit)) atomicOr(&sm.bits[bi], bit);
+    }
+  }
+  if (my_kept) atomicAdd((uint32_t*)&s_flags[0], my_kept);
+  __syncthreads();
+  if (s_flags[1]) return 0xffffffffu;   // block-uniform: table overflow (single-position mode only)
+
+  // ---- epilogue A: compact the occupied entries in region (= position) order ----
+  uint32_t G = 0;
+  for (uint32_t base = 0; base < E_used; base += THREADS) {
+    const uint32_t e = base + tid;
+    const uint32_t occf = (e < E_used && sm.word[e] != EMPTY64) ? 1u : 0u;
+    uint32_t tot;
+    const uint32_t exc = tb_block_exscan<OpSumU32>(occf, s_scan, &tot);
+    if (occf) sm.occ[G + exc] = (uint16_t)e;
+    G += tot;
+  }
+  __syncthreads();
+  // ---- epilogue B: sort keys ----
+  for (uint32_t r = tid; r < G; r += THREADS) {
+    const uint32_t e = sm.occ[r];
+    const unsigned long long w = sm.word[e];
+    const uint32_t o = (uint32_t)w; const unsigned sc = (unsigned)(w >> 62);
+    sm.word[e] = tile_sort_key(in, o, sc);
+    sm.rep[e] = ((unsigned long long)o << 32) | (uint32_t)sm.rep[e];
+  }
+  __syncthreads();
+  // ---- epilogue C: rank inside the position, write the groups in final order ----
+  for (uint32_t r = tid; r < G; r += THREADS) {
+    const uint32_t e = sm.occ[r];
+    uint32_t a = r, b = r + 1;
+    if (single) { a = 0; b = G; }
+    else {
+      const uint16_t rb = sm.rbase[e];
+      while (a > 0 && sm.rbase[sm.occ[a - 1]] == rb) --a;
+      while (b < G && sm.rbase[sm.occ[b]] == rb) ++b;
+    }
+    const unsigned long long ki = sm.word[e];
+    const uint32_t oi = (uint32_t)(sm.rep[e] >> 32);
+    uint32_t rank = 0;
+    for (uint32_t q = a; q < b; ++q) {
+      if (q == r) continue;
+      const uint32_t eq = sm.occ[q];
+      const unsigned long long kq = sm.word[eq];
+      if (kq < ki) ++rank;
+      else if (kq == ki) { if (tb_mode_cmp(in, (uint32_t)(sm.rep[eq] >> 32), oi) < 0) ++rank; }
+    }
+    const uint64_t o = outbase + a + rank;
+    tp.st_rep[o] = (uint32_t)sm.rep[e];
+    tp.st_yc[o] = (float)sm.cnt[e];
+    uint32_t yx = 0;
+    for (uint32_t w = 0; w < W; ++w) { const uint32_t bw = sm.bits[e * W + w]; yx += __popc(bw); tp.st_bits[o * W + w] = bw; }
+    tp.st_yx[o] = yx;
+  }
+  return G;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) col_tile_kernel(ColIn in, TileParams tp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_scan[33];
+  __shared__ uint32_t s_flags[4];
+  __shared__ uint32_t s_m, s_pbig;
+  const uint32_t E = tp.ecap, W = tp.W, k = (uint32_t)in.k, tid = threadIdx.x;
+  TileSmem<THREADS> sm;
+  sm.word = (unsigned long long*)smem_raw;
+  sm.rep = sm.word + E;
+  sm.cnt = (uint32_t*)(sm.rep + E);
+  sm.bits = sm.cnt + E;
+  sm.a = sm.bits + (size_t)E * W;
+  sm.b = sm.a + k;
+  sm.c = sm.b + k;
+  sm.soff = sm.c + k;
+  sm.rbase = (uint16_t*)(sm.soff + k + 1);
+  sm.occ = sm.rbase + E;
+  uint32_t kept_total = 0;   // thread 0 only
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_m = atomicAdd(tp.slot_counter, 1u);
+    __syncthreads();
+    const uint32_t m = s_m;
+    if (m >= tp.M) break;
+    const uint32_t p0 = tp.slotpos[m], p1 = tp.slotpos[m + 1];
+    const uint32_t rank0 = tp.P[p0], rank1 = tp.P[p1];
+    const uint32_t n_t = rank1 - rank0;
+    if (n_t == 0) { if (tid == 0) tp.gcount[m] = 0; continue; }
+    for (uint32_t f = tid; f < k; f += THREADS) { sm.a[f] = tp.off[(uint64_t)m * k + f]; sm.b[f] = tp.off[(uint64_t)(m + 1) * k + f]; }
+    uint32_t G = 0;
+    if (n_t <= tp.cap_records) {
+      __syncthreads();
+      G = tile_process<THREADS>(in, tp, sm, n_t, rank0, false, rank0, s_scan, s_flags);
+      if (G == 0xffffffffu) { if (tid == 0) { tp.status[CS_TABLE_OVERFLOW] = 1; tp.gcount[m] = 0; } continue; }
+      if (tid == 0) kept_total += s_flags[0];
+    } else {
+      // the last position of the slot is a pile-up: split it off
+      if (tid == 0) {
+        uint32_t lo = p0, hi = p1;  // last p in [p0,p1) with P[p] < rank1 (the last non-empty position)
+        while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (tp.P[mid] < rank1) lo = mid; else hi = mid; }
+        s_pbig = lo;
+      }
+      __syncthreads();
+      const uint32_t pbig = s_pbig;
+      const uint32_t rb = tp.P[pbig];
+      const int big_pos = (int)pbig + in.pos_lo;
+      for (uint32_t f = tid; f < k; f += THREADS) {  // first record of the slice at the pile-up position
+        uint32_t lo = sm.a[f], hi = sm.b[f];
+        while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (in.pos[mid] >= big_pos) hi = mid; else lo = mid + 1; }
+        sm.c[f] = sm.b[f]; sm.b[f] = lo;
+      }
+      __syncthreads();
+      uint32_t G1 = 0;
+      if (rb > rank0) {
+        G1 = tile_process<THREADS>(in, tp, sm, rb - rank0, rank0, false, rank0, s_scan, s_flags);
+        if (G1 == 0xffffffffu) { if (tid == 0) { tp.status[CS_TABLE_OVERFLOW] = 1; tp.gcount[m] = 0; } continue; }
+        if (tid == 0) kept_total += s_flags[0];
+      }
+      __syncthreads();
+      for (uint32_t f = tid; f < k; f += THREADS) { sm.a[f] = sm.b[f]; sm.b[f] = sm.c[f]; }
+      __syncthreads();
+      const uint32_t G2 = tile_process<THREADS>(in, tp, sm, rank1 - rb, rb, true, (uint64_t)rank0 + G1, s_scan, s_flags);
+      if (G2 == 0xffffffffu) { if (tid == 0) { tp.status[CS_TABLE_OVERFLOW] = 1; tp.gcount[m] = 0; } continue; }
+      if (tid == 0) kept_total += s_flags[0];
+      G = G1 + G2;
+    }
+    if (tid == 0) tp.gcount[m] = G;
+  }
+  if (tid == 0 && kept_total) atomicAdd((unsigned long long*)&tp.status[CS_NKEPT], (unsigned long long)kept_total);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C6: compaction of the staged groups
+// ---------------------------------------------------------------------------------------------------
+struct GcIn { const uint32_t* c; __device__ uint32_t operator()(int64_t i) const { return c[i]; } };
+struct GcOut { uint32_t* b; __device__ void operator()(int64_t i, uint32_t exc, uint32_t) const { b[i] = exc; } };
+
+__global__ void __launch_bounds__(128) col_compact_kernel(TileParams tp, const uint32_t* __restrict__ gbase, uint32_t* __restrict__ o_rep,
+                                                          float* __restrict__ o_yc, uint32_t* __restrict__ o_yx, int32_t* __restrict__ o_yd,
+                                                          uint32_t* __restrict__ o_bits, int64_t capacity) {
+  const uint32_t m = blockIdx.x;
+  const uint32_t G = tp.gcount[m];
+  if (G == 0) return;
+  const uint64_t src = tp.P[tp.slotpos[m]];
+  const uint64_t dst = gbase[m];
+  for (uint32_t r = threadIdx.x; r < G; r += blockDim.x) {
+    if ((int64_t)(dst + r) >= capacity) break;
+    o_rep[dst + r] = tp.st_rep[src + r];
+    o_yc[dst + r] = tp.st_yc[src + r];
+    o_yx[dst + r] = tp.st_yx[src + r];
+    o_yd[dst + r] = 0;
+  }
+  for (uint64_t x = threadIdx.x; x < (uint64_t)G * tp.W; x += blockDim.x) {
+    if ((int64_t)(dst + x / tp.W) >= capacity) break;
+    o_bits[dst * tp.W + x] = tp.st_bits[src * tp.W + x];
+  }
+}
+
+__global__ void col_store_total_kernel(const uint32_t* tot, long long* status) { status[CS_NGROUPS] = *tot; }
+
+constexpr int TILE_THREADS = 1024;
+
+}  // namespace
+
+int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& out, int64_t* n_groups, int64_t* n_kept) {
+  cudaStream_t st = ctx->stream;
+  DevBuf* B = ctx->buf;
+  const int64_t n = g.n; const int k = g.k; const uint32_t W = g.W, S = g.S;
+  // ---- geometry: as many table entries as fit the opt-in shared memory ----
+  const size_t smem_limit = (ctx->smem_optin ? ctx->smem_optin : 232448) - 1024;
+  uint32_t E = 8192;   // region bases are u16 and the match key keeps 13 bits for the entry
+  while (E > 64 && tile_smem_bytes((uint32_t)k, E, W) > smem_limit) E -= 64;
+  if (tile_smem_bytes((uint32_t)k, E, W) > smem_limit) { ctx->set_error("tb_collapse_window: %d samples do not fit the shared-memory group table", k); return 1; }
+  const uint32_t cap_records = (uint32_t)(((uint64_t)(E - 1) * 4) / 5);   // floor(1.25*n)+1 <= E
+  const uint32_t T = cap_records / 2;
+  if (T < 8) { ctx->set_error("tb_collapse_window: %d samples leave no room for a shared-memory tile", k); return 1; }
+  const uint32_t M = (uint32_t)((n + T - 1) / T);
+
+  TB_CUDA(B[XB_SLOTPOS].ensure(sizeof(uint32_t) * ((size_t)M + 2)));
+  TB_CUDA(B[XB_OFF].ensure(sizeof(uint32_t) * ((size_t)M + 1) * k));
+  TB_CUDA(B[XB_GCOUNT].ensure(sizeof(uint32_t) * ((size_t)M + 2)));
+  TB_CUDA(B[XB_GBASE].ensure(sizeof(uint32_t) * ((size_t)M + 2)));
+  TB_CUDA(B[XB_ST_REP].ensure(sizeof(uint32_t) * n));
+  TB_CUDA(B[XB_ST_YC].ensure(sizeof(float) * n));
+  TB_CUDA(B[XB_ST_YX].ensure(sizeof(uint32_t) * n));
+  TB_CUDA(B[XB_ST_BITS].ensure(sizeof(uint32_t) * (size_t)n * W));
+  TB_CUDA(B[XB_WORK].ensure(256));
+  TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks((int64_t)M + 2) + 8) * sizeof(uint64_t)));
+
+  // ---- C3, C4 ----
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[5], st));
+  col_slotpos_kernel<<<tb_grid_for((int64_t)M + 1, 256), 256, 0, st>>>(g.P, S, T, M, B[XB_SLOTPOS].as<uint32_t>());
+  const uint64_t off_total = ((uint64_t)M + 1) * k;
+  col_off_init_kernel<<<tb_grid_for((int64_t)off_total, 256), 256, 0, st>>>(B[XB_OFF].as<uint32_t>(), g.d_runoff, k, off_total);
+  col_off_kernel<<<tb_grid_for(n, 256), 256, 0, st>>>(in, g.d_runoff, g.P, T, B[XB_OFF].as<uint32_t>(), g.d_status);
+  col_off_heads_kernel<<<tb_grid_for(k, 128), 128, 0, st>>>(in, g.d_runoff, g.P, T, B[XB_OFF].as<uint32_t>());
+  ctx->launches += 4;
+  // ---- C5 ----
+  TileParams tp; memset(&tp, 0, sizeof(tp));
+  tp.T = T; tp.M = M; tp.ecap = E; tp.W = W; tp.cap_records = cap_records; tp.P = g.P; tp.slotpos = B[XB_SLOTPOS].as<uint32_t>(); tp.off = B[XB_OFF].as<uint32_t>();
+  tp.gcount = B[XB_GCOUNT].as<uint32_t>(); tp.st_rep = B[XB_ST_REP].as<uint32_t>(); tp.st_yc = B[XB_ST_YC].as<float>();
+  tp.st_yx = B[XB_ST_YX].as<uint32_t>(); tp.st_bits = B[XB_ST_BITS].as<uint32_t>(); tp.status = g.d_status; tp.seed = 0x243F6A8885A308D3ULL;
+  tp.slot_counter = B[XB_WORK].as<unsigned int>();
+  TB_CUDA(cudaMemsetAsync(tp.slot_counter, 0, 64, st));
+  const size_t smem = tile_smem_bytes((uint32_t)k, E, W);
+  TB_CUDA(cudaFuncSetAttribute(col_tile_kernel<TILE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
+  const unsigned grid = (unsigned)(M < (uint32_t)ctx->sm_count ? M : (uint32_t)ctx->sm_count);
+  col_tile_kernel<TILE_THREADS><<<grid, TILE_THREADS, smem, st>>>(in, tp);
+  ctx->launches++;
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[1], st));
+  // ---- C6 ----
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[6], st));
+  TB_CUDA((tb_device_scan<OpSumU32>(ctx, GcIn{tp.gcount}, (int64_t)M, B[XB_AGG].as<uint32_t>(), GcOut{B[XB_GBASE].as<uint32_t>()})));
+  col_store_total_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(M), g.d_status);
+  ctx->launches++;
+  long long* h_status = ctx->pinned[0].as<long long>();
+  TB_CUDA(cudaMemcpyAsync(h_status, g.d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  if (ctx->profiling) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_ms[0] = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[0]) == cudaSuccess) ctx->last_ms[3] = ms;
+  }
+  if (h_status[CS_ERR] == ERR_UNSORTED) { ctx->set_error("tb_collapse_window: run not coordinate-sorted at record %lld", h_status[CS_ERRIDX]); return 1; }
+  if (h_status[CS_TABLE_OVERFLOW]) return 2;
+  const int64_t G = h_status[CS_NGROUPS];
+  *n_groups = G; *n_kept = h_status[CS_NKEPT];
+  if (G > out.capacity) { ctx->set_error("tb_collapse_window: output capacity %lld < %lld groups", (long long)out.capacity, (long long)G); return 1; }
+  if (G == 0) return 0;
+  TB_CUDA(B[XB_BITS].ensure(sizeof(uint32_t) * (size_t)G * W));
+  out.bits = B[XB_BITS].as<uint32_t>();
+  col_compact_kernel<<<M, 128, 0, st>>>(tp, B[XB_GBASE].as<uint32_t>(), out.rep, out.yc, out.yx, out.yd, out.bits, G);
+  ctx->launches++;
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[7], st));
+  return 0;
+}

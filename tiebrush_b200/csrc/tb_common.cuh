@@ -70,6 +70,7 @@ struct tb_ctx {
   int profiling = 0;
   float last_ms[16] = {};   // per-stage device times of the last call (see tb_last_kernel_ms)
   int64_t launches = 0;
+  int last_path = 0;        // front end of the last collapse call: 0 tile, 1 ordered (by options), 2 ordered (table overflow fallback)
   std::string err;
   DevBuf buf[TB_NBUF];   // workspace slots (see the enum in each pipeline)
   DevBuf in_stage[20];   // device copies of host input arrays
@@ -124,8 +125,10 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 template <class Op>
 __device__ __forceinline__ typename Op::T tb_block_reduce(typename Op::T v, typename Op::T* s_warp /*[32]*/) {
   typedef typename Op::T T;
+  // ascending distances keep the operands in element order (lane l ends with v_l + ... + v_{l+2d-1}), which matters for
+  // non-commutative operators such as the segmented maximum; lane 0 holds the warp total
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
+  for (int d = 1; d < 32; d <<= 1) {
     T o = tb_shfl_down(v, d);
     v = Op::combine(v, o);
   }
