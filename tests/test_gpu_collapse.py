@@ -33,15 +33,24 @@ def test_collapse_merged(case):
     H.assert_collapse_equal(H.run_collapse(gpu_collapse, files, opts, fm), exp, case)
 
 
+@pytest.fixture(params=["par", "seq"])
+def yd_path(request, monkeypatch):
+    """Both YD implementations: the parallel formulation (frontier + link bitmaps) and the sequential segment lists."""
+    monkeypatch.setenv("TB_YD_PATH", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("mode", [0, 2, 3])
 @pytest.mark.parametrize("n_tx,k,reads", [(40, 12, 20000), (2000, 40, 5000), (3, 5, 30000)])
-def test_collapse_synthetic_vs_oracle(mode, n_tx, k, reads):
+def test_collapse_synthetic_vs_oracle(mode, n_tx, k, reads, yd_path):
     """Seeded synthetic cohorts (deep pile-ups when n_tx is tiny) against the oracle, bit for bit."""
     from oracle import oracle
-    from tiebrush_b200 import synth
+    from tiebrush_b200 import api, synth
     cols, run_off, pr = synth.cohort_window(k, reads, seed=3, n_tx=n_tx, device="cpu")
     host = synth.to_host(cols)
-    got = gpu_collapse(host, run_off, mode=mode)
+    with api.Context(device=0, n_samples=k, mode=mode) as ctx:
+        got = ctx.collapse_window(host, run_off)
+        assert ctx.last_yd_path() == (0 if yd_path == "par" else 1)
     exp = oracle.collapse(host, run_off, mode=mode)
     assert got["n_kept"] == exp["n_kept"]
     for key in ("rep_index", "yc", "yx", "yd"):
@@ -127,6 +136,45 @@ def test_collapse_pileup_position_single_mode():
     assert got["n_kept"] == exp["n_kept"]
     for key in ("rep_index", "yc", "yx", "yd"):
         assert np.array_equal(np.asarray(got[key]), exp[key]), key
+
+
+def test_yd_many_exons_and_degenerate_exons():
+    """Representatives with more than three exons (decoded from the CIGAR by the YD kernels) stay on the parallel YD
+    path; a degenerate exon (N directly followed by N, GSam.cpp:376-388) sends the window to the sequential lists."""
+    from oracle import oracle
+    from tiebrush_b200 import api
+    rng = np.random.default_rng(8)
+    k, per = 4, 3000
+    n = k * per
+
+    def make(degenerate):
+        cigs, pos = [], []
+        for i in range(n):
+            nb = int(rng.integers(1, 7))
+            words = []
+            for b in range(nb):
+                words.append((int(rng.integers(5, 40)) << 4) | 0)
+                if b < nb - 1:
+                    words.append((int(rng.choice([1, 30, 80, 200])) << 4) | 3)
+                    if degenerate and rng.random() < 0.02:
+                        words.append((int(rng.integers(1, 9)) << 4) | 3)
+            cigs.append(words); pos.append(int(rng.integers(1000, 3000)))
+        pos = np.asarray(pos, np.int32)
+        order = np.concatenate([f * per + np.argsort(pos[f * per:(f + 1) * per], kind="stable") for f in range(k)])
+        off = np.zeros(n + 1, np.uint32); off[1:] = np.cumsum([len(cigs[i]) for i in order])
+        cigar = np.asarray([w for i in order for w in cigs[i]], np.uint32)
+        return dict(pos=pos[order], flag=np.zeros(n, np.uint16), mapq=np.full(n, 60, np.uint8),
+                    strand=rng.choice(np.frombuffer(b"+-.", np.uint8), n), nh=np.ones(n, np.uint16), cig_off=off, cigar=cigar)
+
+    run_off = np.arange(k + 1, dtype=np.int64) * per
+    for degenerate in (False, True):
+        cols = make(degenerate)
+        with api.Context(device=0, n_samples=k) as ctx:
+            got = ctx.collapse_window(cols, run_off)
+            assert ctx.last_yd_path() == (1 if degenerate else 0)
+        exp = oracle.collapse(cols, run_off)
+        for key in ("rep_index", "yc", "yx", "yd"):
+            assert np.array_equal(np.asarray(got[key]), exp[key]), (degenerate, key)
 
 
 def test_collapse_device_resident_properties():

@@ -73,6 +73,10 @@ class Context:
     def launch_count(self):
         return int(self.lib.tb_launch_count(self.h))
 
+    def last_yd_path(self):
+        """0 parallel YD formulation, 1 sequential segment lists."""
+        return int(self.lib.tb_last_yd_path(self.h))
+
     def last_path(self):
         """0 tile path, 1 ordered path (by options), 2 ordered path (table-overflow fallback)."""
         return int(self.lib.tb_last_path(self.h))

@@ -91,7 +91,7 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
   const uint32_t W = (uint32_t)((k + 31) / 32);
   const uint32_t S = in.span;
   TB_CUDA(B[XB_STATUS].ensure(sizeof(int64_t) * 16));
-  TB_CUDA(ctx->pinned[0].ensure(sizeof(int64_t) * 16 + (size_t)k + 64));
+  TB_CUDA(ctx->pinned[0].ensure(1024));
   long long* d_status = B[XB_STATUS].as<long long>();
   long long* h_status = ctx->pinned[0].as<long long>();
   memset(h_status, 0, sizeof(int64_t) * 16); h_status[CS_ERRIDX] = -1;

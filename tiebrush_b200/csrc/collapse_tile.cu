@@ -118,7 +118,7 @@ struct TileSmem {
 };
 
 static size_t tile_smem_bytes(uint32_t k, uint32_t E, uint32_t W) {
-  return (size_t)E * (8 + 8 + 4 + 4 * (size_t)W + 2 + 2) + (size_t)(4 * k + 1) * 4 + 64;
+  return (size_t)E * (8 + 8 + 4 + 4 * (size_t)W + 2 + 2) + (size_t)(6 * k + 1) * 4 + 64;
 }
 
 // 64-bit epilogue sort key: strand(2) | ref_len(30) | key length(8, saturated) | first key word, byte order of memcmp (24).
@@ -146,6 +146,17 @@ __device__ unsigned long long tile_sort_key(const ColIn& in, uint32_t o, unsigne
   return ((unsigned long long)sc << 62) | ((unsigned long long)(reflen & 0x3fffffffu) << 32) | ((unsigned long long)len8 << 24) | w24;
 }
 
+// is record i (own CIGAR range [c0,c1)) the same alignment as the table owner o? Same position by construction, same
+// strand by the tag. The default mode is compared inline; the other modes go through the general comparator.
+__device__ __forceinline__ bool tile_same_key(const ColIn& in, uint32_t i, uint32_t c0, uint32_t c1, uint32_t o) {
+  if (in.mode != TB_MODE_CIGAR) return tb_mode_cmp(in, i, o) == 0;
+  const uint32_t o0 = in.cig_off[o], o1 = in.cig_off[o + 1];
+  const uint32_t nc = c1 - c0;
+  if (o1 - o0 != nc) return false;
+  for (uint32_t q = 0; q < nc; ++q) if (in.cigar[c0 + q] != in.cigar[o0 + q]) return false;
+  return true;
+}
+
 template <int THREADS>
 __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem<THREADS>& sm, uint32_t n_sub, uint32_t rankbase, bool single,
                                  uint64_t outbase, uint32_t* s_scan, volatile uint32_t* s_flags /*[0]=kept [1]=overflow [2]=ngroups*/) {
@@ -168,7 +179,11 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
   uint32_t E_used = single ? E : ((5u * n_sub) >> 2) + 1u;
   if (E_used > E) E_used = E;
   for (uint32_t s = tid; s < E_used; s += THREADS) { sm.word[s] = EMPTY64; sm.rep[s] = EMPTY64; sm.cnt[s] = 0; }
-  for (uint32_t s = tid; s < E_used * W; s += THREADS) sm.bits[s] = 0;
+  {  // bitsets: 16-byte stores (the array starts 16-byte aligned: E is a multiple of 64)
+    uint4* b4 = reinterpret_cast<uint4*>(sm.bits);
+    const uint32_t n4 = (E_used * W + 3) >> 2;
+    for (uint32_t s = tid; s < n4; s += THREADS) b4[s] = make_uint4(0u, 0u, 0u, 0u);
+  }
   if (tid == 0) { s_flags[0] = 0; s_flags[1] = 0; s_flags[2] = 0; }
   __syncthreads();
 
@@ -176,14 +191,15 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
   const uint32_t j0 = (uint32_t)(((unsigned long long)n_sub * warp) / NW), j1 = (uint32_t)(((unsigned long long)n_sub * (warp + 1)) / NW);
   uint32_t carry_f = 0xffffffffu; int carry_pos = INT_MIN; int carry_max = 0;
   uint32_t my_kept = 0;
+  uint32_t f_lo = 0;   // file of the first record of the next step (warp-uniform)
   if (j0 < j1) {
-    // look-back: if the range starts inside a (file,position) run, the running maximum of the part before it is needed
     uint32_t lo = 0, hi = k;
     while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.soff[mid] <= j0) lo = mid; else hi = mid; }
-    const uint32_t f0 = lo;
-    if (j0 > sm.soff[f0]) {
-      const uint32_t slo = sm.a[f0];
-      const uint32_t i0 = slo + (j0 - sm.soff[f0]);
+    f_lo = lo;
+    // look-back: if the range starts inside a (file,position) run, the running maximum of the part before it is needed
+    if (j0 > sm.soff[f_lo]) {
+      const uint32_t slo = sm.a[f_lo];
+      const uint32_t i0 = slo + (j0 - sm.soff[f_lo]);
       const int p = in.pos[i0];
       if (in.pos[i0 - 1] == p) {
         int mx = 0;
@@ -200,7 +216,7 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-        carry_f = f0; carry_pos = p; carry_max = mx;
+        carry_f = f_lo; carry_pos = p; carry_max = mx;
       }
     }
   }
@@ -209,17 +225,16 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
     if (single && s_flags[2] > glimit) { s_flags[1] = 1; break; }   // warp-uniform (broadcast read)
     const uint32_t j = jb + lane;
     const bool valid = j < j1;
-    uint32_t f = 0xfffffffeu, i = 0; int pos = INT_MIN + 1 + (int)lane, reflen = 0; uint64_t kh = 0; bool pass = false; unsigned sc = 0;
+    uint32_t f = 0xfffffffeu, i = 0, c0 = 0, c1 = 0, h1 = 0, h2 = 0; int pos = INT_MIN + 1 + (int)lane, reflen = 0; bool pass = false; unsigned sc = 0;
     if (valid) {
-      uint32_t lo = 0, hi = k;  // last f with soff[f] <= j
-      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.soff[mid] <= j) lo = mid; else hi = mid; }
-      f = lo;
+      f = f_lo;                                   // slices are contiguous in j: walk forward from the step's first file
+      while (sm.soff[f + 1] <= j) ++f;
       i = sm.a[f] + (j - sm.soff[f]);
       pos = in.pos[i];
-      const uint32_t c0 = in.cig_off[i], c1 = in.cig_off[i + 1];
+      c0 = in.cig_off[i]; c1 = in.cig_off[i + 1];
       const uint16_t fl = in.flag[i]; const uint8_t mq = in.mapq[i]; const uint16_t nh = in.nh[i];
       sc = tb_strand_code(in.strand[i]);
-      tb_parse_record(in, i, pos, c0, c1, reflen, kh);
+      tb_parse_record32(in, i, pos, c0, c1, reflen, h1, h2);
       pass = tb_passes_options(in, fl, mq, nh);
     }
     // segmented inclusive max-scan of ref_len over (file,position) runs == the running max that orders the reference's
@@ -230,12 +245,13 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
     int v = valid ? reflen : 0;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const int v2 = __shfl_up_sync(0xffffffffu, v, d), h2 = __shfl_up_sync(0xffffffffu, h, d);
-      if ((int)lane >= d) { if (!h) v = max(v, v2); h |= h2; }
+      const int v2 = __shfl_up_sync(0xffffffffu, v, d), h2s = __shfl_up_sync(0xffffffffu, h, d);
+      if ((int)lane >= d) { if (!h) v = max(v, v2); h |= h2s; }
     }
     if (!h) v = max(v, carry_max);
     const int Erel = v;
     carry_f = __shfl_sync(0xffffffffu, f, 31); carry_pos = __shfl_sync(0xffffffffu, pos, 31); carry_max = __shfl_sync(0xffffffffu, Erel, 31);
+    f_lo = carry_f;   // only meaningful while lane 31 is valid, i.e. while another step follows
 
     uint32_t s = 0;
     if (pass) {
@@ -246,9 +262,8 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
         const uint32_t Pa = tp.P[rel] - rankbase, Pb = tp.P[rel + 1] - rankbase;
         base = (5u * Pa) >> 2; size = ((5u * Pb) >> 2) - base;
       }
-      const unsigned long long hh = tb_mix64(kh ^ ((unsigned long long)(uint32_t)reflen * 0xD6E8FEB86659FD93ULL) ^ tp.seed);
-      const uint32_t tag = (sc << 30) | (uint32_t)(hh >> 34);
-      s = base + __umulhi((uint32_t)hh, size);
+      const uint32_t tag = (sc << 30) | (tb_mix32(h1 ^ ((uint32_t)reflen * 0x9E3779B1u) ^ (uint32_t)tp.seed) >> 2);
+      s = base + __umulhi(tb_mix32(h2 + (uint32_t)reflen), size);
       const unsigned long long mine = ((unsigned long long)tag << 32) | i;
       bool placed = false;
       for (uint32_t t = 0; t < size; ++t) {
@@ -258,8 +273,8 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
           if (w == EMPTY64) { sm.rbase[s] = (uint16_t)base; atomicAdd((uint32_t*)&s_flags[2], 1u); placed = true; break; }
         }
         if ((uint32_t)(w >> 32) == tag) {
-          const uint32_t o = (uint32_t)w;  // owner: compare the real keys (same position by construction, same strand by the tag)
-          if (o == i || tb_mode_cmp(in, i, o) == 0) { placed = true; break; }
+          const uint32_t o = (uint32_t)w;  // owner: compare the real keys
+          if (o == i || tile_same_key(in, i, c0, c1, o)) { placed = true; break; }
         }
         if (++s == base + size) s = base;
       }
@@ -300,25 +315,25 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
     sm.rep[e] = ((unsigned long long)o << 32) | (uint32_t)sm.rep[e];
   }
   __syncthreads();
-  // ---- epilogue C: rank inside the position, write the groups in final order ----
+  // ---- epilogue C: rank inside the position (one walk to the left, one to the right), write in final order ----
   for (uint32_t r = tid; r < G; r += THREADS) {
     const uint32_t e = sm.occ[r];
-    uint32_t a = r, b = r + 1;
-    if (single) { a = 0; b = G; }
-    else {
-      const uint16_t rb = sm.rbase[e];
-      while (a > 0 && sm.rbase[sm.occ[a - 1]] == rb) --a;
-      while (b < G && sm.rbase[sm.occ[b]] == rb) ++b;
-    }
+    const uint16_t rb = sm.rbase[e];
     const unsigned long long ki = sm.word[e];
     const uint32_t oi = (uint32_t)(sm.rep[e] >> 32);
-    uint32_t rank = 0;
-    for (uint32_t q = a; q < b; ++q) {
-      if (q == r) continue;
-      const uint32_t eq = sm.occ[q];
+    uint32_t rank = 0, a = r;
+    while (a > 0) {
+      const uint32_t eq = sm.occ[a - 1];
+      if (!single && sm.rbase[eq] != rb) break;
+      --a;
       const unsigned long long kq = sm.word[eq];
-      if (kq < ki) ++rank;
-      else if (kq == ki) { if (tb_mode_cmp(in, (uint32_t)(sm.rep[eq] >> 32), oi) < 0) ++rank; }
+      if (kq < ki || (kq == ki && tb_mode_cmp(in, (uint32_t)(sm.rep[eq] >> 32), oi) < 0)) ++rank;
+    }
+    for (uint32_t q = r + 1; q < G; ++q) {
+      const uint32_t eq = sm.occ[q];
+      if (!single && sm.rbase[eq] != rb) break;
+      const unsigned long long kq = sm.word[eq];
+      if (kq < ki || (kq == ki && tb_mode_cmp(in, (uint32_t)(sm.rep[eq] >> 32), oi) < 0)) ++rank;
     }
     const uint64_t o = outbase + a + rank;
     tp.st_rep[o] = (uint32_t)sm.rep[e];
@@ -330,39 +345,52 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
   return G;
 }
 
+// slot descriptor handed from the prefetching thread to the block
+struct SlotMeta { uint32_t m, rank0, rank1, p0, p1; };
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) col_tile_kernel(ColIn in, TileParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_scan[33];
   __shared__ uint32_t s_flags[4];
-  __shared__ uint32_t s_m, s_pbig;
+  __shared__ SlotMeta s_meta[2];
+  __shared__ uint32_t s_pbig;
   const uint32_t E = tp.ecap, W = tp.W, k = (uint32_t)in.k, tid = threadIdx.x;
   TileSmem<THREADS> sm;
   sm.word = (unsigned long long*)smem_raw;
   sm.rep = sm.word + E;
   sm.cnt = (uint32_t*)(sm.rep + E);
   sm.bits = sm.cnt + E;
-  sm.a = sm.bits + (size_t)E * W;
-  sm.b = sm.a + k;
-  sm.c = sm.b + k;
+  uint32_t* ab = sm.bits + (size_t)E * W;          // [2][2k] double-buffered slice bounds (next slot's are prefetched)
+  sm.c = ab + 4 * (size_t)k;
   sm.soff = sm.c + k;
   sm.rbase = (uint16_t*)(sm.soff + k + 1);
   sm.occ = sm.rbase + E;
   uint32_t kept_total = 0;   // thread 0 only
-  for (;;) {
+  auto fetch_meta = [&](SlotMeta& d) {   // one thread: claim the next slot and read its geometry
+    SlotMeta t; t.m = atomicAdd(tp.slot_counter, 1u); t.rank0 = t.rank1 = t.p0 = t.p1 = 0;
+    if (t.m < tp.M) { t.p0 = tp.slotpos[t.m]; t.p1 = tp.slotpos[t.m + 1]; t.rank0 = tp.P[t.p0]; t.rank1 = tp.P[t.p1]; }
+    d = t;
+  };
+  auto load_bounds = [&](const SlotMeta& d, uint32_t* dst) {   // all threads: per-file slices of a slot
+    if (d.m < tp.M) for (uint32_t f = tid; f < k; f += THREADS) { dst[f] = tp.off[(uint64_t)d.m * k + f]; dst[k + f] = tp.off[(uint64_t)(d.m + 1) * k + f]; }
+  };
+  if (tid == 0) { fetch_meta(s_meta[0]); fetch_meta(s_meta[1]); }
+  __syncthreads();
+  load_bounds(s_meta[0], ab);
+  for (uint32_t it = 0;; ++it) {
     __syncthreads();
-    if (tid == 0) s_m = atomicAdd(tp.slot_counter, 1u);
-    __syncthreads();
-    const uint32_t m = s_m;
-    if (m >= tp.M) break;
-    const uint32_t p0 = tp.slotpos[m], p1 = tp.slotpos[m + 1];
-    const uint32_t rank0 = tp.P[p0], rank1 = tp.P[p1];
+    const SlotMeta cur = s_meta[it & 1], nxt = s_meta[(it + 1) & 1];
+    if (cur.m >= tp.M) break;
+    sm.a = ab + (size_t)(it & 1) * 2 * k; sm.b = sm.a + k;
+    load_bounds(nxt, ab + (size_t)((it + 1) & 1) * 2 * k);   // overlaps with this slot's work
+    __syncthreads();                                          // everybody has read s_meta[it&1]
+    if (tid == THREADS - 1) fetch_meta(s_meta[it & 1]);       // slot it+2; its latency hides behind this slot
+    const uint32_t m = cur.m, rank0 = cur.rank0, rank1 = cur.rank1, p0 = cur.p0, p1 = cur.p1;
     const uint32_t n_t = rank1 - rank0;
     if (n_t == 0) { if (tid == 0) tp.gcount[m] = 0; continue; }
-    for (uint32_t f = tid; f < k; f += THREADS) { sm.a[f] = tp.off[(uint64_t)m * k + f]; sm.b[f] = tp.off[(uint64_t)(m + 1) * k + f]; }
     uint32_t G = 0;
     if (n_t <= tp.cap_records) {
-      __syncthreads();
       G = tile_process<THREADS>(in, tp, sm, n_t, rank0, false, rank0, s_scan, s_flags);
       if (G == 0xffffffffu) { if (tid == 0) { tp.status[CS_TABLE_OVERFLOW] = 1; tp.gcount[m] = 0; } continue; }
       if (tid == 0) kept_total += s_flags[0];

@@ -1,63 +1,117 @@
 // collapse_yd.cu — the YD tag: GSegList::processRead / mergeRead (src/tiebrush.cpp:151-250) driven by flushPData
 // (src/tiebrush.cpp:512-524) over the collapsed groups in output order.
 //
-// The reference keeps, per (sample, strand list), a linked list of merged exon segments; for every emitted group and
-// every sample that contributed to it, processRead returns the distance from the read start back to the start of the
-// segment that reaches it, and YD = max over those samples (and over YD tags carried by TieBrush-made inputs).
-// The list is a sequential state machine with binding quirks (touching segments are not merged; when the merge cursor
-// runs off the list the current and all later exons are dropped), so it is emulated literally.
+// The reference keeps, per (sample, strand list) — a "chain" — a linked list of merged exon segments; for every emitted
+// group and every sample that contributed to it, processRead returns the distance d from the read start back to the
+// start of the segment that reaches it, and YD = max of d over those samples (and over YD tags carried by
+// TieBrush-made inputs). The list is a sequential state machine with binding quirks (touching segments are not merged;
+// when the merge cursor runs off the list the current and all later exons are silently dropped).
 //
-// A chain = (sample s, strand list): the groups, in output order, that contain s and whose strand feeds the list
-// ('+','.' -> forward; '-','.' -> reverse). Chains are independent (tiebrush.cpp:512-521). Stages:
-//   Y1  one 32-byte descriptor per group (start, strand, first three exons of the representative) + its end
-//   Y2-Y4  member lists of all 2k chains by a stable counting scatter over the sample bitsets
-//   Y5  every chain is cut where a member starts beyond every earlier end of its chain: there processRead finds only dead
-//       nodes (d == 0 => clearTo(prev), prev = last node) and leaves exactly the read's own exons, so the pieces
-//       ("sub-chains") are independent. Segmented prefix max over the member array (chain ids ascend).
-//   Y6  persistent warps pull batches of 32 sub-chains: short ones run one per LANE (lists in shared memory, [node][lane]
-//       layout), long ones are walked by the whole warp (lanes prefetch 32 descriptors, lane 0 runs the state machine).
-// Nodes lying before `prev` can never be touched again before they are freed (disjoint, sorted, ends < read start), so
-// they are dropped eagerly; results are unchanged. If a list outgrows shared memory the launch is repeated with lists in
-// global memory.
+// PARALLEL FORMULATION (default). Reading the list code closely gives two facts (checked against a literal model of the
+// list on randomised chains, and through the oracle in tests/):
+//   (1) which exons enter the list depends on ONE scalar per chain, the frontier E = largest end of any exon kept so
+//       far: a read at x with E < x finds only dead nodes, empties the list and appends all its exons ("bulk"); otherwise
+//       exon j >= 2 is kept iff its start <= max(E, ends of the read's earlier kept exons) — else the cursor runs off the
+//       list and it and all later exons are dropped. E never decreases.
+//   (2) the list is the interval union of the kept exons, and links left of x are final when the read at x arrives
+//       (later reads start at >= x). With link[p] = "some kept exon contains p and p+1", d = the number of consecutive
+//       set links ending at x-1 (0 if link[x-1] is clear). Reads sharing a start get the same d (the reference's
+//       last_pos cache).
+//   So: Y1 group descriptors + union bitmap U of all exon positions; Y2 rank(U) gives compact coordinates (runs of links
+//   are preserved: a link at p implies p+1 is covered); Y3-Y5 chain member lists by a stable counting scatter over the
+//   sample bitsets, cut into independent sub-chains where a member starts beyond every earlier end of its chain;
+//   Y6 the frontier recurrence per sub-chain (one scalar, lane-parallel; long sub-chains are walked by a whole warp with
+//   prefetch) -> kept-exon count per member; Y7 kept exons OR their links into the chain's bitmap; Y8 prefix max of
+//   "last clear link" over 512-bit blocks; Y9 one lookup per member, atomicMax into the group.
+//
+// SEQUENTIAL FALLBACK. The literal list (sorted arrays in shared memory, dead nodes dropped eagerly) per sub-chain:
+// used when a representative has a degenerate exon (N directly followed by N), more than 255 exons, an
+// exon reaching beyond the union bitmap, or when TB_YD_PATH=seq is set (tests run both).
+#include <stdlib.h>
 #include "collapse_internal.cuh"
 
 namespace {
 
 constexpr int YD_INLINE_EX = 3;   // exons kept in the descriptor; longer chains are decoded from the CIGAR
-struct __align__(16) GDesc {      // 32 bytes
-  int32_t start;                  // 1-based start of the representative (== first exon start)
+struct __align__(16) GDesc {      // 32 bytes; coordinates 1-based genomic (desc) or compact (cdesc)
+  int32_t start;                  // start of the representative (== first exon start)
   uint32_t meta;                  // n_exons (low 16) | strand char << 16
-  int32_t e[6];                   // ex0.end, ex1.start, ex1.end, ex2.start, ex2.end, rep record index
+  int32_t e0, s1, e1, s2, e2;     // first three exons: [start,e0] [s1,e1] [s2,e2]
+  int32_t zend;                   // end of the last exon
 };
+enum { YS_FALLBACK = 8, YS_LC = 9 };   // status slots used by this file (CS_* occupy 0..6)
+constexpr int64_t YD_U_SLACK = 1 << 22;  // union bitmap extends this far beyond the last start position
 
+__device__ __forceinline__ void yd_set_bits32(uint32_t* bm, int64_t lo, int64_t hi) {  // set bits [lo,hi]
+  for (int64_t w = lo >> 5; w <= (hi >> 5); ++w) {
+    const int b0 = w == (lo >> 5) ? (int)(lo & 31) : 0, b1 = w == (hi >> 5) ? (int)(hi & 31) : 31;
+    const uint32_t mask = (b1 == 31 ? 0xffffffffu : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
+    if ((bm[w] & mask) != mask) atomicOr(&bm[w], mask);
+  }
+}
+__device__ __forceinline__ void yd_set_bits64(unsigned long long* bm, int64_t lo, int64_t hi) {  // set bits [lo,hi]
+  for (int64_t w = lo >> 6; w <= (hi >> 6); ++w) {
+    const int b0 = w == (lo >> 6) ? (int)(lo & 63) : 0, b1 = w == (hi >> 6) ? (int)(hi & 63) : 63;
+    const unsigned long long mask = (b1 == 63 ? ~0ULL : ((1ULL << (b1 + 1)) - 1ULL)) & ~((1ULL << b0) - 1ULL);
+    if ((bm[w] & mask) != mask) atomicOr(&bm[w], mask);
+  }
+}
+
+// Y1: descriptor per group (genomic coordinates), group end, strand; union bitmap of exon positions (bit = coordinate - ubase)
 __global__ void __launch_bounds__(256) yd_desc_kernel(ColIn in, const uint32_t* __restrict__ rep, int64_t G, GDesc* __restrict__ desc,
-                                                      uint32_t* __restrict__ gend, uint8_t* __restrict__ gstrand) {
+                                                      uint32_t* __restrict__ gend, uint8_t* __restrict__ gstrand, uint32_t* __restrict__ U,
+                                                      int64_t ubits, long long* __restrict__ status) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   const uint32_t r = rep[g];
   const int pos = in.pos[r];
+  const int ubase = in.pos_lo + 1;
   ExonIter it; it.init(in.cigar, in.cig_off[r], in.cig_off[r + 1], pos);
-  GDesc d; d.start = pos + 1;
-  int s, e, ne = 0;
-#pragma unroll
-  for (int q = 0; q < 6; ++q) d.e[q] = 0;
+  GDesc d; d.start = pos + 1; d.e0 = d.s1 = d.e1 = d.s2 = d.e2 = 0;
+  int s, e, ne = 0; bool bad = false;
   while (it.next(s, e)) {
-    if (ne == 0) d.e[0] = e;
-    else if (ne == 1) { d.e[1] = s; d.e[2] = e; }
-    else if (ne == 2) { d.e[3] = s; d.e[4] = e; }
+    if (ne == 0) d.e0 = e;
+    else if (ne == 1) { d.s1 = s; d.e1 = e; }
+    else if (ne == 2) { d.s2 = s; d.e2 = e; }
+    if (e < s) bad = true;                                   // degenerate exon (N directly after N)
+    else if (U) { if ((int64_t)e - ubase >= ubits) bad = true; else yd_set_bits32(U, (int64_t)s - ubase, (int64_t)e - ubase); }
     ++ne;
   }
-  d.e[5] = (int32_t)r;
+  if (ne > 255) bad = true;
+  if (bad) status[YS_FALLBACK] = 1;
   const uint8_t sc = in.strand[r];
   d.meta = (uint32_t)(ne > 0xffff ? 0xffff : ne) | ((uint32_t)sc << 16);
+  d.zend = pos + it.l;
   desc[g] = d;
   gend[g] = (uint32_t)(pos + it.l);
   gstrand[g] = sc;
 }
 
-constexpr int YD_BLOCK = 1024;   // groups per counting block
+// Y2: compact coordinates. rank(p) = number of covered positions before p.
+struct UPopIn { const uint32_t* U; __device__ uint32_t operator()(int64_t w) const { return (uint32_t)__popc(U[w]); } };
+struct UPopOut { uint32_t* r; __device__ void operator()(int64_t w, uint32_t exc, uint32_t) const { r[w] = exc; } };
+__device__ __forceinline__ int32_t yd_rank(const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre, int64_t bit) {
+  const int64_t w = bit >> 5;
+  return (int32_t)(rankpre[w] + (uint32_t)__popc(U[w] & ((1u << (bit & 31)) - 1u)));
+}
+__global__ void __launch_bounds__(256) yd_compact_kernel(const GDesc* __restrict__ desc, int64_t G, const uint32_t* __restrict__ U,
+                                                         const uint32_t* __restrict__ rankpre, int ubase, GDesc* __restrict__ cdesc, uint32_t* __restrict__ cend) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  GDesc d = desc[g];
+  const int ne = (int)(d.meta & 0xffffu);
+  d.start = yd_rank(U, rankpre, (int64_t)d.start - ubase);
+  d.e0 = yd_rank(U, rankpre, (int64_t)d.e0 - ubase);
+  if (ne >= 2) { d.s1 = yd_rank(U, rankpre, (int64_t)d.s1 - ubase); d.e1 = yd_rank(U, rankpre, (int64_t)d.e1 - ubase); }
+  if (ne >= 3) { d.s2 = yd_rank(U, rankpre, (int64_t)d.s2 - ubase); d.e2 = yd_rank(U, rankpre, (int64_t)d.e2 - ubase); }
+  d.zend = yd_rank(U, rankpre, (int64_t)d.zend - ubase);
+  cdesc[g] = d;
+  cend[g] = (uint32_t)d.zend;
+}
 
-// Y2: members per (block of groups, chain). One warp per (block, 32-sample word).
+// ---- Y3-Y5: chain member lists ---------------------------------------------------------------------------------------
+constexpr int YD_BLOCK = 1024;   // groups per counting block
+// members per (chain, block of groups); chain c = side*k + sample, table is chain-major: blkcnt[c*nblk + b]
 __global__ void __launch_bounds__(128) yd_count_kernel(const uint32_t* __restrict__ bits, uint32_t W, int k, int64_t G, const uint8_t* __restrict__ gstrand,
                                                       uint32_t* __restrict__ blkcnt, int64_t nblk) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -79,31 +133,20 @@ __global__ void __launch_bounds__(128) yd_count_kernel(const uint32_t* __restric
     }
   }
   const int s = (int)(w * 32 + lane);
-  if (s < k) { blkcnt[(b * 2 + 0) * k + s] = cf; blkcnt[(b * 2 + 1) * k + s] = cr; }
+  if (s < k) { blkcnt[(int64_t)s * nblk + b] = cf; blkcnt[((int64_t)k + s) * nblk + b] = cr; }
 }
-
-// Y3: exclusive prefix over blocks per chain column (in place), then chain base offsets
-__global__ void __launch_bounds__(128) yd_prefix_kernel(uint32_t* __restrict__ blkcnt, int64_t nblk, int k, uint32_t* __restrict__ coltot) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= 2 * k) return;
-  uint32_t run = 0;
-  const int side = col / k, s = col % k;   // column (side, sample) lives at blkcnt[(b*2+side)*k + s]
-  for (int64_t b = 0; b < nblk; ++b) {
-    uint32_t* p = &blkcnt[(b * 2 + side) * k + s];
-    const uint32_t v = *p; *p = run; run += v;
-  }
-  coltot[col] = run;
+struct CntIn { const uint32_t* c; __device__ unsigned long long operator()(int64_t i) const { return c[i]; } };
+struct CntOut { unsigned long long* o; __device__ void operator()(int64_t i, unsigned long long exc, unsigned long long) const { o[i] = exc; } };
+struct OpSumU64 { typedef unsigned long long T; __host__ __device__ static T identity() { return 0; } __host__ __device__ static T combine(T a, T b) { return a + b; } };
+__global__ void __launch_bounds__(128) yd_colbase_kernel(const unsigned long long* __restrict__ blkoff, const unsigned long long* __restrict__ total, int64_t nblk,
+                                                         int nchains, unsigned long long* __restrict__ colbase) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nchains) colbase[c] = blkoff[(int64_t)c * nblk];
+  if (c == nchains) colbase[c] = *total;
 }
-__global__ void yd_colbase_kernel(const uint32_t* __restrict__ coltot, int k, unsigned long long* __restrict__ colbase) {
-  unsigned long long run = 0;
-  for (int c = 0; c < 2 * k; ++c) { colbase[c] = run; run += coltot[c]; }
-  colbase[2 * k] = run;
-}
-
-// Y4: stable scatter of the group ids into the chain lists (chain c = side*k + sample)
+// stable scatter of the group ids into the chain lists
 __global__ void __launch_bounds__(128) yd_scatter_kernel(const uint32_t* __restrict__ bits, uint32_t W, int k, int64_t G, const uint8_t* __restrict__ gstrand,
-                                                        const uint32_t* __restrict__ blkoff, const unsigned long long* __restrict__ colbase, int64_t nblk,
-                                                        uint32_t* __restrict__ chain) {
+                                                        const unsigned long long* __restrict__ blkoff, int64_t nblk, uint32_t* __restrict__ chain) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= nblk * W) return;
   const int64_t b = warp / W; const uint32_t w = (uint32_t)(warp % W);
@@ -111,7 +154,7 @@ __global__ void __launch_bounds__(128) yd_scatter_kernel(const uint32_t* __restr
   const int s = (int)(w * 32 + lane);
   const int64_t g0 = b * YD_BLOCK, g1 = (g0 + YD_BLOCK < G) ? g0 + YD_BLOCK : G;
   unsigned long long pf = 0, pr = 0;
-  if (s < k) { pf = colbase[s] + blkoff[(b * 2 + 0) * k + s]; pr = colbase[k + s] + blkoff[(b * 2 + 1) * k + s]; }
+  if (s < k) { pf = blkoff[(int64_t)s * nblk + b]; pr = blkoff[((int64_t)k + s) * nblk + b]; }
   for (int64_t base = g0; base < g1; base += 32) {
     const int64_t g = base + lane;
     uint32_t word = 0; uint8_t sc = 0;
@@ -129,22 +172,21 @@ __global__ void __launch_bounds__(128) yd_scatter_kernel(const uint32_t* __restr
   }
 }
 
-// Y5: sub-chain heads. Prefix max of (chain<<32 | end) over the member array is a segmented prefix max because chain
-// ids ascend along the array.
+// sub-chain heads: prefix max of (chain<<32 | end) over the member array is a segmented prefix max (chain ids ascend)
+__device__ __forceinline__ int yd_chain_of(const unsigned long long* __restrict__ colbase, int nchains, int64_t i) {
+  int lo = 0, hi = nchains;  // last c with colbase[c] <= i
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (colbase[mid] <= (unsigned long long)i) lo = mid; else hi = mid; }
+  return lo;
+}
 struct MemberKeyIn {
   const uint32_t* chain; const uint32_t* gend; const unsigned long long* colbase; int nchains;
-  __device__ int chain_of(int64_t i) const {
-    int lo = 0, hi = nchains;  // last c with colbase[c] <= i
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (colbase[mid] <= (unsigned long long)i) lo = mid; else hi = mid; }
-    return lo;
-  }
-  __device__ unsigned long long operator()(int64_t i) const { return ((unsigned long long)(uint32_t)chain_of(i) << 32) | gend[chain[i]]; }
+  __device__ unsigned long long operator()(int64_t i) const { return ((unsigned long long)(uint32_t)yd_chain_of(colbase, nchains, i) << 32) | gend[chain[i]]; }
 };
 struct MemberHeadOut {
   MemberKeyIn mk; const GDesc* desc; uint32_t* flag;
   __device__ void operator()(int64_t i, unsigned long long exc, unsigned long long) const {
     uint32_t h = 1u;
-    if (i > 0 && (int)(exc >> 32) == mk.chain_of(i)) h = (uint32_t)desc[mk.chain[i]].start > (uint32_t)exc ? 1u : 0u;
+    if (i > 0 && (int)(exc >> 32) == yd_chain_of(mk.colbase, mk.nchains, i)) h = (uint32_t)desc[mk.chain[i]].start > (uint32_t)exc ? 1u : 0u;
     flag[i] = h;
   }
 };
@@ -154,6 +196,163 @@ __global__ void yd_subchain_total_kernel(const uint32_t* tot, uint32_t* heads, u
   heads[*tot] = n_members; work[0] = 0; work[1] = *tot;
 }
 
+constexpr int YD_WARPS = 8;
+constexpr uint32_t YD_LONG = 96;     // sub-chains longer than this are walked by the whole warp
+
+// ---- Y6: frontier recurrence -> kept-exon count per member -----------------------------------------------------------
+struct Frontier {
+  int E;
+  __device__ __forceinline__ void reset() { E = -1; }
+  // returns the number of kept exons of the read described by d (compact coordinates). Reads with more than three exons
+  // continue over the CIGAR (genomic coordinates mapped through rank()).
+  __device__ __forceinline__ uint32_t step(const ColIn& in, const GDesc& d, uint32_t rep, const uint32_t* U, const uint32_t* rankpre) {
+    const int ne = (int)(d.meta & 0xffffu);
+    if (E < d.start) { E = d.zend; return (uint32_t)ne; }   // bulk: the list is empty when the read is merged
+    int cur = max(E, d.e0); uint32_t r = 1;
+    if (ne >= 2 && d.s1 <= cur) {
+      r = 2; cur = max(cur, d.e1);
+      if (ne >= 3 && d.s2 <= cur) {
+        r = 3; cur = max(cur, d.e2);
+        if (ne > YD_INLINE_EX) {
+          const int ubase = in.pos_lo + 1;
+          ExonIter it; it.init(in.cigar, in.cig_off[rep], in.cig_off[rep + 1], in.pos[rep]);
+          int s, e, j = 0;
+          while (it.next(s, e)) {
+            if (j++ < YD_INLINE_EX) continue;
+            if (yd_rank(U, rankpre, (int64_t)s - ubase) > cur) break;
+            ++r; cur = max(cur, (int)yd_rank(U, rankpre, (int64_t)e - ubase));
+          }
+        }
+      }
+    }
+    E = cur;
+    return r;
+  }
+};
+
+__global__ void __launch_bounds__(YD_WARPS * 32) yd_frontier_kernel(ColIn in, const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ rep,
+                                                                   const uint32_t* __restrict__ chain, const uint32_t* __restrict__ heads,
+                                                                   unsigned long long* work, const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre,
+                                                                   uint8_t* __restrict__ kept) {
+  __shared__ GDesc s_desc[YD_WARPS][32];
+  __shared__ uint32_t s_g[YD_WARPS][32];
+  __shared__ uint8_t s_r[YD_WARPS][32];
+  const int wl = tb_warp(), lane = tb_lane();
+  const unsigned long long nsub = work[1];
+  for (;;) {
+    unsigned long long j0 = 0;
+    if (lane == 0) j0 = atomicAdd(&work[0], 32ULL);
+    j0 = __shfl_sync(0xffffffffu, j0, 0);
+    if (j0 >= nsub) break;
+    const unsigned long long j = j0 + lane;
+    uint32_t c0 = 0, c1 = 0;
+    if (j < nsub) { c0 = heads[j]; c1 = heads[j + 1]; }
+    const uint32_t len = c1 - c0;
+    if (len > 0 && len <= YD_LONG) {   // short sub-chains: one per lane
+      Frontier F; F.reset();
+      for (uint32_t i = c0; i < c1; ++i) {
+        const uint32_t g = chain[i];
+        kept[i] = (uint8_t)F.step(in, cdesc[g], rep[g], U, rankpre);
+      }
+    }
+    unsigned longs = __ballot_sync(0xffffffffu, len > YD_LONG);
+    while (longs) {                    // long sub-chains: lanes prefetch 32 descriptors, lane 0 runs the recurrence
+      const int q = __ffs(longs) - 1; longs &= longs - 1;
+      const uint32_t a = __shfl_sync(0xffffffffu, c0, q), b = __shfl_sync(0xffffffffu, c1, q);
+      Frontier F; F.reset();
+      uint32_t gnext = 0; GDesc dnext; dnext.start = 0; dnext.meta = 0; dnext.e0 = dnext.s1 = dnext.e1 = dnext.s2 = dnext.e2 = dnext.zend = 0;
+      if (a + lane < b) { gnext = chain[a + lane]; dnext = cdesc[gnext]; }
+      for (uint32_t cb = a; cb < b; cb += 32) {
+        s_desc[wl][lane] = dnext; s_g[wl][lane] = gnext;
+        __syncwarp();
+        if (cb + 32 + lane < b) { gnext = chain[cb + 32 + lane]; dnext = cdesc[gnext]; }   // prefetch the next batch
+        if (lane == 0) {
+          const int cnt = (int)((b - cb) < 32u ? (b - cb) : 32u);
+          for (int t = 0; t < cnt; ++t) {
+            const GDesc& d = s_desc[wl][t];
+            const uint32_t rr = ((d.meta & 0xffffu) > (uint32_t)YD_INLINE_EX) ? rep[s_g[wl][t]] : 0u;
+            s_r[wl][t] = (uint8_t)F.step(in, d, rr, U, rankpre);
+          }
+        }
+        __syncwarp();
+        if (cb + lane < b) kept[cb + lane] = s_r[wl][lane];
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// ---- Y7: links of the kept exons into the chain bitmaps ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) yd_link_kernel(ColIn in, const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ rep, const uint32_t* __restrict__ chain,
+                                                      const uint8_t* __restrict__ kept, int64_t n_members, const unsigned long long* __restrict__ colbase, int nchains,
+                                                      const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre,
+                                                      unsigned long long* __restrict__ bm, int64_t lpad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_members) return;
+  const uint32_t g = chain[i];
+  const GDesc d = cdesc[g];
+  const uint32_t r = kept[i];
+  const int64_t base = (int64_t)yd_chain_of(colbase, nchains, i) * lpad;
+  // exon [s,t] sets links s .. t-1
+  if (d.e0 > d.start) yd_set_bits64(bm, base + d.start, base + d.e0 - 1);
+  if (r >= 2 && d.e1 > d.s1) yd_set_bits64(bm, base + d.s1, base + d.e1 - 1);
+  if (r >= 3 && d.e2 > d.s2) yd_set_bits64(bm, base + d.s2, base + d.e2 - 1);
+  if (r > (uint32_t)YD_INLINE_EX) {
+    const int ubase = in.pos_lo + 1;
+    const uint32_t rr = rep[g];
+    ExonIter it; it.init(in.cigar, in.cig_off[rr], in.cig_off[rr + 1], in.pos[rr]);
+    int s, e; uint32_t j = 0;
+    while (j < r && it.next(s, e)) {
+      if (j++ < (uint32_t)YD_INLINE_EX) continue;
+      const int64_t cs = yd_rank(U, rankpre, (int64_t)s - ubase), ce = yd_rank(U, rankpre, (int64_t)e - ubase);
+      if (ce > cs) yd_set_bits64(bm, base + cs, base + ce - 1);
+    }
+  }
+}
+
+// ---- Y8: position of the last clear link before every 512-bit block ---------------------------------------------------
+struct OpMaxI64 { typedef long long T; __host__ __device__ static T identity() { return -1; } __host__ __device__ static T combine(T a, T b) { return a > b ? a : b; } };
+struct LastZeroIn {   // highest clear bit of block b (global bit index), -1 if the block is all ones
+  const unsigned long long* bm;
+  __device__ long long operator()(int64_t b) const {
+    for (int w = 7; w >= 0; --w) {
+      const unsigned long long z = ~bm[b * 8 + w];
+      if (z) return (b * 8 + w) * 64 + (63 - __clzll((long long)z));
+    }
+    return -1;
+  }
+};
+struct LastZeroOut { long long* lz; __device__ void operator()(int64_t b, long long exc, long long) const { lz[b] = exc; } };
+
+// ---- Y9: d = number of consecutive set links ending at start-1 --------------------------------------------------------
+__global__ void __launch_bounds__(256) yd_lookup_kernel(const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ chain, int64_t n_members,
+                                                        const unsigned long long* __restrict__ colbase, int nchains, const unsigned long long* __restrict__ bm,
+                                                        const long long* __restrict__ lz, int64_t lpad, int32_t* __restrict__ yd) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_members) return;
+  const uint32_t g = chain[i];
+  const int x = cdesc[g].start;
+  if (x <= 0) return;
+  const int64_t base = (int64_t)yd_chain_of(colbase, nchains, i) * lpad;
+  const int64_t q = base + x - 1;
+  int64_t w = q >> 6; const int b = (int)(q & 63);
+  const unsigned long long word = bm[w];
+  if (!((word >> b) & 1ULL)) return;
+  unsigned long long zeros = ~word & ((1ULL << b) - 1ULL);
+  long long z = -2;
+  const int64_t wb = w & ~7LL;   // first word of the 512-bit block
+  for (;;) {
+    if (zeros) { z = w * 64 + (63 - __clzll((long long)zeros)); break; }
+    if (w == wb) break;
+    --w; zeros = ~bm[w];
+  }
+  if (z == -2) z = lz[wb >> 3];
+  if (z < base - 1) z = base - 1;   // cannot happen (every chain's region ends with clear padding); keeps d bounded
+  const long long d = q - z;
+  if (d > 0) atomicMax(&yd[g], (int32_t)d);
+}
+
+// ---- sequential fallback: the literal list ------------------------------------------------------------------------------
 // one segment list; node q lives at st[q*32], en[q*32] (the lane offset is folded into the pointers)
 struct SegArr {
   int n; uint32_t last_pos; int last_dist; int cap;
@@ -227,25 +426,23 @@ struct InlineExons {  // exon source over a descriptor
   }
 };
 
-__device__ __forceinline__ int yd_step(const ColIn& in, SegArr& L, const GDesc& d, bool& ok) {
+__device__ __forceinline__ int yd_step(const ColIn& in, SegArr& L, const GDesc& d, uint32_t r, bool& ok) {
   const int ne = (int)(d.meta & 0xffffu);
-  if (ne <= YD_INLINE_EX) { InlineExons src{d.start, ne, 0, d.e[0], d.e[1], d.e[2], d.e[3], d.e[4]}; return L.process(src, (uint32_t)d.start, ok); }
-  const uint32_t r = (uint32_t)d.e[5];
+  if (ne <= YD_INLINE_EX) { InlineExons src{d.start, ne, 0, d.e0, d.s1, d.e1, d.s2, d.e2}; return L.process(src, (uint32_t)d.start, ok); }
   ExonIter it; it.init(in.cigar, in.cig_off[r], in.cig_off[r + 1], d.start - 1);
   return L.process(it, (uint32_t)d.start, ok);
 }
 
-constexpr int YD_WARPS = 8;
 constexpr int YD_CAP_SMEM = 24;      // live nodes per list in shared memory
 constexpr int YD_CAP_GLOBAL = 4096;  // live nodes per list in the global-memory repeat
-constexpr uint32_t YD_LONG = 96;     // sub-chains longer than this are walked by the whole warp
 
 template <bool SMEM>
-__global__ void __launch_bounds__(YD_WARPS * 32) yd_chain_kernel(ColIn in, const GDesc* __restrict__ desc, const uint32_t* __restrict__ chain,
-                                                                const uint32_t* __restrict__ heads, unsigned long long* work, int32_t* __restrict__ yd,
-                                                                uint32_t* gscratch, long long* status) {
+__global__ void __launch_bounds__(YD_WARPS * 32) yd_chain_kernel(ColIn in, const GDesc* __restrict__ desc, const uint32_t* __restrict__ rep,
+                                                                const uint32_t* __restrict__ chain, const uint32_t* __restrict__ heads,
+                                                                unsigned long long* work, int32_t* __restrict__ yd, uint32_t* gscratch, long long* status) {
   extern __shared__ __align__(16) uint32_t s_dyn[];   // SMEM: YD_WARPS * 2 * YD_CAP_SMEM * 32 words of lists
   __shared__ GDesc s_desc[YD_WARPS][32];
+  __shared__ uint32_t s_g[YD_WARPS][32];
   __shared__ int s_d[YD_WARPS][32];
   const int wl = tb_warp(), lane = tb_lane();
   const int cap = SMEM ? YD_CAP_SMEM : YD_CAP_GLOBAL;
@@ -263,32 +460,33 @@ __global__ void __launch_bounds__(YD_WARPS * 32) yd_chain_kernel(ColIn in, const
     uint32_t c0 = 0, c1 = 0;
     if (j < nsub) { c0 = heads[j]; c1 = heads[j + 1]; }
     const uint32_t len = c1 - c0;
-    // ---- short sub-chains: one per lane ----
-    if (len > 0 && len <= YD_LONG) {
+    if (len > 0 && len <= YD_LONG) {   // short sub-chains: one per lane
       L.reset();
       for (uint32_t i = c0; i < c1; ++i) {
         const uint32_t g = chain[i];
-        const GDesc d = desc[g];
-        const int dist = yd_step(in, L, d, ok);
+        const int dist = yd_step(in, L, desc[g], rep[g], ok);
         if (dist > 0) atomicMax(&yd[g], dist);
       }
     }
-    // ---- long sub-chains: the whole warp walks them one after the other ----
     unsigned longs = __ballot_sync(0xffffffffu, len > YD_LONG);
-    while (longs) {
+    while (longs) {                    // long sub-chains: the whole warp walks them one after the other
       const int q = __ffs(longs) - 1; longs &= longs - 1;
       const uint32_t a = __shfl_sync(0xffffffffu, c0, q), b = __shfl_sync(0xffffffffu, c1, q);
       L0.reset();
-      uint32_t gnext = 0; GDesc dnext; dnext.start = 0; dnext.meta = 0;
+      uint32_t gnext = 0; GDesc dnext; dnext.start = 0; dnext.meta = 0; dnext.e0 = dnext.s1 = dnext.e1 = dnext.s2 = dnext.e2 = dnext.zend = 0;
       if (a + lane < b) { gnext = chain[a + lane]; dnext = desc[gnext]; }
       for (uint32_t cb = a; cb < b; cb += 32) {
         const uint32_t g = gnext;
-        s_desc[wl][lane] = dnext;
+        s_desc[wl][lane] = dnext; s_g[wl][lane] = gnext;
         __syncwarp();
         if (cb + 32 + lane < b) { gnext = chain[cb + 32 + lane]; dnext = desc[gnext]; }   // prefetch the next batch
         if (lane == 0) {
           const int cnt = (int)((b - cb) < 32u ? (b - cb) : 32u);
-          for (int t = 0; t < cnt; ++t) s_d[wl][t] = yd_step(in, L0, s_desc[wl][t], ok);
+          for (int t = 0; t < cnt; ++t) {
+            const GDesc& d = s_desc[wl][t];
+            const uint32_t rr = ((d.meta & 0xffffu) > (uint32_t)YD_INLINE_EX) ? rep[s_g[wl][t]] : 0u;
+            s_d[wl][t] = yd_step(in, L0, d, rr, ok);
+          }
         }
         __syncwarp();
         if (cb + lane < b) { const int dist = s_d[wl][lane]; if (dist > 0) atomicMax(&yd[g], dist); }
@@ -303,71 +501,127 @@ __global__ void __launch_bounds__(256) yd_combine_kernel(int32_t* __restrict__ y
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g < G) { const int32_t a = yd[g], b = ydc[g]; yd[g] = a > b ? a : b; }   // max(carried YD tags, chain distance); 0 = no tag
 }
+__global__ void yd_store_lc_kernel(const uint32_t* tot, long long* status) { status[YS_LC] = *tot; }
 
 }  // namespace
 
 int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp, int64_t G) {
   cudaStream_t st = ctx->stream;
   DevBuf* B = ctx->buf;
-  const uint32_t W = g.W; const int k = g.k;
+  const uint32_t W = g.W; const int k = g.k; const int nchains = 2 * k;
   const int64_t nblk = (G + YD_BLOCK - 1) / YD_BLOCK;
-  TB_CUDA(B[XB_GDESC].ensure(sizeof(GDesc) * (size_t)G));
-  TB_CUDA(B[XB_YDPM].ensure(sizeof(uint32_t) * (size_t)G + (size_t)G + 64));
-  TB_CUDA(B[XB_YDBLK].ensure(sizeof(uint32_t) * (size_t)nblk * 2 * k + sizeof(uint32_t) * 2 * k + sizeof(uint64_t) * (2 * (size_t)k + 8)));
+  const char* env = getenv("TB_YD_PATH");
+  bool parallel = !(env && env[0] == 's');
+  const int64_t ubits = (int64_t)g.S + YD_U_SLACK;
+  const int64_t nuw = (ubits + 31) / 32 + 1;
+  const int ubase = in.pos_lo + 1;
+  TB_CUDA(B[XB_GDESC].ensure(sizeof(GDesc) * (size_t)G * 2));
+  TB_CUDA(B[XB_YDPM].ensure(sizeof(uint32_t) * (size_t)G * 2 + (size_t)G + 64));
+  TB_CUDA(B[XB_YDBLK].ensure(sizeof(uint32_t) * (size_t)nblk * nchains + sizeof(uint64_t) * ((size_t)nblk * nchains + nchains + 16)));
   TB_CUDA(B[XB_WORK].ensure(256));
   TB_CUDA(B[XB_YDC].ensure(sizeof(int32_t) * (size_t)G));
   GDesc* desc = B[XB_GDESC].as<GDesc>();
+  GDesc* cdesc = desc + G;
   uint32_t* gend = B[XB_YDPM].as<uint32_t>();
-  uint8_t* gstrand = (uint8_t*)(gend + G);
-  unsigned long long* colbase = B[XB_YDBLK].as<unsigned long long>();       // [2k+1] (+pad), 8-byte aligned at the buffer start
-  uint32_t* coltot = (uint32_t*)(colbase + 2 * (size_t)k + 8);                // [2k]
-  uint32_t* blkcnt = coltot + 2 * k;                                          // [nblk*2*k]
-  unsigned long long* work = B[XB_WORK].as<unsigned long long>() + 8;         // the tile kernel's slot counter sits at +0
+  uint32_t* cend = gend + G;
+  uint8_t* gstrand = (uint8_t*)(cend + G);
+  unsigned long long* blkoff = B[XB_YDBLK].as<unsigned long long>();            // [nchains*nblk] exclusive member offsets, chain-major
+  unsigned long long* colbase = blkoff + (size_t)nblk * nchains;                // [nchains+1]
+  uint32_t* blkcnt = (uint32_t*)(colbase + nchains + 16);                       // [nchains*nblk]
+  unsigned long long* work = B[XB_WORK].as<unsigned long long>() + 8;           // the tile kernel's slot counter sits at +0
   int32_t* ydc = B[XB_YDC].as<int32_t>();
   long long* h_status = ctx->pinned[0].as<long long>();
+  uint32_t* U = nullptr; uint32_t* rankpre = nullptr;
+  if (parallel) {
+    TB_CUDA(B[XB_YDU].ensure(sizeof(uint32_t) * (size_t)nuw * 2 + 64));
+    U = B[XB_YDU].as<uint32_t>(); rankpre = U + nuw;
+    TB_CUDA(cudaMemsetAsync(U, 0, sizeof(uint32_t) * (size_t)nuw, st));
+  }
   TB_CUDA(cudaMemsetAsync(ydc, 0, sizeof(int32_t) * (size_t)G, st));
-  yd_desc_kernel<<<tb_grid_for(G, 256), 256, 0, st>>>(in, grp.rep, G, desc, gend, gstrand);
+  TB_CUDA(cudaMemsetAsync(g.d_status + YS_FALLBACK, 0, 2 * sizeof(long long), st));
+  int64_t agg_need = tb_scan_blocks((int64_t)nblk * nchains); if (tb_scan_blocks(nuw) > agg_need) agg_need = tb_scan_blocks(nuw);
+  TB_CUDA(B[XB_AGG].ensure((size_t)(agg_need + 8) * sizeof(uint64_t)));
+  // ---- Y1, Y2 ----
+  yd_desc_kernel<<<tb_grid_for(G, 256), 256, 0, st>>>(in, grp.rep, G, desc, gend, gstrand, U, ubits, g.d_status);
+  ctx->launches++;
+  if (parallel) {
+    TB_CUDA((tb_device_scan<OpSumU32>(ctx, UPopIn{U}, nuw, B[XB_AGG].as<uint32_t>(), UPopOut{rankpre})));
+    yd_store_lc_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(nuw), g.d_status);
+    ctx->launches++;
+  }
+  // ---- Y3: member counts -> offsets ----
   const int64_t nwarps = nblk * W;
   yd_count_kernel<<<tb_grid_for(nwarps * 32, 128), 128, 0, st>>>(grp.bits, W, k, G, gstrand, blkcnt, nblk);
-  yd_prefix_kernel<<<tb_grid_for(2 * k, 128), 128, 0, st>>>(blkcnt, nblk, k, coltot);
-  yd_colbase_kernel<<<1, 1, 0, st>>>(coltot, k, colbase);
-  ctx->launches += 4;
-  // the number of chain members (<= 2 x sum of direct-sample counts) is only known on the device
-  TB_CUDA(cudaMemcpyAsync(h_status, colbase + 2 * k, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  ctx->launches++;
+  TB_CUDA((tb_device_scan<OpSumU64>(ctx, CntIn{blkcnt}, (int64_t)nblk * nchains, B[XB_AGG].as<unsigned long long>(), CntOut{blkoff})));
+  yd_colbase_kernel<<<tb_grid_for(nchains + 1, 128), 128, 0, st>>>(blkoff, B[XB_AGG].as<unsigned long long>() + tb_scan_blocks((int64_t)nblk * nchains), nblk, nchains, colbase);
+  ctx->launches++;
+  // member count, compact length and the fallback flag are only known on the device
+  TB_CUDA(cudaMemcpyAsync(h_status, g.d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(h_status + 16, colbase + nchains, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
-  const int64_t n_members = h_status[0];
+  const int64_t n_members = h_status[16];
   if (n_members >= (1LL << 32)) { ctx->set_error("tb_collapse_window: %lld chain members exceed the 32-bit YD index", (long long)n_members); return 1; }
+  if (h_status[YS_FALLBACK]) parallel = false;
+  const int64_t Lc = h_status[YS_LC];
+  ctx->last_yd_path = parallel ? 0 : 1;
   if (n_members > 0) {
     TB_CUDA(B[XB_YDCHAIN].ensure(sizeof(uint32_t) * ((size_t)n_members + 32)));
     TB_CUDA(B[XB_BHEAD].ensure(sizeof(uint32_t) * ((size_t)n_members + 32)));
     TB_CUDA(B[XB_YDFLAG].ensure(sizeof(uint32_t) * ((size_t)n_members + 32)));
-    TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks(n_members) + 8) * sizeof(uint64_t)));
+    const int64_t lpad = ((Lc + 1 + 511) / 512) * 512;            // bits per chain, at least one clear padding bit
+    const int64_t nwords = lpad / 64 * nchains, nblocks512 = nwords / 8;
+    TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks(nblocks512 > n_members ? nblocks512 : n_members) + 8) * sizeof(uint64_t)));
     uint32_t* chain = B[XB_YDCHAIN].as<uint32_t>(); uint32_t* heads = B[XB_BHEAD].as<uint32_t>(); uint32_t* flag = B[XB_YDFLAG].as<uint32_t>();
-    yd_scatter_kernel<<<tb_grid_for(nwarps * 32, 128), 128, 0, st>>>(grp.bits, W, k, G, gstrand, blkcnt, colbase, nblk, chain);
+    yd_scatter_kernel<<<tb_grid_for(nwarps * 32, 128), 128, 0, st>>>(grp.bits, W, k, G, gstrand, blkoff, nblk, chain);
     ctx->launches++;
-    MemberKeyIn mk{chain, gend, colbase, 2 * k};
-    TB_CUDA((tb_device_scan<OpMaxU64>(ctx, mk, n_members, B[XB_AGG].as<unsigned long long>(), MemberHeadOut{mk, desc, flag})));
+    const GDesc* hd = desc; const uint32_t* he = gend;
+    if (parallel) {
+      yd_compact_kernel<<<tb_grid_for(G, 256), 256, 0, st>>>(desc, G, U, rankpre, ubase, cdesc, cend);
+      ctx->launches++;
+      hd = cdesc; he = cend;
+    }
+    // ---- Y5: sub-chain heads ----
+    MemberKeyIn mk{chain, he, colbase, nchains};
+    TB_CUDA((tb_device_scan<OpMaxU64>(ctx, mk, n_members, B[XB_AGG].as<unsigned long long>(), MemberHeadOut{mk, hd, flag})));
     TB_CUDA((tb_device_scan<OpSumU32>(ctx, FlagIn{flag}, n_members, B[XB_AGG].as<uint32_t>(), HeadListOut{heads})));
     yd_subchain_total_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(n_members), heads, (uint32_t)n_members, work);
     ctx->launches++;
-    const size_t smem = (size_t)YD_WARPS * 2 * YD_CAP_SMEM * 32 * sizeof(uint32_t);
-    TB_CUDA(cudaFuncSetAttribute(yd_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    yd_chain_kernel<true><<<(unsigned)ctx->sm_count * 4, YD_WARPS * 32, smem, st>>>(in, desc, chain, heads, work, ydc, nullptr, g.d_status);
-    ctx->launches++;
-    TB_CUDA(cudaMemcpyAsync(h_status, g.d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
-    TB_CUDA(cudaStreamSynchronize(st));
-    if (h_status[CS_YD_OVERFLOW]) {
-      // a list outgrew shared memory (its later distances are wrong): repeat everything with lists in global memory
-      const unsigned grid2 = (unsigned)ctx->sm_count;
-      TB_CUDA(B[XB_YDSCRATCH].ensure((size_t)grid2 * YD_WARPS * 2 * YD_CAP_GLOBAL * 32 * sizeof(uint32_t)));
-      TB_CUDA(cudaMemsetAsync(ydc, 0, sizeof(int32_t) * (size_t)G, st));
-      TB_CUDA(cudaMemsetAsync(work, 0, sizeof(unsigned long long), st));
-      TB_CUDA(cudaMemsetAsync(g.d_status + CS_YD_OVERFLOW, 0, sizeof(long long), st));
-      yd_chain_kernel<false><<<grid2, YD_WARPS * 32, 0, st>>>(in, desc, chain, heads, work, ydc, B[XB_YDSCRATCH].as<uint32_t>(), g.d_status);
+    if (parallel) {
+      // ---- Y6-Y9 ----
+      TB_CUDA(B[XB_YDKEPT].ensure((size_t)n_members + 64));
+      TB_CUDA(B[XB_YDBM].ensure(sizeof(uint64_t) * (size_t)nwords + 64));
+      TB_CUDA(B[XB_YDLZ].ensure(sizeof(int64_t) * (size_t)nblocks512 + 64));
+      uint8_t* kept = B[XB_YDKEPT].as<uint8_t>();
+      unsigned long long* bm = B[XB_YDBM].as<unsigned long long>();
+      long long* lz = B[XB_YDLZ].as<long long>();
+      TB_CUDA(cudaMemsetAsync(bm, 0, sizeof(uint64_t) * (size_t)nwords, st));
+      yd_frontier_kernel<<<(unsigned)ctx->sm_count * 8, YD_WARPS * 32, 0, st>>>(in, cdesc, grp.rep, chain, heads, work, U, rankpre, kept);
+      yd_link_kernel<<<tb_grid_for(n_members, 256), 256, 0, st>>>(in, cdesc, grp.rep, chain, kept, n_members, colbase, nchains, U, rankpre, bm, lpad);
+      ctx->launches += 2;
+      TB_CUDA((tb_device_scan<OpMaxI64>(ctx, LastZeroIn{bm}, nblocks512, B[XB_AGG].as<long long>(), LastZeroOut{lz})));
+      yd_lookup_kernel<<<tb_grid_for(n_members, 256), 256, 0, st>>>(cdesc, chain, n_members, colbase, nchains, bm, lz, lpad, ydc);
+      ctx->launches++;
+    } else {
+      const size_t smem = (size_t)YD_WARPS * 2 * YD_CAP_SMEM * 32 * sizeof(uint32_t);
+      TB_CUDA(cudaFuncSetAttribute(yd_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      yd_chain_kernel<true><<<(unsigned)ctx->sm_count * 4, YD_WARPS * 32, smem, st>>>(in, desc, grp.rep, chain, heads, work, ydc, nullptr, g.d_status);
       ctx->launches++;
       TB_CUDA(cudaMemcpyAsync(h_status, g.d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
       TB_CUDA(cudaStreamSynchronize(st));
-      if (h_status[CS_YD_OVERFLOW]) { ctx->set_error("tb_collapse_window: YD segment list exceeded %d live nodes", YD_CAP_GLOBAL); return 1; }
+      if (h_status[CS_YD_OVERFLOW]) {
+        // a list outgrew shared memory (its later distances are wrong): repeat everything with lists in global memory
+        const unsigned grid2 = (unsigned)ctx->sm_count;
+        TB_CUDA(B[XB_YDSCRATCH].ensure((size_t)grid2 * YD_WARPS * 2 * YD_CAP_GLOBAL * 32 * sizeof(uint32_t)));
+        TB_CUDA(cudaMemsetAsync(ydc, 0, sizeof(int32_t) * (size_t)G, st));
+        TB_CUDA(cudaMemsetAsync(work, 0, sizeof(unsigned long long), st));
+        TB_CUDA(cudaMemsetAsync(g.d_status + CS_YD_OVERFLOW, 0, sizeof(long long), st));
+        yd_chain_kernel<false><<<grid2, YD_WARPS * 32, 0, st>>>(in, desc, grp.rep, chain, heads, work, ydc, B[XB_YDSCRATCH].as<uint32_t>(), g.d_status);
+        ctx->launches++;
+        TB_CUDA(cudaMemcpyAsync(h_status, g.d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(cudaStreamSynchronize(st));
+        if (h_status[CS_YD_OVERFLOW]) { ctx->set_error("tb_collapse_window: YD segment list exceeded %d live nodes", YD_CAP_GLOBAL); return 1; }
+      }
     }
   }
   yd_combine_kernel<<<tb_grid_for(G, 256), 256, 0, st>>>(grp.yd, ydc, G);

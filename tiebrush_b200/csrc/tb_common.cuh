@@ -70,6 +70,7 @@ struct tb_ctx {
   int profiling = 0;
   float last_ms[16] = {};   // per-stage device times of the last call (see tb_last_kernel_ms)
   int64_t launches = 0;
+  int last_yd_path = 0;     // YD stage of the last collapse call: 0 parallel (frontier + link bitmaps), 1 sequential lists
   int last_path = 0;        // front end of the last collapse call: 0 tile, 1 ordered (by options), 2 ordered (table overflow fallback)
   std::string err;
   DevBuf buf[TB_NBUF];   // workspace slots (see the enum in each pipeline)
@@ -141,30 +142,41 @@ __device__ __forceinline__ typename Op::T tb_block_reduce(typename Op::T v, type
   return r;  // every thread gets the block total (order-preserving: warp order == element order)
 }
 
-// exclusive scan of one value per thread across the block; returns the exclusive prefix, *total gets block total
+// exclusive scan of one value per thread across the block; returns the exclusive prefix, *total gets block total.
+// Two levels: inclusive scan inside every warp, then warp 0 scans the (<= 32) warp totals with shuffles.
+// s_warp holds 33 elements. Operand order is preserved (non-commutative operators are fine).
 template <class Op>
 __device__ __forceinline__ typename Op::T tb_block_exscan(typename Op::T v, typename Op::T* s_warp /*[33]*/, typename Op::T* total) {
   typedef typename Op::T T;
+  const int lane = tb_lane(), warp = tb_warp();
   T inc = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     T o = tb_shfl_up(inc, d);
-    if (tb_lane() >= d) inc = Op::combine(o, inc);
+    if (lane >= d) inc = Op::combine(o, inc);
+  }
+  __syncthreads();  // s_warp may still be read from a previous call
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    T x = lane < nw ? s_warp[lane] : Op::identity();
+    T xi = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      T o = tb_shfl_up(xi, d);
+      if (lane >= d) xi = Op::combine(o, xi);
+    }
+    T xe = tb_shfl_up(xi, 1);
+    if (lane == 0) xe = Op::identity();
+    s_warp[lane] = xe;              // exclusive prefix of the warp totals
+    if (lane == 31) s_warp[32] = xi;  // block total (identity padding on the right)
   }
   __syncthreads();
-  if (tb_lane() == 31) s_warp[tb_warp()] = inc;
-  __syncthreads();
-  T wpre = Op::identity();
-  int nw = blockDim.x >> 5;
-  T tot = Op::identity();
-  for (int w = 0; w < nw; ++w) {
-    if (w == tb_warp()) wpre = tot;
-    tot = Op::combine(tot, s_warp[w]);
-  }
   T exc = tb_shfl_up(inc, 1);
-  if (tb_lane() == 0) exc = Op::identity();
-  if (total) *total = tot;
-  return Op::combine(wpre, exc);
+  if (lane == 0) exc = Op::identity();
+  if (total) *total = s_warp[32];
+  return Op::combine(s_warp[warp], exc);
 }
 
 template <class Op, class InF>

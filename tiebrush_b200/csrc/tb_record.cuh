@@ -84,6 +84,40 @@ __device__ __forceinline__ void tb_parse_record(const ColIn& in, int64_t i, int 
   reflen = l; khash = h;
 }
 
+
+// 32-bit variant for the tile kernel (64-bit multiplies cost four IMADs each): two independent running hashes
+__device__ __forceinline__ uint32_t tb_mix32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
+__device__ __forceinline__ void tb_fold2(uint32_t& h1, uint32_t& h2, uint32_t w) {
+  h1 = (h1 ^ w) * 0x9E3779B1u; h1 ^= h1 >> 15;
+  h2 = (h2 + w) * 0x85EBCA77u; h2 ^= h2 >> 13;
+}
+__device__ __forceinline__ void tb_parse_record32(const ColIn& in, int64_t i, int pos, uint32_t c0, uint32_t c1, int& reflen, uint32_t& h1o, uint32_t& h2o) {
+  int l = 0;
+  uint32_t h1, h2;
+  if (in.mode == TB_MODE_EXON) {
+    ExonIter it; it.init(in.cigar, c0, c1, pos);
+    int s, e, nex = 0; h1 = 0x1234567u; h2 = 0x89abcdefu;
+    while (it.next(s, e)) { tb_fold2(h1, h2, (uint32_t)s); tb_fold2(h1, h2, (uint32_t)e); ++nex; }
+    tb_fold2(h1, h2, (uint32_t)nex);
+    l = it.l;
+  } else {
+    uint32_t a = c0, b = c1;
+    if (in.mode == TB_MODE_CLIP) tb_clip_range(in.cigar, a, b);
+    h1 = 0x9876543u ^ (b - a); h2 = 0x3c6ef372u + (b - a);
+    for (uint32_t c = c0; c < c1; ++c) {
+      const uint32_t w = in.cigar[c];
+      if (tb_op_ref(w & 0xf)) l += (int)(w >> 4);
+      if (c >= a && c < b) tb_fold2(h1, h2, w);
+    }
+    if (in.mode == TB_MODE_FULL) {
+      const uint32_t m0 = in.md_off[i], m1 = in.md_off[i + 1];
+      tb_fold2(h1, h2, (uint32_t)(m1 > m0));
+      for (uint32_t q = m0; q < m1; ++q) { const uint8_t ch = in.md[q]; if (ch == 0) break; tb_fold2(h1, h2, ch); }
+    }
+  }
+  reflen = l; h1o = h1; h2o = h2;
+}
+
 // exact mode comparison of two records, sign as in the reference's cmp* functions (cmpFlags NOT applied)
 static __device__ __noinline__ int tb_mode_cmp(const ColIn& in, uint32_t ia, uint32_t ib) {
   uint32_t a0 = in.cig_off[ia], a1 = in.cig_off[ia + 1], b0 = in.cig_off[ib], b1 = in.cig_off[ib + 1];
@@ -158,7 +192,7 @@ enum {
   XB_WORK,       // small device counters
   XB_YDC,        // YD: chain distances per group
   XB_YDSCRATCH,  // YD: global-memory lists of the repeat launch
-  XB_YDBLK, XB_YDCHAIN, XB_YDFLAG,   // YD: per-block member counts, chain member lists, sub-chain head flags
+  XB_YDBLK, XB_YDCHAIN, XB_YDFLAG, XB_YDU, XB_YDKEPT, XB_YDBM, XB_YDLZ,   // YD: per-block member counts, chain member lists, sub-chain head flags
   XB_ORD_KEY, XB_ORD_KEY2, XB_ORD_VAL, XB_ORD_VAL2, XB_ORD_REFLEN, XB_ORD_TABLE, XB_ORD_AGG,   // ordered path: merge-order sort
   XB_ORD_LIST, XB_ORD_GREP, XB_ORD_GYC, XB_ORD_GYX, XB_ORD_GYD, XB_ORD_VALID, XB_ORD_GBITS,                // ordered path: per-position group lists
   XB_COUNT_
