@@ -20,6 +20,7 @@
 //   epilogue   occupied entries are compacted in region (= position) order, ranked inside their position by
 //              (strand, end, mode key) with the reference's comparator, and written to the staging arrays.
 #include <limits.h>
+#include <stdlib.h>
 #include "collapse_internal.cuh"
 
 namespace {
@@ -349,7 +350,7 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
 struct SlotMeta { uint32_t m, rank0, rank1, p0, p1; };
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) col_tile_kernel(ColIn in, TileParams tp) {
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) col_tile_kernel(ColIn in, TileParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_scan[33];
   __shared__ uint32_t s_flags[4];
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(128) col_compact_kernel(TileParams tp, const u
 
 __global__ void col_store_total_kernel(const uint32_t* tot, long long* status) { status[CS_NGROUPS] = *tot; }
 
-constexpr int TILE_THREADS = 1024;
+constexpr int TILE_THREADS_DEFAULT = 256;
 
 }  // namespace
 
@@ -467,11 +468,22 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
   cudaStream_t st = ctx->stream;
   DevBuf* B = ctx->buf;
   const int64_t n = g.n; const int k = g.k; const uint32_t W = g.W, S = g.S;
-  // ---- geometry: as many table entries as fit the opt-in shared memory ----
-  const size_t smem_limit = (ctx->smem_optin ? ctx->smem_optin : 232448) - 1024;
+  // ---- geometry: CTAs of `threads` threads, 1024/threads of them per SM, each with an equal share of the opt-in
+  // shared memory for its table (TB_TILE_THREADS=256|512|1024 overrides the default for experiments) ----
+  int threads = TILE_THREADS_DEFAULT;
+  if (const char* e = getenv("TB_TILE_THREADS")) { const int t = atoi(e); if (t == 256 || t == 512 || t == 1024) threads = t; }
+  const int ctas_per_sm = 1024 / threads;
+  const size_t smem_sm = ctx->smem_optin ? ctx->smem_optin + 1024 : 233472;   // shared memory per SM (opt-in per block + 1 KB reserved)
+  const size_t smem_limit = smem_sm / ctas_per_sm - 1024 - 512;               // per CTA: minus the reserved KB and the static part
   uint32_t E = 8192;   // region bases are u16 and the match key keeps 13 bits for the entry
   while (E > 64 && tile_smem_bytes((uint32_t)k, E, W) > smem_limit) E -= 64;
-  if (tile_smem_bytes((uint32_t)k, E, W) > smem_limit) { ctx->set_error("tb_collapse_window: %d samples do not fit the shared-memory group table", k); return 1; }
+  if (tile_smem_bytes((uint32_t)k, E, W) > smem_limit) {
+    if (threads != 1024) { threads = 1024; }   // fall through to the single-CTA geometry below
+    const size_t lim1 = smem_sm - 1024 - 512;
+    E = 8192;
+    while (E > 64 && tile_smem_bytes((uint32_t)k, E, W) > lim1) E -= 64;
+    if (tile_smem_bytes((uint32_t)k, E, W) > lim1) { ctx->set_error("tb_collapse_window: %d samples do not fit the shared-memory group table", k); return 1; }
+  }
   const uint32_t cap_records = (uint32_t)(((uint64_t)(E - 1) * 4) / 5);   // floor(1.25*n)+1 <= E
   const uint32_t T = cap_records / 2;
   if (T < 8) { ctx->set_error("tb_collapse_window: %d samples leave no room for a shared-memory tile", k); return 1; }
@@ -504,10 +516,19 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
   tp.slot_counter = B[XB_WORK].as<unsigned int>();
   TB_CUDA(cudaMemsetAsync(tp.slot_counter, 0, 64, st));
   const size_t smem = tile_smem_bytes((uint32_t)k, E, W);
-  TB_CUDA(cudaFuncSetAttribute(col_tile_kernel<TILE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned want = (unsigned)ctx->sm_count * (1024u / (unsigned)threads);
+  const unsigned grid = M < want ? M : want;
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
-  const unsigned grid = (unsigned)(M < (uint32_t)ctx->sm_count ? M : (uint32_t)ctx->sm_count);
-  col_tile_kernel<TILE_THREADS><<<grid, TILE_THREADS, smem, st>>>(in, tp);
+  if (threads == 1024) {
+    TB_CUDA(cudaFuncSetAttribute(col_tile_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    col_tile_kernel<1024><<<grid, 1024, smem, st>>>(in, tp);
+  } else if (threads == 512) {
+    TB_CUDA(cudaFuncSetAttribute(col_tile_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    col_tile_kernel<512><<<grid, 512, smem, st>>>(in, tp);
+  } else {
+    TB_CUDA(cudaFuncSetAttribute(col_tile_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    col_tile_kernel<256><<<grid, 256, smem, st>>>(in, tp);
+  }
   ctx->launches++;
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[1], st));
   // ---- C6 ----

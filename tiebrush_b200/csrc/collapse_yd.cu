@@ -197,7 +197,7 @@ __global__ void yd_subchain_total_kernel(const uint32_t* tot, uint32_t* heads, u
 }
 
 constexpr int YD_WARPS = 8;
-constexpr uint32_t YD_LONG = 96;     // sub-chains longer than this are walked by the whole warp
+constexpr uint32_t YD_LONG = 16;     // sub-chains longer than this are walked by the whole warp
 
 // ---- Y6: frontier recurrence -> kept-exon count per member -----------------------------------------------------------
 struct Frontier {
@@ -230,77 +230,15 @@ struct Frontier {
   }
 };
 
-__global__ void __launch_bounds__(YD_WARPS * 32) yd_frontier_kernel(ColIn in, const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ rep,
-                                                                   const uint32_t* __restrict__ chain, const uint32_t* __restrict__ heads,
-                                                                   unsigned long long* work, const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre,
-                                                                   uint8_t* __restrict__ kept) {
-  __shared__ GDesc s_desc[YD_WARPS][32];
-  __shared__ uint32_t s_g[YD_WARPS][32];
-  __shared__ uint8_t s_r[YD_WARPS][32];
-  const int wl = tb_warp(), lane = tb_lane();
-  const unsigned long long nsub = work[1];
-  for (;;) {
-    unsigned long long j0 = 0;
-    if (lane == 0) j0 = atomicAdd(&work[0], 32ULL);
-    j0 = __shfl_sync(0xffffffffu, j0, 0);
-    if (j0 >= nsub) break;
-    const unsigned long long j = j0 + lane;
-    uint32_t c0 = 0, c1 = 0;
-    if (j < nsub) { c0 = heads[j]; c1 = heads[j + 1]; }
-    const uint32_t len = c1 - c0;
-    if (len > 0 && len <= YD_LONG) {   // short sub-chains: one per lane
-      Frontier F; F.reset();
-      for (uint32_t i = c0; i < c1; ++i) {
-        const uint32_t g = chain[i];
-        kept[i] = (uint8_t)F.step(in, cdesc[g], rep[g], U, rankpre);
-      }
-    }
-    unsigned longs = __ballot_sync(0xffffffffu, len > YD_LONG);
-    while (longs) {                    // long sub-chains: lanes prefetch 32 descriptors, lane 0 runs the recurrence
-      const int q = __ffs(longs) - 1; longs &= longs - 1;
-      const uint32_t a = __shfl_sync(0xffffffffu, c0, q), b = __shfl_sync(0xffffffffu, c1, q);
-      Frontier F; F.reset();
-      uint32_t gnext = 0; GDesc dnext; dnext.start = 0; dnext.meta = 0; dnext.e0 = dnext.s1 = dnext.e1 = dnext.s2 = dnext.e2 = dnext.zend = 0;
-      if (a + lane < b) { gnext = chain[a + lane]; dnext = cdesc[gnext]; }
-      for (uint32_t cb = a; cb < b; cb += 32) {
-        s_desc[wl][lane] = dnext; s_g[wl][lane] = gnext;
-        __syncwarp();
-        if (cb + 32 + lane < b) { gnext = chain[cb + 32 + lane]; dnext = cdesc[gnext]; }   // prefetch the next batch
-        if (lane == 0) {
-          const int cnt = (int)((b - cb) < 32u ? (b - cb) : 32u);
-          for (int t = 0; t < cnt; ++t) {
-            const GDesc& d = s_desc[wl][t];
-            const uint32_t rr = ((d.meta & 0xffffu) > (uint32_t)YD_INLINE_EX) ? rep[s_g[wl][t]] : 0u;
-            s_r[wl][t] = (uint8_t)F.step(in, d, rr, U, rankpre);
-          }
-        }
-        __syncwarp();
-        if (cb + lane < b) kept[cb + lane] = s_r[wl][lane];
-        __syncwarp();
-      }
-    }
-  }
-}
-
-// ---- Y7: links of the kept exons into the chain bitmaps ---------------------------------------------------------------
-__global__ void __launch_bounds__(256) yd_link_kernel(ColIn in, const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ rep, const uint32_t* __restrict__ chain,
-                                                      const uint8_t* __restrict__ kept, int64_t n_members, const unsigned long long* __restrict__ colbase, int nchains,
-                                                      const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre,
-                                                      unsigned long long* __restrict__ bm, int64_t lpad) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_members) return;
-  const uint32_t g = chain[i];
-  const GDesc d = cdesc[g];
-  const uint32_t r = kept[i];
-  const int64_t base = (int64_t)yd_chain_of(colbase, nchains, i) * lpad;
-  // exon [s,t] sets links s .. t-1
+// links of the first `r` exons of a read into the chain bitmap that starts at bit `base` (exon [s,t] sets links s..t-1)
+__device__ __forceinline__ void yd_emit_links(const ColIn& in, const GDesc& d, uint32_t r, uint32_t rep, const uint32_t* U, const uint32_t* rankpre,
+                                              unsigned long long* bm, int64_t base) {
   if (d.e0 > d.start) yd_set_bits64(bm, base + d.start, base + d.e0 - 1);
   if (r >= 2 && d.e1 > d.s1) yd_set_bits64(bm, base + d.s1, base + d.e1 - 1);
   if (r >= 3 && d.e2 > d.s2) yd_set_bits64(bm, base + d.s2, base + d.e2 - 1);
   if (r > (uint32_t)YD_INLINE_EX) {
     const int ubase = in.pos_lo + 1;
-    const uint32_t rr = rep[g];
-    ExonIter it; it.init(in.cigar, in.cig_off[rr], in.cig_off[rr + 1], in.pos[rr]);
+    ExonIter it; it.init(in.cigar, in.cig_off[rep], in.cig_off[rep + 1], in.pos[rep]);
     int s, e; uint32_t j = 0;
     while (j < r && it.next(s, e)) {
       if (j++ < (uint32_t)YD_INLINE_EX) continue;
@@ -308,6 +246,118 @@ __global__ void __launch_bounds__(256) yd_link_kernel(ColIn in, const GDesc* __r
       if (ce > cs) yd_set_bits64(bm, base + cs, base + ce - 1);
     }
   }
+}
+
+// Y6: frontier recurrence -> kept-exon count per member.
+// The member array (all chains back to back, sub-chain heads flagged) is cut into work units that start at sub-chain
+// heads (first head at or after a multiple of YD_UNIT members), so a unit needs no state from outside. Persistent warps
+// pull units and walk them 32 members per step, YD_PF steps of descriptors in flight. Within a step the frontier is
+// SPECULATED ("nothing is dropped, nobody but a head finds the list empty": member j then sees the maximum end of the
+// members before it in its sub-chain, a segmented prefix max); if every lane's own exons pass under that assumption it
+// is exact by induction, otherwise lane 0 replays the step sequentially.
+constexpr int YD_PF = 4;
+constexpr uint32_t YD_UNIT = 2048;
+__global__ void __launch_bounds__(256) yd_unit_kernel(const uint32_t* __restrict__ heads, const uint32_t* __restrict__ nsub_p, uint32_t n_members, uint32_t nunits,
+                                                      uint32_t* __restrict__ ustart) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nsub = *nsub_p;
+  if (u > nunits) return;
+  if (u == nunits) { ustart[u] = n_members; return; }
+  const uint32_t target = u * YD_UNIT;
+  uint32_t lo = 0, hi = nsub;   // first h in [0,nsub] with heads[h] >= target (heads[nsub] = n_members)
+  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (heads[mid] >= target) hi = mid; else lo = mid + 1; }
+  ustart[u] = heads[lo];
+}
+
+__global__ void __launch_bounds__(YD_WARPS * 32) yd_frontier_kernel(ColIn in, const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ rep,
+                                                                   const uint32_t* __restrict__ chain, const uint32_t* __restrict__ headflag,
+                                                                   const uint32_t* __restrict__ ustart, uint32_t nunits, unsigned long long* work,
+                                                                   const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre, uint8_t* __restrict__ kept) {
+  __shared__ GDesc s_desc[YD_WARPS][32];
+  __shared__ uint32_t s_g[YD_WARPS][32];
+  __shared__ uint8_t s_r[YD_WARPS][32];
+  const int wl = tb_warp(), lane = tb_lane();
+  for (;;) {
+    unsigned long long u = 0;
+    if (lane == 0) u = atomicAdd(&work[0], 1ULL);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= nunits) break;
+    const uint32_t a = ustart[u], b = ustart[u + 1];
+    if (a >= b) continue;
+    Frontier F; F.reset();
+    GDesc dq[YD_PF]; uint32_t gq[YD_PF];   // gq: group id | head flag << 31
+#pragma unroll
+    for (int p = 0; p < YD_PF; ++p) {
+      gq[p] = 0; dq[p].start = 0; dq[p].meta = 0; dq[p].e0 = dq[p].s1 = dq[p].e1 = dq[p].s2 = dq[p].e2 = dq[p].zend = 0;
+      const uint32_t idx = a + (uint32_t)p * 32u + lane;
+      if (idx < b) { const uint32_t g = chain[idx]; dq[p] = cdesc[g]; gq[p] = g | (headflag[idx] << 31); }
+    }
+    for (uint32_t cb0 = a; cb0 < b; cb0 += 32u * YD_PF) {
+#pragma unroll
+      for (int p = 0; p < YD_PF; ++p) {
+        const uint32_t cb = cb0 + (uint32_t)p * 32u;
+        if (cb < b) {   // warp-uniform
+          const GDesc dm = dq[p]; const uint32_t g = gq[p] & 0x7fffffffu; const int head = (int)(gq[p] >> 31);
+          { const uint32_t idx = cb + 32u * YD_PF + lane; if (idx < b) { const uint32_t g2 = chain[idx]; dq[p] = cdesc[g2]; gq[p] = g2 | (headflag[idx] << 31); } }
+          const int cnt = (int)((b - cb) < 32u ? (b - cb) : 32u);
+          const bool live = lane < cnt;
+          const int ne = (int)(dm.meta & 0xffffu);
+          int v = live ? dm.zend : -1, h = head;
+#pragma unroll
+          for (int dd = 1; dd < 32; dd <<= 1) {
+            const int v2 = __shfl_up_sync(0xffffffffu, v, dd), h2 = __shfl_up_sync(0xffffffffu, h, dd);
+            if (lane >= dd) { if (!h) v = max(v, v2); h |= h2; }
+          }
+          if (!h) v = max(v, F.E);                     // no head at or before this lane: the carried sub-chain continues
+          const int e_after = __shfl_sync(0xffffffffu, v, cnt - 1);   // frontier after the step if the speculation holds
+          int pm = __shfl_up_sync(0xffffffffu, v, 1);
+          if (lane == 0) pm = F.E;
+          bool fine = true;
+          if (live && !head) {
+            fine = pm >= dm.start && ne <= YD_INLINE_EX;
+            if (ne >= 2) fine = fine && dm.s1 <= max(pm, dm.e0);
+            if (ne >= 3) fine = fine && dm.s2 <= max(pm, max(dm.e0, dm.e1));
+          }
+          uint32_t r = (uint32_t)ne;
+          if (__all_sync(0xffffffffu, fine)) {
+            F.E = e_after;
+          } else {
+            s_desc[wl][lane] = dm; s_g[wl][lane] = g | ((uint32_t)head << 31);
+            __syncwarp();
+            if (lane == 0) {
+              for (int t = 0; t < cnt; ++t) {
+                const GDesc& d = s_desc[wl][t];
+                const uint32_t gg = s_g[wl][t];
+                if (gg >> 31) F.reset();
+                const uint32_t rr = ((d.meta & 0xffffu) > (uint32_t)YD_INLINE_EX) ? rep[gg & 0x7fffffffu] : 0u;
+                s_r[wl][t] = (uint8_t)F.step(in, d, rr, U, rankpre);
+              }
+            }
+            F.E = __shfl_sync(0xffffffffu, F.E, 0);
+            __syncwarp();
+            r = s_r[wl][lane];
+            __syncwarp();
+          }
+          if (live) kept[cb + lane] = (uint8_t)r;
+        }
+      }
+    }
+  }
+}
+
+// Y7: kept exons OR their links into the chain bitmaps; compact start per member for the lookup
+__global__ void __launch_bounds__(256) yd_link_kernel(ColIn in, const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ rep, const uint32_t* __restrict__ chain,
+                                                      const uint8_t* __restrict__ kept, int64_t n_members, const unsigned long long* __restrict__ colbase, int nchains,
+                                                      const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre,
+                                                      unsigned long long* __restrict__ bm, int64_t lpad, int32_t* __restrict__ mstart) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_members) return;
+  const uint32_t g = chain[i];
+  const GDesc d = cdesc[g];
+  const uint32_t r = kept[i];
+  const int64_t base = (int64_t)yd_chain_of(colbase, nchains, i) * lpad;
+  yd_emit_links(in, d, r, r > (uint32_t)YD_INLINE_EX ? rep[g] : 0u, U, rankpre, bm, base);
+  mstart[i] = d.start;
 }
 
 // ---- Y8: position of the last clear link before every 512-bit block ---------------------------------------------------
@@ -325,14 +375,14 @@ struct LastZeroIn {   // highest clear bit of block b (global bit index), -1 if 
 struct LastZeroOut { long long* lz; __device__ void operator()(int64_t b, long long exc, long long) const { lz[b] = exc; } };
 
 // ---- Y9: d = number of consecutive set links ending at start-1 --------------------------------------------------------
-__global__ void __launch_bounds__(256) yd_lookup_kernel(const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ chain, int64_t n_members,
+__global__ void __launch_bounds__(256) yd_lookup_kernel(const int32_t* __restrict__ mstart, const uint32_t* __restrict__ chain, int64_t n_members,
                                                         const unsigned long long* __restrict__ colbase, int nchains, const unsigned long long* __restrict__ bm,
                                                         const long long* __restrict__ lz, int64_t lpad, int32_t* __restrict__ yd) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_members) return;
-  const uint32_t g = chain[i];
-  const int x = cdesc[g].start;
+  const int x = mstart[i];
   if (x <= 0) return;
+  const uint32_t g = chain[i];
   const int64_t base = (int64_t)yd_chain_of(colbase, nchains, i) * lpad;
   const int64_t q = base + x - 1;
   int64_t w = q >> 6; const int b = (int)(q & 63);
@@ -589,18 +639,24 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
     ctx->launches++;
     if (parallel) {
       // ---- Y6-Y9 ----
-      TB_CUDA(B[XB_YDKEPT].ensure((size_t)n_members + 64));
+      TB_CUDA(B[XB_YDKEPT].ensure(sizeof(int32_t) * (size_t)n_members + (size_t)n_members + 128));
       TB_CUDA(B[XB_YDBM].ensure(sizeof(uint64_t) * (size_t)nwords + 64));
       TB_CUDA(B[XB_YDLZ].ensure(sizeof(int64_t) * (size_t)nblocks512 + 64));
-      uint8_t* kept = B[XB_YDKEPT].as<uint8_t>();
+      int32_t* mstart = B[XB_YDKEPT].as<int32_t>();
+      uint8_t* kept = (uint8_t*)(mstart + n_members + 8);
       unsigned long long* bm = B[XB_YDBM].as<unsigned long long>();
       long long* lz = B[XB_YDLZ].as<long long>();
       TB_CUDA(cudaMemsetAsync(bm, 0, sizeof(uint64_t) * (size_t)nwords, st));
-      yd_frontier_kernel<<<(unsigned)ctx->sm_count * 8, YD_WARPS * 32, 0, st>>>(in, cdesc, grp.rep, chain, heads, work, U, rankpre, kept);
-      yd_link_kernel<<<tb_grid_for(n_members, 256), 256, 0, st>>>(in, cdesc, grp.rep, chain, kept, n_members, colbase, nchains, U, rankpre, bm, lpad);
+      const uint32_t nunits = (uint32_t)((n_members + YD_UNIT - 1) / YD_UNIT);
+      TB_CUDA(B[XB_YDUNIT].ensure(sizeof(uint32_t) * ((size_t)nunits + 2)));
+      uint32_t* ustart = B[XB_YDUNIT].as<uint32_t>();
+      yd_unit_kernel<<<tb_grid_for((int64_t)nunits + 1, 256), 256, 0, st>>>(heads, B[XB_AGG].as<uint32_t>() + tb_scan_blocks(n_members), (uint32_t)n_members, nunits, ustart);
+      yd_frontier_kernel<<<(unsigned)ctx->sm_count * 8, YD_WARPS * 32, 0, st>>>(in, cdesc, grp.rep, chain, flag, ustart, nunits, work, U, rankpre, kept);
+      ctx->launches++;
+      yd_link_kernel<<<tb_grid_for(n_members, 256), 256, 0, st>>>(in, cdesc, grp.rep, chain, kept, n_members, colbase, nchains, U, rankpre, bm, lpad, mstart);
       ctx->launches += 2;
       TB_CUDA((tb_device_scan<OpMaxI64>(ctx, LastZeroIn{bm}, nblocks512, B[XB_AGG].as<long long>(), LastZeroOut{lz})));
-      yd_lookup_kernel<<<tb_grid_for(n_members, 256), 256, 0, st>>>(cdesc, chain, n_members, colbase, nchains, bm, lz, lpad, ydc);
+      yd_lookup_kernel<<<tb_grid_for(n_members, 256), 256, 0, st>>>(mstart, chain, n_members, colbase, nchains, bm, lz, lpad, ydc);
       ctx->launches++;
     } else {
       const size_t smem = (size_t)YD_WARPS * 2 * YD_CAP_SMEM * 32 * sizeof(uint32_t);

@@ -128,24 +128,31 @@ __global__ void cov_publish_kernel(const uint32_t* nb_total, const long long* le
   if (len_total) status[ST_DENSE_LEN] = *len_total;
 }
 
-// ---- K7 + K9 insert: one thread per record walks its CIGAR ----------------------------------------
+// ---- K7 + K9 insert ---------------------------------------------------------------------------------
+// Junction table: open addressing on the full 64-bit key (start<<33 | end<<2 | strand code; code 3 never occurs, so ~0 is
+// a safe EMPTY) claimed by CAS, the reference id claimed by a second CAS (-1 = not yet written), the value added with a
+// RED. Equality is decided on the real key and tid, never on a hash.
 struct JTable {
-  unsigned long long* tag; unsigned long long* kmin; unsigned long long* kmax; int32_t* tmin; int32_t* tmax; long long* val;
+  unsigned long long* key; int32_t* tid; long long* val;
   uint32_t mask; uint64_t seed;
 };
+constexpr unsigned long long J_EMPTY = ~0ULL;
 
 __device__ __forceinline__ void junc_insert(const JTable& jt, int tid, unsigned long long k64, long long w, long long* status) {
-  unsigned long long tag = tb_mix64(k64 ^ tb_mix64((unsigned long long)(uint32_t)tid + jt.seed));
-  if (tag == 0) tag = 1;
-  uint32_t s = (uint32_t)(tag >> 20) & jt.mask;
+  const unsigned long long h = tb_mix64(k64 ^ tb_mix64((unsigned long long)(uint32_t)tid + jt.seed));
+  uint32_t s = (uint32_t)(h >> 20) & jt.mask;
   for (uint32_t probe = 0; probe <= jt.mask; ++probe) {
-    unsigned long long old = atomicCAS(&jt.tag[s], 0ULL, tag);
-    if (old == 0ULL || old == tag) {
-      if (old == 0ULL) atomicAdd((unsigned long long*)&status[ST_NJUNC], 1ULL);
-      atomicAdd((unsigned long long*)&jt.val[s], (unsigned long long)w);
-      atomicMin(&jt.kmin[s], k64); atomicMax(&jt.kmax[s], k64);
-      atomicMin(&jt.tmin[s], tid); atomicMax(&jt.tmax[s], tid);
-      return;
+    unsigned long long cur = jt.key[s];
+    if (cur == J_EMPTY) {
+      cur = atomicCAS(&jt.key[s], J_EMPTY, k64);
+      if (cur == J_EMPTY) { atomicAdd((unsigned long long*)&status[ST_NJUNC], 1ULL); cur = k64; }
+    }
+    if (cur == k64) {
+      int t = jt.tid[s];
+      if (t == -1) { t = atomicCAS(&jt.tid[s], -1, tid); if (t == -1) t = tid; }
+      if (t == tid) { atomicAdd((unsigned long long*)&jt.val[s], (unsigned long long)w); return; }
+      // same coordinates on another reference: a different junction, keep probing. The slot claim above counted a new
+      // junction only when this thread created the key; a (key, other tid) pair is created further down the probe.
     }
     s = (s + 1) & jt.mask;
   }
@@ -155,53 +162,80 @@ __device__ __forceinline__ void junc_insert(const JTable& jt, int tid, unsigned 
 __device__ __forceinline__ unsigned strand_code(uint8_t c) { return c == '+' ? 0u : (c == '-' ? 1u : 2u); }  // '+' < '-' < '.'
 __device__ __forceinline__ uint8_t strand_char(unsigned c) { return c == 0 ? '+' : (c == 1 ? '-' : '.'); }
 
+// Sum `val` over runs of adjacent lanes (`head` marks the first lane of a run; records are coordinate sorted, so the
+// members of a pile-up sit in adjacent lanes); returns true on the last lane of a run, with the run total in `val`.
+__device__ __forceinline__ bool cov_run_sum(bool head_in, long long& val) {
+  const unsigned lane = threadIdx.x & 31;
+  const int head = (lane == 0 || head_in) ? 1 : 0;
+  int h = head;
+  long long v = val;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const long long v2 = __shfl_up_sync(0xffffffffu, v, d); const int h2 = __shfl_up_sync(0xffffffffu, h, d);
+    if ((int)lane >= d) { if (!h) v += v2; h |= h2; }
+  }
+  const int next_head = __shfl_down_sync(0xffffffffu, head, 1);
+  val = v;
+  return lane == 31 || next_head;
+}
+
+// One thread per record walks its CIGAR; the warp advances op by op so that lanes with the same alignment (pile-ups)
+// merge their updates before touching memory: one 64-bit RED per distinct difference-array cell and warp step.
 __global__ void __launch_bounds__(256) cov_accumulate_kernel(CovIn in, const uint32_t* __restrict__ bid, const int32_t* __restrict__ bstart,
                                                              const long long* __restrict__ bbase, long long* __restrict__ diff,
                                                              int do_cov, int do_junc, JTable jt, long long* __restrict__ status) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= in.n) return;
-  uint32_t c0 = in.cig_off[i], c1 = in.cig_off[i + 1];
-  int pos = in.pos[i];
-  long long w = (long long)rintf(in.yc[i] * (float)COV_FX_SCALE);
-  uint32_t b = bid[i];
-  long long shift = bbase[b] - (long long)bstart[b];  // compact index of 1-based coordinate x is x + shift
-  int tid = in.tid[i];
-  unsigned sc = strand_code(in.strand[i]);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < in.n;
+  uint32_t c0 = 0, nc = 0; int pos = 0, tid = 0; long long w = 0, shift = 0; unsigned sc = 0;
+  if (valid) {
+    c0 = in.cig_off[i]; nc = in.cig_off[i + 1] - c0;
+    pos = in.pos[i];
+    w = (long long)rintf(in.yc[i] * (float)COV_FX_SCALE);
+    const uint32_t b = bid[i];
+    shift = bbase[b] - (long long)bstart[b];  // compact index of 1-based coordinate x is x + shift
+    tid = in.tid[i];
+    sc = strand_code(in.strand[i]);
+  }
+  const uint32_t maxnc = __reduce_max_sync(0xffffffffu, nc);
   // setupCoordinates state (GSam.cpp:351-417) for the junctions
   int l = 0, exstart = pos, nclosed = 0, last_end = 0;
   bool intron = false, ins = false;
-  for (uint32_t c = c0; c < c1; ++c) {
-    uint32_t cw = in.cigar[c];
-    uint32_t op = cw & 0xf; int len = (int)(cw >> 4);
-    switch (op) {
-      case TB_OP_M:
-        if (do_cov && len > 0) {
-          long long ci = (long long)(pos + l + 1) + shift;
-          atomicAdd((unsigned long long*)&diff[ci], (unsigned long long)w);
-          atomicAdd((unsigned long long*)&diff[ci + len], (unsigned long long)(-w));
-        }
-        l += len; intron = false; ins = false; break;
-      case TB_OP_EQ: case TB_OP_X: case TB_OP_D:
-        l += len; intron = false; ins = false; break;
-      case TB_OP_N:
-        if (!ins || !intron) {
-          if (do_junc && nclosed > 0) {
-            unsigned long long k64 = ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc;
-            junc_insert(jt, tid, k64, w, status);
+  const unsigned long long NOID = ~0ULL;
+  for (uint32_t q = 0; q <= maxnc; ++q) {   // the extra round flushes the junction that ends at the last exon
+    unsigned long long ida = NOID, idb = NOID, jid = NOID; long long wa = 0, wb = 0, wj = 0;
+    if (q < nc) {
+      const uint32_t cw = in.cigar[c0 + q];
+      const uint32_t op = cw & 0xf; const int len = (int)(cw >> 4);
+      switch (op) {
+        case TB_OP_M:
+          if (do_cov && len > 0) { ida = (unsigned long long)((long long)(pos + l + 1) + shift); idb = ida + (unsigned long long)len; wa = w; wb = -w; }
+          l += len; intron = false; ins = false; break;
+        case TB_OP_EQ: case TB_OP_X: case TB_OP_D:
+          l += len; intron = false; ins = false; break;
+        case TB_OP_N:
+          if (!ins || !intron) {
+            if (do_junc && nclosed > 0) { jid = ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc; wj = w; }
+            last_end = pos + l; nclosed++;
           }
-          last_end = pos + l; nclosed++;
-        }
-        l += len; exstart = pos + l; intron = true; break;
-      case TB_OP_S: case TB_OP_H:
-        intron = false; ins = false; break;
-      case TB_OP_I:
-        ins = true; break;
-      default: break;
+          l += len; exstart = pos + l; intron = true; break;
+        case TB_OP_S: case TB_OP_H:
+          intron = false; ins = false; break;
+        case TB_OP_I:
+          ins = true; break;
+        default: break;
+      }
+    } else if (valid && q == nc && do_junc && nclosed > 0) {
+      jid = ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc; wj = w;
     }
-  }
-  if (do_junc && nclosed > 0) {
-    unsigned long long k64 = ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc;
-    junc_insert(jt, tid, k64, w, status);
+    if (do_cov && __any_sync(0xffffffffu, ida != NOID)) {
+      const unsigned long long pa = __shfl_up_sync(0xffffffffu, ida, 1), pb = __shfl_up_sync(0xffffffffu, idb, 1);
+      if (cov_run_sum(pa != ida, wa) && ida != NOID && wa != 0) atomicAdd((unsigned long long*)&diff[ida], (unsigned long long)wa);
+      if (cov_run_sum(pb != idb, wb) && idb != NOID && wb != 0) atomicAdd((unsigned long long*)&diff[idb], (unsigned long long)wb);
+    }
+    if (do_junc && __any_sync(0xffffffffu, jid != NOID)) {
+      const unsigned long long pj = __shfl_up_sync(0xffffffffu, jid, 1); const int pt = __shfl_up_sync(0xffffffffu, tid, 1);
+      if (cov_run_sum(pj != jid || pt != tid, wj) && jid != NOID) junc_insert(jt, tid, jid, wj, status);
+    }
   }
 }
 
@@ -258,24 +292,23 @@ __global__ void cov_store_total_kernel(const SumNz* tot, const uint32_t* nruns, 
 __global__ void __launch_bounds__(256) junc_init_kernel(JTable jt, uint32_t cap) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= cap) return;
-  jt.tag[s] = 0; jt.kmin[s] = ~0ULL; jt.kmax[s] = 0; jt.tmin[s] = 0x7fffffff; jt.tmax[s] = -0x7fffffff - 1; jt.val[s] = 0;
+  jt.key[s] = J_EMPTY; jt.tid[s] = -1; jt.val[s] = 0;
 }
 
 __global__ void __launch_bounds__(256) junc_compact_kernel(JTable jt, uint32_t cap, unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx,
                                                            unsigned long long* __restrict__ counter, long long* __restrict__ status) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= cap) return;
-  if (jt.tag[s] == 0) return;
-  if (jt.kmin[s] != jt.kmax[s] || jt.tmin[s] != jt.tmax[s]) status[ST_JCOLLISION] = 1;
+  if (jt.key[s] == J_EMPTY) return;
   unsigned long long k = atomicAdd(counter, 1ULL);
-  keys[k] = jt.kmin[s];
+  keys[k] = jt.key[s];
   idx[k] = s;
 }
 
 __global__ void __launch_bounds__(256) junc_tidkey_kernel(JTable jt, const uint32_t* __restrict__ idx, int64_t J, unsigned long long* __restrict__ tkeys) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= J) return;
-  tkeys[k] = (unsigned long long)(uint32_t)jt.tmin[idx[k]];
+  tkeys[k] = (unsigned long long)(uint32_t)jt.tid[idx[k]];
 }
 
 __global__ void __launch_bounds__(256) junc_emit_kernel(JTable jt, const uint32_t* __restrict__ idx, int64_t J, int32_t* o_tid, int32_t* o_start,
@@ -283,8 +316,8 @@ __global__ void __launch_bounds__(256) junc_emit_kernel(JTable jt, const uint32_
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= J) return;
   uint32_t s = idx[k];
-  unsigned long long key = jt.kmin[s];
-  o_tid[k] = jt.tmin[s];
+  unsigned long long key = jt.key[s];
+  o_tid[k] = jt.tid[s];
   o_start[k] = (int32_t)(key >> 33);
   o_end[k] = (int32_t)((key >> 2) & 0x7fffffffULL);
   o_strand[k] = strand_char((unsigned)(key & 3));
@@ -384,12 +417,9 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
   for (int attempt = 0;; ++attempt) {
     if (do_junc) {
       TB_CUDA(B[CB_JTAG].ensure(sizeof(uint64_t) * jcap));
-      TB_CUDA(B[CB_JKMIN].ensure(sizeof(uint64_t) * jcap));
-      TB_CUDA(B[CB_JKMAX].ensure(sizeof(uint64_t) * jcap));
-      TB_CUDA(B[CB_JTID].ensure(sizeof(int32_t) * 2 * jcap));
+      TB_CUDA(B[CB_JTID].ensure(sizeof(int32_t) * jcap));
       TB_CUDA(B[CB_JVAL].ensure(sizeof(int64_t) * jcap));
-      jt.tag = B[CB_JTAG].as<unsigned long long>(); jt.kmin = B[CB_JKMIN].as<unsigned long long>(); jt.kmax = B[CB_JKMAX].as<unsigned long long>();
-      jt.tmin = B[CB_JTID].as<int32_t>(); jt.tmax = jt.tmin + jcap; jt.val = B[CB_JVAL].as<long long>();
+      jt.key = B[CB_JTAG].as<unsigned long long>(); jt.tid = B[CB_JTID].as<int32_t>(); jt.val = B[CB_JVAL].as<long long>();
       jt.mask = jcap - 1; jt.seed = seed;
       junc_init_kernel<<<grid_for(jcap, 256), 256, 0, st>>>(jt, jcap);
       ctx->launches++;
@@ -418,8 +448,9 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
 
   // ---- K8 ----
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[10], st));
-  int64_t kmax = 2 * ncig + 16;
   if (do_cov) {
+    // change points: at most one per non-zero difference cell, and no more than two per M block
+    int64_t kmax = 2 * ncig + 16; if (L + 1 < kmax) kmax = L + 1;
     TB_CUDA(B[CB_CPPOS].ensure(sizeof(int64_t) * kmax));
     TB_CUDA(B[CB_CPDEPTH].ensure(sizeof(int64_t) * kmax));
     long long* d_diff = B[CB_DIFF].as<long long>();
@@ -428,10 +459,15 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     TB_CUDA((tb_device_scan<OpSumNz>(ctx, DiffIn{d_diff}, L, B[CB_AGG].as<SumNz>(), ChangeOut{d_diff, cppos, cpdepth})));
     cov_store_total_kernel<<<1, 1, 0, st>>>(B[CB_AGG].as<SumNz>() + tb_scan_blocks(L), nullptr, d_status);
     ctx->launches++;
+    // the number of change points is only known on the device
+    TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    const int64_t K = h_status[ST_NCHANGE];
     // output staging
     int64_t cap = runs->capacity;
     int32_t *o_tid = runs->tid, *o_start = runs->start0, *o_end = runs->end0; double* o_val = runs->value;
-    int64_t stage_cap = cap < kmax ? cap : kmax;
+    int64_t stage_cap = cap < K ? cap : K;
+    if (stage_cap < 1) stage_cap = 1;
     if (!runs->on_device) {
       TB_CUDA(ctx->out_stage[0].ensure(sizeof(int32_t) * stage_cap)); TB_CUDA(ctx->out_stage[1].ensure(sizeof(int32_t) * stage_cap));
       TB_CUDA(ctx->out_stage[2].ensure(sizeof(int32_t) * stage_cap)); TB_CUDA(ctx->out_stage[3].ensure(sizeof(double) * stage_cap));
@@ -440,9 +476,8 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     }
     RunOut ro{cppos, cpdepth, d_status, B[CB_BBASE].as<long long>(), B[CB_BSTART].as<int32_t>(), B[CB_BTID].as<int32_t>(),
               o_tid, o_start, o_end, o_val, stage_cap};
-    // the number of change points is only known on the device: scan the upper bound, functor masks the tail
-    TB_CUDA((tb_device_scan<OpSumU32>(ctx, RunValidIn{cpdepth, d_status}, kmax, B[CB_AGG].as<uint32_t>(), ro)));
-    cov_store_total_kernel<<<1, 1, 0, st>>>(nullptr, B[CB_AGG].as<uint32_t>() + tb_scan_blocks(kmax), d_status);
+    TB_CUDA((tb_device_scan<OpSumU32>(ctx, RunValidIn{cpdepth, d_status}, K, B[CB_AGG].as<uint32_t>(), ro)));
+    cov_store_total_kernel<<<1, 1, 0, st>>>(nullptr, B[CB_AGG].as<uint32_t>() + tb_scan_blocks(K), d_status);
     ctx->launches++;
   }
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[11], st));
@@ -509,7 +544,6 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
       TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
     }
     TB_CUDA(cudaStreamSynchronize(st));
-    if (h_status[ST_JCOLLISION]) { ctx->set_error("junction fingerprint collision (retry with another seed not implemented)"); return 1; }
     juncs->n_juncs = J;
   }
   TB_CUDA(cudaStreamSynchronize(st));
