@@ -250,16 +250,20 @@ def main():
     if args.cov_records > 0:
         cov = synth.coverage_stream(args.cov_records, seed=rank, chroms=1, device=dev)
         ncov = args.cov_records
-        ocov = None
+        capr, capj = 2 * int(cov["n_cig"]) + 16, int(cov["n_cig"]) + 16
+        i32 = lambda m: torch.empty(m, dtype=torch.int32, device=dev)
+        ocov = dict(r_tid=i32(capr), r_start=i32(capr), r_end=i32(capr), r_val=torch.empty(capr, dtype=torch.float64, device=dev),
+                    j_tid=i32(capj), j_start=i32(capj), j_end=i32(capj), j_strand=torch.empty(capj, dtype=torch.uint8, device=dev),
+                    j_val=torch.empty(capj, dtype=torch.float64, device=dev))
         for _ in range(max(1, args.warmup)):
-            r = ctx.coverage_window(cov) if ocov is None else ctx.coverage_window(cov, out=ocov)
+            r = ctx.coverage_window(cov, out=ocov)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         cms = []
         barrier()
         with torch.cuda.stream(stream):
             c0.record(stream)
             for _ in range(args.steps):
-                r = ctx.coverage_window(cov)
+                r = ctx.coverage_window(cov, out=ocov)
                 cms.append(ctx.last_kernel_ms(1))
             c1.record(stream)
         barrier()

@@ -168,6 +168,9 @@ int tb_last_path(tb_ctx*);
 /* YD stage of the last tb_collapse_window call: 0 = parallel formulation (frontier recurrence + link bitmaps),
  * 1 = sequential segment lists (degenerate exons / more than 255 exons in a representative, or TB_YD_PATH=seq). */
 int tb_last_yd_path(tb_ctx*);
+/* Tile slots of the last call that were redone by the full-size-table launch (pile-up positions with more distinct
+ * alignments than a quarter-SM table holds). */
+int64_t tb_last_heavy_slots(tb_ctx*);
 /* Device time in ms of one stage of the last call, measured with CUDA events on the launching stream
  * (enabled by tb_set_profiling(ctx,1)):
  *   0 collapse tile kernel (dominant)      1 coverage accumulate kernel (dominant)

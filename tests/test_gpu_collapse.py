@@ -114,6 +114,30 @@ def test_collapse_table_overflow_falls_back_to_ordered_path():
         assert np.array_equal(np.asarray(got[key]), exp[key]), key
 
 
+def test_collapse_heavy_position_uses_full_size_table():
+    """A pile-up position with more distinct alignments than a quarter-SM table holds (but fewer than a full-SM one) is
+    redone by the second tile launch and stays on the tile path."""
+    from oracle import oracle
+    from tiebrush_b200 import api
+    rng = np.random.default_rng(15)
+    k, per = 3, 6000
+    n = k * per
+    a = rng.integers(1, 60, n); b = rng.integers(1, 60, n)     # ~3400 distinct (a,b) pairs at the pile-up position
+    cigar = np.stack([(a << 4) | 0, np.full(n, (1 << 4) | 2), (b << 4) | 0], 1).astype(np.uint32)
+    pos = np.where(rng.random(n) < 0.95, 7000, rng.integers(6000, 8000, n)).astype(np.int32)
+    order = np.concatenate([f * per + np.argsort(pos[f * per:(f + 1) * per], kind="stable") for f in range(k)])
+    cols = dict(pos=pos[order], flag=np.zeros(n, np.uint16), mapq=np.full(n, 60, np.uint8), strand=np.full(n, ord("-"), np.uint8),
+                nh=np.ones(n, np.uint16), cig_off=(np.arange(n + 1) * 3).astype(np.uint32), cigar=cigar[order].reshape(-1))
+    run_off = np.arange(k + 1, dtype=np.int64) * per
+    with api.Context(device=0, n_samples=k) as ctx:
+        got = ctx.collapse_window(cols, run_off)
+        assert ctx.last_path() == 0 and ctx.last_heavy_slots() >= 1
+    exp = oracle.collapse(cols, run_off)
+    assert got["n_groups"] == len(exp["rep_index"]) > 3000
+    for key in ("rep_index", "yc", "yx", "yd"):
+        assert np.array_equal(np.asarray(got[key]), exp[key]), key
+
+
 def test_collapse_pileup_position_single_mode():
     """A pile-up position (more records than a tile) with few distinct alignments stays on the tile path."""
     from oracle import oracle

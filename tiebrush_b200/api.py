@@ -73,6 +73,9 @@ class Context:
     def launch_count(self):
         return int(self.lib.tb_launch_count(self.h))
 
+    def last_heavy_slots(self):
+        return int(self.lib.tb_last_heavy_slots(self.h))
+
     def last_yd_path(self):
         """0 parallel YD formulation, 1 sequential segment lists."""
         return int(self.lib.tb_last_yd_path(self.h))

@@ -32,6 +32,9 @@ struct TileParams {
   const uint32_t* P; const uint32_t* slotpos; const uint32_t* off;
   uint32_t* gcount; uint32_t* st_rep; float* st_yc; uint32_t* st_yx; uint32_t* st_bits;
   long long* status; unsigned int* slot_counter; uint64_t seed;
+  uint32_t* heavy_list;        // launch 1: slots whose pile-up position overflowed this launch's table are appended here ...
+  const uint32_t* slot_list;   // launch 2 (one CTA per SM, full-size table): ... and redone from this list
+  uint32_t n_list;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -370,6 +373,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) col_tile_kernel(ColIn
   uint32_t kept_total = 0;   // thread 0 only
   auto fetch_meta = [&](SlotMeta& d) {   // one thread: claim the next slot and read its geometry
     SlotMeta t; t.m = atomicAdd(tp.slot_counter, 1u); t.rank0 = t.rank1 = t.p0 = t.p1 = 0;
+    if (tp.slot_list) t.m = t.m < tp.n_list ? tp.slot_list[t.m] : tp.M;
     if (t.m < tp.M) { t.p0 = tp.slotpos[t.m]; t.p1 = tp.slotpos[t.m + 1]; t.rank0 = tp.P[t.p0]; t.rank1 = tp.P[t.p1]; }
     d = t;
   };
@@ -390,11 +394,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) col_tile_kernel(ColIn
     const uint32_t m = cur.m, rank0 = cur.rank0, rank1 = cur.rank1, p0 = cur.p0, p1 = cur.p1;
     const uint32_t n_t = rank1 - rank0;
     if (n_t == 0) { if (tid == 0) tp.gcount[m] = 0; continue; }
-    uint32_t G = 0;
+    uint32_t G = 0, kept_slot = 0;   // kept_slot: thread 0 only
+    bool overflow = false;
     if (n_t <= tp.cap_records) {
       G = tile_process<THREADS>(in, tp, sm, n_t, rank0, false, rank0, s_scan, s_flags);
-      if (G == 0xffffffffu) { if (tid == 0) { tp.status[CS_TABLE_OVERFLOW] = 1; tp.gcount[m] = 0; } continue; }
-      if (tid == 0) kept_total += s_flags[0];
+      overflow = G == 0xffffffffu;
+      if (tid == 0) kept_slot = s_flags[0];
     } else {
       // the last position of the slot is a pile-up: split it off
       if (tid == 0) {
@@ -415,17 +420,28 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) col_tile_kernel(ColIn
       uint32_t G1 = 0;
       if (rb > rank0) {
         G1 = tile_process<THREADS>(in, tp, sm, rb - rank0, rank0, false, rank0, s_scan, s_flags);
-        if (G1 == 0xffffffffu) { if (tid == 0) { tp.status[CS_TABLE_OVERFLOW] = 1; tp.gcount[m] = 0; } continue; }
-        if (tid == 0) kept_total += s_flags[0];
+        overflow = G1 == 0xffffffffu;
+        if (tid == 0) kept_slot = s_flags[0];
       }
-      __syncthreads();
-      for (uint32_t f = tid; f < k; f += THREADS) { sm.a[f] = sm.b[f]; sm.b[f] = sm.c[f]; }
-      __syncthreads();
-      const uint32_t G2 = tile_process<THREADS>(in, tp, sm, rank1 - rb, rb, true, (uint64_t)rank0 + G1, s_scan, s_flags);
-      if (G2 == 0xffffffffu) { if (tid == 0) { tp.status[CS_TABLE_OVERFLOW] = 1; tp.gcount[m] = 0; } continue; }
-      if (tid == 0) kept_total += s_flags[0];
-      G = G1 + G2;
+      if (!overflow) {
+        __syncthreads();
+        for (uint32_t f = tid; f < k; f += THREADS) { sm.a[f] = sm.b[f]; sm.b[f] = sm.c[f]; }
+        __syncthreads();
+        const uint32_t G2 = tile_process<THREADS>(in, tp, sm, rank1 - rb, rb, true, (uint64_t)rank0 + G1, s_scan, s_flags);
+        overflow = G2 == 0xffffffffu;
+        if (tid == 0) kept_slot += s_flags[0];
+        G = G1 + G2;
+      }
     }
+    if (overflow) {   // block-uniform
+      if (tid == 0) {
+        tp.gcount[m] = 0;
+        if (tp.heavy_list) tp.heavy_list[atomicAdd((unsigned long long*)&tp.status[CS_NHEAVY], 1ULL)] = m;   // redone by the full-size launch
+        else tp.status[CS_TABLE_OVERFLOW] = 1;
+      }
+      continue;
+    }
+    if (tid == 0) kept_total += kept_slot;
     if (tid == 0) tp.gcount[m] = G;
   }
   if (tid == 0 && kept_total) atomicAdd((unsigned long long*)&tp.status[CS_NKEPT], (unsigned long long)kept_total);
@@ -514,35 +530,62 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
   tp.gcount = B[XB_GCOUNT].as<uint32_t>(); tp.st_rep = B[XB_ST_REP].as<uint32_t>(); tp.st_yc = B[XB_ST_YC].as<float>();
   tp.st_yx = B[XB_ST_YX].as<uint32_t>(); tp.st_bits = B[XB_ST_BITS].as<uint32_t>(); tp.status = g.d_status; tp.seed = 0x243F6A8885A308D3ULL;
   tp.slot_counter = B[XB_WORK].as<unsigned int>();
-  TB_CUDA(cudaMemsetAsync(tp.slot_counter, 0, 64, st));
-  const size_t smem = tile_smem_bytes((uint32_t)k, E, W);
-  const unsigned want = (unsigned)ctx->sm_count * (1024u / (unsigned)threads);
-  const unsigned grid = M < want ? M : want;
-  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
-  if (threads == 1024) {
-    TB_CUDA(cudaFuncSetAttribute(col_tile_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    col_tile_kernel<1024><<<grid, 1024, smem, st>>>(in, tp);
-  } else if (threads == 512) {
-    TB_CUDA(cudaFuncSetAttribute(col_tile_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    col_tile_kernel<512><<<grid, 512, smem, st>>>(in, tp);
-  } else {
-    TB_CUDA(cudaFuncSetAttribute(col_tile_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    col_tile_kernel<256><<<grid, 256, smem, st>>>(in, tp);
+  auto launch = [&](int thr, const TileParams& t, unsigned nslots) -> cudaError_t {
+    const size_t smem = tile_smem_bytes((uint32_t)k, t.ecap, W);
+    const unsigned want = (unsigned)ctx->sm_count * (1024u / (unsigned)thr);
+    const unsigned grid = nslots < want ? nslots : want;
+    cudaError_t e = cudaMemsetAsync(t.slot_counter, 0, 64, st);
+    if (e != cudaSuccess) return e;
+    if (thr == 1024) {
+      if ((e = cudaFuncSetAttribute(col_tile_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      col_tile_kernel<1024><<<grid, 1024, smem, st>>>(in, t);
+    } else if (thr == 512) {
+      if ((e = cudaFuncSetAttribute(col_tile_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      col_tile_kernel<512><<<grid, 512, smem, st>>>(in, t);
+    } else {
+      if ((e = cudaFuncSetAttribute(col_tile_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      col_tile_kernel<256><<<grid, 256, smem, st>>>(in, t);
+    }
+    ctx->launches++;
+    return cudaGetLastError();
+  };
+  // launch 1: every slot, small tables (several CTAs per SM). A pile-up position with more distinct alignments than such a
+  // table holds sends its slot to the heavy list; launch 2 redoes those slots with one full-size table per SM.
+  if (threads != 1024) {
+    TB_CUDA(B[XB_HEAVY].ensure(sizeof(uint32_t) * ((size_t)M + 1)));
+    tp.heavy_list = B[XB_HEAVY].as<uint32_t>();
   }
-  ctx->launches++;
+  long long* h_status = ctx->pinned[0].as<long long>();
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
+  TB_CUDA(launch(threads, tp, M));
+  if (tp.heavy_list) {
+    TB_CUDA(cudaMemcpyAsync(h_status, g.d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    const int64_t nheavy = h_status[CS_NHEAVY];
+    ctx->last_heavy = nheavy;
+    if (nheavy > 0 && !h_status[CS_TABLE_OVERFLOW]) {
+      TileParams t2 = tp;
+      const size_t lim1 = smem_sm - 1024 - 512;
+      uint32_t E2 = 8192;
+      while (E2 > 64 && tile_smem_bytes((uint32_t)k, E2, W) > lim1) E2 -= 64;
+      t2.ecap = E2; t2.cap_records = (uint32_t)(((uint64_t)(E2 - 1) * 4) / 5);
+      t2.slot_list = tp.heavy_list; t2.n_list = (uint32_t)nheavy; t2.heavy_list = nullptr;
+      TB_CUDA(launch(1024, t2, (unsigned)nheavy));
+    }
+  } else ctx->last_heavy = 0;
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[1], st));
   // ---- C6 ----
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[6], st));
   TB_CUDA((tb_device_scan<OpSumU32>(ctx, GcIn{tp.gcount}, (int64_t)M, B[XB_AGG].as<uint32_t>(), GcOut{B[XB_GBASE].as<uint32_t>()})));
   col_store_total_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(M), g.d_status);
   ctx->launches++;
-  long long* h_status = ctx->pinned[0].as<long long>();
   TB_CUDA(cudaMemcpyAsync(h_status, g.d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
   if (ctx->profiling) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_ms[0] = ms;
     if (cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[0]) == cudaSuccess) ctx->last_ms[3] = ms;
+    (void)cudaGetLastError();
   }
   if (h_status[CS_ERR] == ERR_UNSORTED) { ctx->set_error("tb_collapse_window: run not coordinate-sorted at record %lld", h_status[CS_ERRIDX]); return 1; }
   if (h_status[CS_TABLE_OVERFLOW]) return 2;

@@ -285,20 +285,29 @@ __global__ void __launch_bounds__(YD_WARPS * 32) yd_frontier_kernel(ColIn in, co
     const uint32_t a = ustart[u], b = ustart[u + 1];
     if (a >= b) continue;
     Frontier F; F.reset();
-    GDesc dq[YD_PF]; uint32_t gq[YD_PF];   // gq: group id | head flag << 31
+    // two-stage software pipeline: member ids (group | head flag << 31) are loaded 2*YD_PF steps ahead, descriptors
+    // YD_PF steps ahead, so each of the two dependent gathers has YD_PF steps to land
+    GDesc dq[YD_PF]; uint32_t gq[2 * YD_PF];
+#pragma unroll
+    for (int p = 0; p < 2 * YD_PF; ++p) {
+      gq[p] = 0;
+      const uint32_t idx = a + (uint32_t)p * 32u + lane;
+      if (idx < b) gq[p] = chain[idx] | (headflag[idx] << 31);
+    }
 #pragma unroll
     for (int p = 0; p < YD_PF; ++p) {
-      gq[p] = 0; dq[p].start = 0; dq[p].meta = 0; dq[p].e0 = dq[p].s1 = dq[p].e1 = dq[p].s2 = dq[p].e2 = dq[p].zend = 0;
-      const uint32_t idx = a + (uint32_t)p * 32u + lane;
-      if (idx < b) { const uint32_t g = chain[idx]; dq[p] = cdesc[g]; gq[p] = g | (headflag[idx] << 31); }
+      dq[p].start = 0; dq[p].meta = 0; dq[p].e0 = dq[p].s1 = dq[p].e1 = dq[p].s2 = dq[p].e2 = dq[p].zend = 0;
+      if (a + (uint32_t)p * 32u + lane < b) dq[p] = cdesc[gq[p] & 0x7fffffffu];
     }
-    for (uint32_t cb0 = a; cb0 < b; cb0 += 32u * YD_PF) {
+    for (uint32_t cb0 = a; cb0 < b; cb0 += 32u * 2 * YD_PF) {
 #pragma unroll
-      for (int p = 0; p < YD_PF; ++p) {
-        const uint32_t cb = cb0 + (uint32_t)p * 32u;
+      for (int p2 = 0; p2 < 2 * YD_PF; ++p2) {
+        const int p = p2 % YD_PF;
+        const uint32_t cb = cb0 + (uint32_t)p2 * 32u;
         if (cb < b) {   // warp-uniform
-          const GDesc dm = dq[p]; const uint32_t g = gq[p] & 0x7fffffffu; const int head = (int)(gq[p] >> 31);
-          { const uint32_t idx = cb + 32u * YD_PF + lane; if (idx < b) { const uint32_t g2 = chain[idx]; dq[p] = cdesc[g2]; gq[p] = g2 | (headflag[idx] << 31); } }
+          const GDesc dm = dq[p]; const uint32_t g = gq[p2] & 0x7fffffffu; const int head = (int)(gq[p2] >> 31);
+          { const uint32_t idx = cb + 32u * YD_PF + lane; if (idx < b) dq[p] = cdesc[gq[(p2 + YD_PF) % (2 * YD_PF)] & 0x7fffffffu]; }      // step +YD_PF
+          { const uint32_t idx = cb + 32u * 2 * YD_PF + lane; gq[p2] = idx < b ? (chain[idx] | (headflag[idx] << 31)) : 0u; }              // step +2*YD_PF
           const int cnt = (int)((b - cb) < 32u ? (b - cb) : 32u);
           const bool live = lane < cnt;
           const int ne = (int)(dm.meta & 0xffffu);

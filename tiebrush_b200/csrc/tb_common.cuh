@@ -70,6 +70,7 @@ struct tb_ctx {
   int profiling = 0;
   float last_ms[16] = {};   // per-stage device times of the last call (see tb_last_kernel_ms)
   int64_t launches = 0;
+  int64_t last_heavy = 0;   // slots redone by the full-size tile launch in the last collapse call
   int last_yd_path = 0;     // YD stage of the last collapse call: 0 parallel (frontier + link bitmaps), 1 sequential lists
   int last_path = 0;        // front end of the last collapse call: 0 tile, 1 ordered (by options), 2 ordered (table overflow fallback)
   std::string err;
