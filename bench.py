@@ -179,6 +179,50 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    peak, peak_src = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- tiecov leg (secondary): coverage + junctions + bedgraph runs on a collapsed-like stream ----
+    tiecov_line = None
+    if args.cov_records > 0:
+        cctx = api.Context(device=local, n_samples=1)
+        cctx.set_stream(stream.cuda_stream); cctx.set_profiling(True)
+        cov = synth.coverage_stream(args.cov_records, seed=rank, chroms=1, device=dev)
+        ncov = args.cov_records
+        capr, capj = 2 * int(cov["n_cig"]) + 16, int(cov["n_cig"]) + 16
+        i32 = lambda m: torch.empty(m, dtype=torch.int32, device=dev)
+        ocov = dict(r_tid=i32(capr), r_start=i32(capr), r_end=i32(capr), r_val=torch.empty(capr, dtype=torch.float64, device=dev),
+                    j_tid=i32(capj), j_start=i32(capj), j_end=i32(capj), j_strand=torch.empty(capj, dtype=torch.uint8, device=dev),
+                    j_val=torch.empty(capj, dtype=torch.float64, device=dev))
+        for _ in range(max(1, args.warmup)):
+            r = cctx.coverage_window(cov, out=ocov)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cms = []
+        barrier()
+        with torch.cuda.stream(stream):
+            c0.record(stream)
+            for _ in range(args.steps):
+                r = cctx.coverage_window(cov, out=ocov)
+                cms.append(cctx.last_kernel_ms(1))
+            c1.record(stream)
+        barrier()
+        cov_ms = c0.elapsed_time(c1) / args.steps
+        host_cov = None
+        mbases = float(synth.m_bases(cov))
+        a_cov = ncov * (19 + 4 * cov["n_cig"] / ncov) + 16 * r["n_runs"] + 16 * r["n_juncs"]
+        tiecov_line = {"metric": "coverage_bases_per_sec", "value": world * mbases / (cov_ms / 1000.0), "unit": "bases/s",
+                          "records_per_sec": world * ncov / (cov_ms / 1000.0), "ms_per_step": cov_ms, "records": ncov, "runs": r["n_runs"], "juncs": r["n_juncs"],
+                          "roofline": {"bound": "hbm", "kernel": "cov_accumulate_kernel", "achieved": a_cov / (np.mean(cms) / 1000.0) / 1e9, "peak": peak,
+                                       "unit": "GB/s", "frac": a_cov / (np.mean(cms) / 1000.0) / 1e9 / peak, "kernel_ms": float(np.mean(cms)), "traffic": None}}
+        del cov, ocov, r
+        cctx.close()
+        torch.cuda.empty_cache()
+
     k, reads = args.samples, args.reads
     n = k * reads
     # ---- synthetic cohort straight into HBM; rank r owns an independent coordinate shard (weak scaling) ----
@@ -187,7 +231,6 @@ def main():
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
     n_cig = cols["n_cig"]
-    stream = torch.cuda.Stream(device=dev)
     ctx = api.Context(device=local, n_samples=k, mode=args.mode)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_profiling(True)
@@ -196,11 +239,6 @@ def main():
 
     def step_dev():
         return ctx.collapse_window(cols, run_off, pos_range=pr, out=out)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         res = step_dev()
@@ -229,7 +267,6 @@ def main():
     value = world * n / (ms_step / 1000.0)
     clocks = sampler
     # ---- roofline of the dominant kernel (collapse tile kernel) ----
-    peak, peak_src = peaks()
     cbar = n_cig / n
     a_col = n * (30 + 4 * cbar) + 12 * G            # SURVEY §8d algorithmic bytes (default mode: m = 0)
     kernel_ms = float(np.mean(kms))
@@ -245,39 +282,11 @@ def main():
                        "parallelism": f"coordinate shards x{world}, no data-path collective", "gen_seconds": t_gen},
             "roofline": roofline, "gpu_launches": int(launches),
             "stage_ms": dict(zip(("hist_scan", "slots_offsets", "tile", "compaction", "yd"), [float(x) for x in np.mean(np.asarray(stages), 0)]))}
-
-    # ---- tiecov leg (secondary): coverage + junctions + bedgraph runs on a collapsed-like stream ----
-    if args.cov_records > 0:
-        cov = synth.coverage_stream(args.cov_records, seed=rank, chroms=1, device=dev)
-        ncov = args.cov_records
-        capr, capj = 2 * int(cov["n_cig"]) + 16, int(cov["n_cig"]) + 16
-        i32 = lambda m: torch.empty(m, dtype=torch.int32, device=dev)
-        ocov = dict(r_tid=i32(capr), r_start=i32(capr), r_end=i32(capr), r_val=torch.empty(capr, dtype=torch.float64, device=dev),
-                    j_tid=i32(capj), j_start=i32(capj), j_end=i32(capj), j_strand=torch.empty(capj, dtype=torch.uint8, device=dev),
-                    j_val=torch.empty(capj, dtype=torch.float64, device=dev))
-        for _ in range(max(1, args.warmup)):
-            r = ctx.coverage_window(cov, out=ocov)
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        cms = []
-        barrier()
-        with torch.cuda.stream(stream):
-            c0.record(stream)
-            for _ in range(args.steps):
-                r = ctx.coverage_window(cov, out=ocov)
-                cms.append(ctx.last_kernel_ms(1))
-            c1.record(stream)
-        barrier()
-        cov_ms = c0.elapsed_time(c1) / args.steps
-        host_cov = None
-        mbases = float(synth.m_bases(cov))
-        a_cov = ncov * (19 + 4 * cov["n_cig"] / ncov) + 16 * r["n_runs"] + 16 * r["n_juncs"]
-        line["tiecov"] = {"metric": "coverage_bases_per_sec", "value": world * mbases / (cov_ms / 1000.0), "unit": "bases/s",
-                          "records_per_sec": world * ncov / (cov_ms / 1000.0), "ms_per_step": cov_ms, "records": ncov, "runs": r["n_runs"], "juncs": r["n_juncs"],
-                          "roofline": {"bound": "hbm", "kernel": "cov_accumulate_kernel", "achieved": a_cov / (np.mean(cms) / 1000.0) / 1e9, "peak": peak,
-                                       "unit": "GB/s", "frac": a_cov / (np.mean(cms) / 1000.0) / 1e9 / peak, "kernel_ms": float(np.mean(cms)), "traffic": None}}
-        del cov
+    if tiecov_line is not None:
+        line["tiecov"] = tiecov_line
 
     # ---- end to end through the C ABI with host buffers ----
+    host = None
     if not args.no_e2e:
         host = {}
         h2d = 0
@@ -288,6 +297,9 @@ def main():
             host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32, "flag": np.uint16, "nh": np.uint16}.get(name, ht.numpy().dtype))
             h2d += ht.numel() * ht.element_size()
         host["n_cig"] = n_cig
+        # the device-resident copy is not needed any more: the host path stages its own (full size: 25 GB each)
+        del cols, out, res
+        torch.cuda.empty_cache()
         cap = max(G + 1024, 1)
         hout_t = dict(rep_index=torch.empty(cap, dtype=torch.int32, pin_memory=True), yc=torch.empty(cap, dtype=torch.float32, pin_memory=True),
                       yx=torch.empty(cap, dtype=torch.int32, pin_memory=True), yd=torch.empty(cap, dtype=torch.int32, pin_memory=True))
@@ -316,7 +328,7 @@ def main():
     # ---- CPU baseline: the oracle port on a bounded coordinate slice of the same window (rank 0, N=1 only) ----
     if rank == 0 and world == 1 and args.cpu_sample > 0:
         from oracle import oracle
-        hostc = synth.to_host({kk: cols[kk] for kk in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar")})
+        hostc = host if host is not None else synth.to_host({kk: cols[kk] for kk in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar")})
         sub, sub_off = host_slice_sample(hostc, run_off, args.cpu_sample)
         t0 = time.perf_counter()
         ro = oracle.collapse(sub, sub_off, mode=args.mode)

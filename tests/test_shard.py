@@ -1,0 +1,167 @@
+"""Coordinate sharding: host-side edge logic of tiebrush_b200/shard.py on CPU.
+
+The per-record compute is injected: here it is the oracle (tests may use it as the checker's engine), on the GPU box it
+is api.Context (tests/test_gpu_shard.py). The multi-rank paths run with the gloo backend, world_size 2 and 3."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tiebrush_b200 import shard, synth
+
+
+def _cov_compute(cols, want_runs, want_juncs):
+    return oracle.coverage(cols, want_runs=want_runs, want_juncs=want_juncs)
+
+
+def _col_compute(cols, run_off):
+    return oracle.collapse(cols, run_off)
+
+
+def _cov_stream(n, seed, chroms=1, n_tx=40):
+    return synth.to_host(synth.coverage_stream(n, seed=seed, n_tx=n_tx, chroms=chroms))
+
+
+def _simulate_cov(cols, cuts):
+    """All ranks in one process: what coverage_sharded does, without the collectives."""
+    world = len(cuts) + 1
+    bounds = [None] + list(cuts) + [None]
+    owns = [shard.cov_slice(cols, bounds[g], bounds[g + 1]) for g in range(world)]
+    fars = []
+    for g in range(world):
+        hi = bounds[g + 1]
+        e = shard.ref_end(owns[g])
+        far = np.nonzero((owns[g]["tid"] == hi[0]) & (e > hi[1]))[0] if hi is not None else np.zeros(0, np.int64)
+        fars.append(shard._unpack_cov(shard._pack_cov(shard._cov_take(owns[g], far))))
+    parts = []
+    for g in range(world):
+        lo = bounds[g]
+        halo = []
+        if lo is not None:
+            for h in range(g):
+                c = fars[h]
+                if len(c["pos"]):
+                    halo.append(shard._cov_take(c, np.nonzero((c["tid"] == lo[0]) & (shard.ref_end(c) > lo[1]))[0]))
+        halo_in = shard._cov_concat(halo)
+        if len(halo_in["pos"]) > 1:
+            halo_in = shard._cov_take(halo_in, np.argsort(halo_in["pos"], kind="stable"))
+        parts.append(shard.coverage_shard_local(_cov_compute, owns[g], lo, bounds[g + 1], halo_in))
+    return shard._assemble(parts, cuts)
+
+
+def _assert_cov(got, exp):
+    for a, b, name in zip(got[0], exp["runs"], ("tid", "start0", "end0", "value")):
+        assert np.array_equal(np.asarray(a), b), f"runs.{name}"
+    for a, b, name in zip(got[1], exp["juncs"], ("tid", "start", "end", "strand", "value")):
+        assert np.array_equal(np.asarray(a), b), f"juncs.{name}"
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_coverage_shards_balanced_cuts(seed, world):
+    cols = _cov_stream(6000, seed, chroms=2 if seed % 2 else 1)
+    exp = oracle.coverage(cols)
+    _assert_cov(_simulate_cov(cols, shard.cov_cuts(cols, world)), exp)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_coverage_shards_arbitrary_cuts(seed):
+    """Cuts at random coordinates: inside reads, inside introns, between bundles, before the first / after the last record,
+    and several cuts inside one long bundle (a rank that owns nothing but sees the halo)."""
+    rng = np.random.default_rng(seed)
+    cols = _cov_stream(3000, 100 + seed, n_tx=12)
+    exp = oracle.coverage(cols)
+    lo, hi = int(cols["pos"].min()), int(cols["pos"].max())
+    for _ in range(6):
+        npos = rng.integers(1, 6)
+        pick = np.sort(rng.choice(cols["pos"], npos) + rng.integers(-40, 200, npos))
+        cuts = [(0, int(np.clip(p, lo - 5, hi + 500))) for p in pick]
+        _assert_cov(_simulate_cov(cols, cuts), exp)
+
+
+def test_coverage_shards_dense_cuts_inside_one_bundle():
+    cols = _cov_stream(400, 7, n_tx=2)
+    exp = oracle.coverage(cols)
+    p0 = int(np.median(cols["pos"]))
+    cuts = [(0, p0 + 7 * i) for i in range(10)]
+    _assert_cov(_simulate_cov(cols, cuts), exp)
+
+
+def test_gap_at_or_before_is_a_gap():
+    cols, run_off, _ = synth.cohort_window(5, 800, seed=3, n_tx=20, device="cpu")
+    host = synth.to_host(cols)
+    e = shard.ref_end(host)
+    for cut in np.quantile(host["pos"], [0.1, 0.35, 0.5, 0.8]).astype(int):
+        g = shard.gap_at_or_before(host, run_off, int(cut))
+        assert g <= cut
+        m = host["pos"] < g
+        assert not m.any() or e[m].max() <= g
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_collapse_shards_equal_whole_window(world):
+    cols, run_off, _ = synth.cohort_window(6, 1500, seed=5, n_tx=25, device="cpu")
+    host = synth.to_host(cols)
+    exp = oracle.collapse(host, run_off)
+    cuts = shard.collapse_cuts(host, run_off, world)
+    bounds = [None] + cuts + [None]
+    parts = [shard.collapse_shard_local(_col_compute, host, run_off, bounds[g], bounds[g + 1]) for g in range(world)]
+    for key in ("rep_index", "yc", "yx", "yd"):
+        got = np.concatenate([p[key] for p in parts])
+        assert np.array_equal(got.astype(np.int64) if key == "rep_index" else got, exp[key].astype(np.int64) if key == "rep_index" else exp[key]), key
+
+
+# ---- torch.distributed, gloo, world_size > 1 ----------------------------------------------------------------------------
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, what, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        if what == "cov":
+            cols = _cov_stream(5000, 11, chroms=2)
+            cuts = shard.cov_cuts(cols, world)
+            cuts[0] = (cuts[0][0], cuts[0][1] + 37)          # off the balanced point: inside reads
+            bounds = [None] + cuts + [None]
+            own = shard.cov_slice(cols, bounds[rank], bounds[rank + 1])
+            runs, juncs = shard.coverage_sharded(_cov_compute, own, bounds[rank], bounds[rank + 1], cuts)
+            if rank == 0:
+                exp = oracle.coverage(cols)
+                ok = all(np.array_equal(a, b) for a, b in zip(runs, exp["runs"])) and all(np.array_equal(a, b) for a, b in zip(juncs, exp["juncs"]))
+                q.put(("cov", bool(ok), len(runs[0]), len(juncs[0])))
+        else:
+            cols, run_off, _ = synth.cohort_window(5, 2000, seed=9, n_tx=25, device="cpu")
+            host = synth.to_host(cols)
+            cuts = shard.collapse_cuts(host, run_off, world)
+            got = shard.collapse_sharded(_col_compute, host, run_off, cuts)
+            if rank == 0:
+                exp = oracle.collapse(host, run_off)
+                ok = all(np.array_equal(np.asarray(got[k]).astype(np.int64), np.asarray(exp[k]).astype(np.int64)) for k in ("rep_index", "yx", "yd")) \
+                    and np.array_equal(got["yc"], exp["yc"])
+                q.put(("col", bool(ok), len(got["rep_index"]), 0))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("what,world", [("cov", 2), ("cov", 3), ("col", 2)])
+def test_sharded_gloo(what, world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, what, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    tag, ok, a, b = q.get(timeout=10)
+    assert tag == what and ok and a > 0
