@@ -230,6 +230,19 @@ struct Frontier {
   }
 };
 
+// for a read with more than YD_INLINE_EX exons: index of the last exon whose (compact) start is <= frontier, and its end
+__device__ __noinline__ int yd_reach(const ColIn& in, uint32_t rep, int frontier, const uint32_t* U, const uint32_t* rankpre, int* e_out) {
+  const int ubase = in.pos_lo + 1;
+  ExonIter it; it.init(in.cigar, in.cig_off[rep], in.cig_off[rep + 1], in.pos[rep]);
+  int s, e, j = -1, last_e = 0;
+  while (it.next(s, e)) {
+    if (j >= 0 && yd_rank(U, rankpre, (int64_t)s - ubase) > frontier) break;
+    ++j; last_e = yd_rank(U, rankpre, (int64_t)e - ubase);
+  }
+  *e_out = last_e;
+  return j;
+}
+
 // links of the first `r` exons of a read into the chain bitmap that starts at bit `base` (exon [s,t] sets links s..t-1)
 __device__ __forceinline__ void yd_emit_links(const ColIn& in, const GDesc& d, uint32_t r, uint32_t rep, const uint32_t* U, const uint32_t* rankpre,
                                               unsigned long long* bm, int64_t base) {
@@ -252,9 +265,8 @@ __device__ __forceinline__ void yd_emit_links(const ColIn& in, const GDesc& d, u
 // The member array (all chains back to back, sub-chain heads flagged) is cut into work units that start at sub-chain
 // heads (first head at or after a multiple of YD_UNIT members), so a unit needs no state from outside. Persistent warps
 // pull units and walk them 32 members per step, YD_PF steps of descriptors in flight. Within a step the frontier is
-// SPECULATED ("nothing is dropped, nobody but a head finds the list empty": member j then sees the maximum end of the
-// members before it in its sub-chain, a segmented prefix max); if every lane's own exons pass under that assumption it
-// is exact by induction, otherwise lane 0 replays the step sequentially.
+// resolved by iterating "classes -> segmented prefix max -> classes" to its fixed point (see the kernel); the common
+// classes (later exons of a spliced read dropped; or everything reached after a spanning read) settle in 1-2 scans.
 constexpr int YD_PF = 4;
 constexpr uint32_t YD_UNIT = 2048;
 __global__ void __launch_bounds__(256) yd_unit_kernel(const uint32_t* __restrict__ heads, const uint32_t* __restrict__ nsub_p, uint32_t n_members, uint32_t nunits,
@@ -311,26 +323,42 @@ __global__ void __launch_bounds__(YD_WARPS * 32) yd_frontier_kernel(ColIn in, co
           const int cnt = (int)((b - cb) < 32u ? (b - cb) : 32u);
           const bool live = lane < cnt;
           const int ne = (int)(dm.meta & 0xffffu);
-          int v = live ? dm.zend : -1, h = head;
+          // For a frontier E >= start the step is  E' = max(E, end of the last exon whose start <= E)  and exactly the
+          // exons up to that one are kept (exon starts lie beyond the previous exon's end); for E < start every exon is
+          // kept and E' = last end. So, GIVEN each member's class (bulk, or index jx of the exon that E reaches), the
+          // frontier is a segmented prefix max of one value per member. Guess the classes (heads: bulk, others: jx = 0,
+          // i.e. later exons dropped), scan, re-derive the classes from the frontier each member then sees, and repeat
+          // until nothing changes: a fixed point satisfies the recurrence member by member, hence is the exact result.
+          int jx = 0; bool bulk = head != 0;
+          int contrib = live ? (bulk ? dm.zend : dm.e0) : -1;
+          int e_after = F.E;
+          bool replay = false;
+          for (int iter = 0;; ++iter) {
+            int v = contrib, h = head;
 #pragma unroll
-          for (int dd = 1; dd < 32; dd <<= 1) {
-            const int v2 = __shfl_up_sync(0xffffffffu, v, dd), h2 = __shfl_up_sync(0xffffffffu, h, dd);
-            if (lane >= dd) { if (!h) v = max(v, v2); h |= h2; }
+            for (int dd = 1; dd < 32; dd <<= 1) {
+              const int v2 = __shfl_up_sync(0xffffffffu, v, dd), h2 = __shfl_up_sync(0xffffffffu, h, dd);
+              if (lane >= dd) { if (!h) v = max(v, v2); h |= h2; }
+            }
+            if (!h) v = max(v, F.E);                     // no head at or before this lane: the carried sub-chain continues
+            int pm = __shfl_up_sync(0xffffffffu, v, 1);
+            if (lane == 0) pm = F.E;
+            bool nb = bulk; int nj = jx, nc = contrib;
+            if (live && !head) {
+              nb = pm < dm.start;
+              if (nb) { nj = 0; nc = dm.zend; }
+              else if (ne <= YD_INLINE_EX) {
+                nj = (ne >= 3 && pm >= dm.s2) ? 2 : ((ne >= 2 && pm >= dm.s1) ? 1 : 0);
+                nc = nj == 2 ? dm.e2 : (nj == 1 ? dm.e1 : dm.e0);
+              } else nj = yd_reach(in, rep[g], pm, U, rankpre, &nc);
+            }
+            const bool changed = nb != bulk || nj != jx;
+            bulk = nb; jx = nj; contrib = nc;
+            if (!__any_sync(0xffffffffu, changed)) { e_after = __shfl_sync(0xffffffffu, v, cnt - 1); break; }
+            if (iter >= 8) { replay = true; break; }
           }
-          if (!h) v = max(v, F.E);                     // no head at or before this lane: the carried sub-chain continues
-          const int e_after = __shfl_sync(0xffffffffu, v, cnt - 1);   // frontier after the step if the speculation holds
-          int pm = __shfl_up_sync(0xffffffffu, v, 1);
-          if (lane == 0) pm = F.E;
-          bool fine = true;
-          if (live && !head) {
-            fine = pm >= dm.start && ne <= YD_INLINE_EX;
-            if (ne >= 2) fine = fine && dm.s1 <= max(pm, dm.e0);
-            if (ne >= 3) fine = fine && dm.s2 <= max(pm, max(dm.e0, dm.e1));
-          }
-          uint32_t r = (uint32_t)ne;
-          if (__all_sync(0xffffffffu, fine)) {
-            F.E = e_after;
-          } else {
+          uint32_t r = bulk ? (uint32_t)ne : (uint32_t)jx + 1u;
+          if (replay) {   // no fixed point within a few rounds: one lane walks the step in order
             s_desc[wl][lane] = dm; s_g[wl][lane] = g | ((uint32_t)head << 31);
             __syncwarp();
             if (lane == 0) {
@@ -346,7 +374,7 @@ __global__ void __launch_bounds__(YD_WARPS * 32) yd_frontier_kernel(ColIn in, co
             __syncwarp();
             r = s_r[wl][lane];
             __syncwarp();
-          }
+          } else F.E = e_after;
           if (live) kept[cb + lane] = (uint8_t)r;
         }
       }
