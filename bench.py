@@ -209,6 +209,7 @@ def main():
             for _ in range(args.steps):
                 r = cctx.coverage_window(cov, out=ocov)
                 cms.append(cctx.last_kernel_ms(1))
+                cstages = [cctx.last_kernel_ms(i) for i in (6, 1, 7)]
             c1.record(stream)
         barrier()
         cov_ms = c0.elapsed_time(c1) / args.steps
@@ -218,7 +219,8 @@ def main():
         tiecov_line = {"metric": "coverage_bases_per_sec", "value": world * mbases / (cov_ms / 1000.0), "unit": "bases/s",
                           "records_per_sec": world * ncov / (cov_ms / 1000.0), "ms_per_step": cov_ms, "records": ncov, "runs": r["n_runs"], "juncs": r["n_juncs"],
                           "roofline": {"bound": "hbm", "kernel": "cov_accumulate_kernel", "achieved": a_cov / (np.mean(cms) / 1000.0) / 1e9, "peak": peak,
-                                       "unit": "GB/s", "frac": a_cov / (np.mean(cms) / 1000.0) / 1e9 / peak, "kernel_ms": float(np.mean(cms)), "traffic": None}}
+                                       "unit": "GB/s", "frac": a_cov / (np.mean(cms) / 1000.0) / 1e9 / peak, "kernel_ms": float(np.mean(cms)), "traffic": None},
+                          "stage_ms": dict(zip(("bundles", "accumulate", "runs"), [float(x) for x in cstages]))}
         del cov, ocov, r
         cctx.close()
         torch.cuda.empty_cache()

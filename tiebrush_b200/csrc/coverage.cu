@@ -162,59 +162,131 @@ __device__ __forceinline__ void junc_insert(const JTable& jt, int tid, unsigned 
 __device__ __forceinline__ unsigned strand_code(uint8_t c) { return c == '+' ? 0u : (c == '-' ? 1u : 2u); }  // '+' < '-' < '.'
 __device__ __forceinline__ uint8_t strand_char(unsigned c) { return c == 0 ? '+' : (c == 1 ? '-' : '.'); }
 
-// Sum `val` over runs of adjacent lanes (`head` marks the first lane of a run; records are coordinate sorted, so the
-// members of a pile-up sit in adjacent lanes); returns true on the last lane of a run, with the run total in `val`.
-__device__ __forceinline__ bool cov_run_sum(bool head_in, long long& val) {
+// Segmented inclusive prefix sum over runs of adjacent lanes (`head` marks the first lane of a run).
+__device__ __forceinline__ long long cov_seg_prefix(bool head_in, long long val) {
   const unsigned lane = threadIdx.x & 31;
-  const int head = (lane == 0 || head_in) ? 1 : 0;
-  int h = head;
+  int h = (lane == 0 || head_in) ? 1 : 0;
   long long v = val;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const long long v2 = __shfl_up_sync(0xffffffffu, v, d); const int h2 = __shfl_up_sync(0xffffffffu, h, d);
     if ((int)lane >= d) { if (!h) v += v2; h |= h2; }
   }
-  const int next_head = __shfl_down_sync(0xffffffffu, head, 1);
-  val = v;
-  return lane == 31 || next_head;
+  return v;
 }
 
-// One thread per record walks its CIGAR; the warp advances op by op so that lanes with the same alignment (pile-ups)
-// merge their updates before touching memory: one 64-bit RED per distinct difference-array cell and warp step.
-__global__ void __launch_bounds__(256) cov_accumulate_kernel(CovIn in, const uint32_t* __restrict__ bid, const int32_t* __restrict__ bstart,
-                                                             const long long* __restrict__ bbase, long long* __restrict__ diff,
-                                                             int do_cov, int do_junc, JTable jt, long long* __restrict__ status) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = i < in.n;
-  uint32_t c0 = 0, nc = 0; int pos = 0, tid = 0; long long w = 0, shift = 0; unsigned sc = 0;
-  if (valid) {
-    c0 = in.cig_off[i]; nc = in.cig_off[i + 1] - c0;
-    pos = in.pos[i];
-    w = (long long)rintf(in.yc[i] * (float)COV_FX_SCALE);
-    const uint32_t b = bid[i];
-    shift = bbase[b] - (long long)bstart[b];  // compact index of 1-based coordinate x is x + shift
-    tid = in.tid[i];
-    sc = strand_code(in.strand[i]);
+// K7 geometry: a CTA owns COV_RPT*256 consecutive records and a shared-memory tile of COV_TILE difference cells that
+// starts at the compact coordinate of its first record. The stream is coordinate sorted, so nearly every update of the
+// CTA (M-block starts and ends within ~COV_TILE bases of the first start) lands in the tile; blocks behind a long intron
+// fall outside and go to global memory directly. A cell is an exact 64-bit two's-complement sum kept as two 32-bit
+// words: native 32-bit shared atomics on the low word, the carry / borrow it reports folded into the high word (64-bit
+// shared atomicAdd is a CAS loop on sm_100). Junction weights are pre-aggregated the same way in a small shared hash
+// table. The flush issues one global RED per NON-ZERO cell / occupied junction slot: an order of magnitude fewer global
+// atomics than one per update, and none of them contended inside the CTA.
+constexpr int COV_THREADS = 256;
+constexpr int COV_RPT = 4;
+constexpr int COV_TILE = 4096;
+constexpr int COV_JSLOTS = 256;
+
+__device__ __forceinline__ void cov_cell_add(uint32_t* lo, uint32_t* hi, uint32_t c, long long w) {   // cell c += w
+  const uint32_t wl = (uint32_t)(unsigned long long)w, wh = (uint32_t)((unsigned long long)w >> 32);
+  const uint32_t old = atomicAdd(&lo[c], wl);
+  const uint32_t add_hi = wh + ((uint32_t)(old + wl) < old ? 1u : 0u);
+  if (add_hi) atomicAdd(&hi[c], add_hi);
+}
+
+struct CovSmem {
+  uint32_t lo[COV_TILE], hi[COV_TILE];
+  unsigned long long jkey[COV_JSLOTS]; uint32_t jlo[COV_JSLOTS], jhi[COV_JSLOTS];
+};
+
+// One thread per record and round (COV_RPT rounds, records strided by the CTA size so loads coalesce), each thread
+// walking its own CIGAR: a warp costs the instructions of its records, not 32 x the longest CIGAR. Before the walk,
+// adjacent records that are the same alignment (pile-ups of an uncollapsed input) are summed in registers by one
+// segmented prefix sum and only the last record of the run issues updates (warp-uniform branch, skipped on collapsed
+// input); and the -w closing an M block cancels against the +w opening the next when the blocks touch (M I M).
+__global__ void __launch_bounds__(COV_THREADS) cov_accumulate_kernel(CovIn in, const uint32_t* __restrict__ bid, const int32_t* __restrict__ bstart,
+                                                                     const long long* __restrict__ bbase, long long* __restrict__ diff,
+                                                                     int do_cov, int do_junc, JTable jt, long long* __restrict__ status) {
+  __shared__ CovSmem sm;
+  const int64_t rec0 = (int64_t)blockIdx.x * (COV_THREADS * COV_RPT);
+  for (int c = threadIdx.x; c < COV_TILE; c += COV_THREADS) { sm.lo[c] = 0; sm.hi[c] = 0; }
+  for (int c = threadIdx.x; c < COV_JSLOTS; c += COV_THREADS) { sm.jkey[c] = J_EMPTY; sm.jlo[c] = 0; sm.jhi[c] = 0; }
+  long long cell0; int tid0;
+  {
+    const uint32_t b0 = bid[rec0];
+    cell0 = (long long)in.pos[rec0] + 1 + bbase[b0] - (long long)bstart[b0];
+    tid0 = in.tid[rec0];
   }
-  const uint32_t maxnc = __reduce_max_sync(0xffffffffu, nc);
-  // setupCoordinates state (GSam.cpp:351-417) for the junctions
-  int l = 0, exstart = pos, nclosed = 0, last_end = 0;
-  bool intron = false, ins = false;
-  const unsigned long long NOID = ~0ULL;
-  for (uint32_t q = 0; q <= maxnc; ++q) {   // the extra round flushes the junction that ends at the last exon
-    unsigned long long ida = NOID, idb = NOID, jid = NOID; long long wa = 0, wb = 0, wj = 0;
-    if (q < nc) {
+  __syncthreads();
+  auto cell_update = [&](long long cell, long long w) {
+    const unsigned long long rel = (unsigned long long)(cell - cell0);
+    if (rel < (unsigned long long)COV_TILE) cov_cell_add(sm.lo, sm.hi, (uint32_t)rel, w);
+    else atomicAdd((unsigned long long*)&diff[cell], (unsigned long long)w);
+  };
+  auto junc_update = [&](int tid, unsigned long long k64, long long w) {
+    if (tid == tid0) {
+      uint32_t s = (uint32_t)(tb_mix64(k64) >> 40) & (COV_JSLOTS - 1);
+      for (int probe = 0; probe < 8; ++probe) {
+        unsigned long long cur = sm.jkey[s];
+        if (cur == J_EMPTY) { cur = atomicCAS(&sm.jkey[s], J_EMPTY, k64); if (cur == J_EMPTY) cur = k64; }
+        if (cur == k64) { cov_cell_add(sm.jlo, sm.jhi, s, w); return; }
+        s = (s + 1) & (COV_JSLOTS - 1);
+      }
+    }
+    junc_insert(jt, tid, k64, w, status);
+  };
+#pragma unroll 1
+  for (int r = 0; r < COV_RPT; ++r) {
+    const int64_t i = rec0 + (int64_t)r * COV_THREADS + threadIdx.x;
+    bool valid = i < in.n;
+    uint32_t c0 = 0, nc = 0; int pos = 0, tid = 0; long long w = 0; uint8_t st = 0;
+    bool dup = false;   // same alignment as record i-1
+    if (valid) {
+      c0 = in.cig_off[i]; nc = in.cig_off[i + 1] - c0;
+      pos = in.pos[i]; tid = in.tid[i]; st = in.strand[i];
+      w = (long long)rintf(in.yc[i] * (float)COV_FX_SCALE);
+      if (i > 0 && in.pos[i - 1] == pos && in.tid[i - 1] == tid && in.strand[i - 1] == st) {
+        const uint32_t p0 = in.cig_off[i - 1];
+        if (c0 - p0 == nc) {
+          dup = true;
+          for (uint32_t q = 0; q < nc; ++q) if (in.cigar[p0 + q] != in.cigar[c0 + q]) { dup = false; break; }
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, dup)) {
+      w = cov_seg_prefix(!dup, w);
+      const int next_dup = __shfl_down_sync(0xffffffffu, (int)dup, 1);
+      if ((threadIdx.x & 31) != 31 && next_dup) valid = false;   // not the last record of its run inside this warp
+    }
+    if (!valid) continue;
+    const uint32_t b = bid[i];
+    const long long shift = bbase[b] - (long long)bstart[b];  // compact index of 1-based coordinate x is x + shift
+    const unsigned sc = strand_code(st);
+    // setupCoordinates state (GSam.cpp:351-417) for the junctions
+    int l = 0, exstart = pos, nclosed = 0, last_end = 0;
+    bool intron = false, ins = false;
+    long long pend = -1;   // difference cell of the pending -w (one past the last M block), -1 = none
+    for (uint32_t q = 0; q < nc; ++q) {
       const uint32_t cw = in.cigar[c0 + q];
       const uint32_t op = cw & 0xf; const int len = (int)(cw >> 4);
       switch (op) {
         case TB_OP_M:
-          if (do_cov && len > 0) { ida = (unsigned long long)((long long)(pos + l + 1) + shift); idb = ida + (unsigned long long)len; wa = w; wb = -w; }
+          if (do_cov && len > 0 && w != 0) {
+            const long long a = (long long)(pos + l + 1) + shift;
+            if (pend != a) {
+              if (pend >= 0) cell_update(pend, -w);
+              cell_update(a, w);
+            }
+            pend = a + len;
+          }
           l += len; intron = false; ins = false; break;
         case TB_OP_EQ: case TB_OP_X: case TB_OP_D:
           l += len; intron = false; ins = false; break;
         case TB_OP_N:
           if (!ins || !intron) {
-            if (do_junc && nclosed > 0) { jid = ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc; wj = w; }
+            if (do_junc && nclosed > 0)
+              junc_update(tid, ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc, w);
             last_end = pos + l; nclosed++;
           }
           l += len; exstart = pos + l; intron = true; break;
@@ -224,19 +296,22 @@ __global__ void __launch_bounds__(256) cov_accumulate_kernel(CovIn in, const uin
           ins = true; break;
         default: break;
       }
-    } else if (valid && q == nc && do_junc && nclosed > 0) {
-      jid = ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc; wj = w;
     }
-    if (do_cov && __any_sync(0xffffffffu, ida != NOID)) {
-      const unsigned long long pa = __shfl_up_sync(0xffffffffu, ida, 1), pb = __shfl_up_sync(0xffffffffu, idb, 1);
-      if (cov_run_sum(pa != ida, wa) && ida != NOID && wa != 0) atomicAdd((unsigned long long*)&diff[ida], (unsigned long long)wa);
-      if (cov_run_sum(pb != idb, wb) && idb != NOID && wb != 0) atomicAdd((unsigned long long*)&diff[idb], (unsigned long long)wb);
-    }
-    if (do_junc && __any_sync(0xffffffffu, jid != NOID)) {
-      const unsigned long long pj = __shfl_up_sync(0xffffffffu, jid, 1); const int pt = __shfl_up_sync(0xffffffffu, tid, 1);
-      if (cov_run_sum(pj != jid || pt != tid, wj) && jid != NOID) junc_insert(jt, tid, jid, wj, status);
-    }
+    if (pend >= 0) cell_update(pend, -w);
+    if (do_junc && nclosed > 0)   // the junction that ends at the last exon
+      junc_update(tid, ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc, w);
   }
+  __syncthreads();
+  if (do_cov)
+    for (int c = threadIdx.x; c < COV_TILE; c += COV_THREADS) {
+      const unsigned long long v = ((unsigned long long)sm.hi[c] << 32) | sm.lo[c];
+      if (v) atomicAdd((unsigned long long*)&diff[cell0 + c], v);
+    }
+  if (do_junc)
+    for (int c = threadIdx.x; c < COV_JSLOTS; c += COV_THREADS) {
+      const unsigned long long k64 = sm.jkey[c];
+      if (k64 != J_EMPTY) junc_insert(jt, tid0, k64, (long long)(((unsigned long long)sm.jhi[c] << 32) | sm.jlo[c]), status);
+    }
 }
 
 // ---- K8: change points and runs --------------------------------------------------------------------
@@ -430,7 +505,7 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     }
     // ---- K7 (+K9 insert): the dominant kernel ----
     if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
-    cov_accumulate_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(), B[CB_BBASE].as<long long>(),
+    cov_accumulate_kernel<<<grid_for(n, COV_THREADS * COV_RPT), COV_THREADS, 0, st>>>(in, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(), B[CB_BBASE].as<long long>(),
                                                            B[CB_DIFF].as<long long>(), do_cov, do_junc, jt, d_status);
     ctx->launches++;
     if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[1], st));
