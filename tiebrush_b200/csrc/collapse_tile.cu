@@ -501,7 +501,12 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
     if (tile_smem_bytes((uint32_t)k, E, W) > lim1) { ctx->set_error("tb_collapse_window: %d samples do not fit the shared-memory group table", k); return 1; }
   }
   const uint32_t cap_records = (uint32_t)(((uint64_t)(E - 1) * 4) / 5);   // floor(1.25*n)+1 <= E
-  const uint32_t T = cap_records / 2;
+  // slot size: a slot holds < T records of ordinary positions plus its last position; a slot that outgrows the table
+  // splits that last position off as a pile-up sub-tile (tile kernel), so any T <= cap_records is correct. Larger T =
+  // fewer, fuller slots (less per-slot work), but more slots that need the split. TB_TILE_T8 = T in eighths of the table.
+  uint32_t t8 = 7;
+  if (const char* e = getenv("TB_TILE_T8")) { const int t = atoi(e); if (t >= 1 && t <= 8) t8 = (uint32_t)t; }
+  const uint32_t T = (uint32_t)(((uint64_t)cap_records * t8) / 8);
   if (T < 8) { ctx->set_error("tb_collapse_window: %d samples leave no room for a shared-memory tile", k); return 1; }
   const uint32_t M = (uint32_t)((n + T - 1) / T);
 

@@ -59,8 +59,8 @@ __device__ __forceinline__ void yd_set_bits64(unsigned long long* bm, int64_t lo
 
 // Y1: descriptor per group (genomic coordinates), group end, strand; union bitmap of exon positions (bit = coordinate - ubase)
 __global__ void __launch_bounds__(256) yd_desc_kernel(ColIn in, const uint32_t* __restrict__ rep, int64_t G, GDesc* __restrict__ desc,
-                                                      uint32_t* __restrict__ gend, uint8_t* __restrict__ gstrand, uint32_t* __restrict__ U,
-                                                      int64_t ubits, long long* __restrict__ status) {
+                                                      uint32_t* __restrict__ gend, uint32_t* __restrict__ gstart, uint8_t* __restrict__ gstrand,
+                                                      uint32_t* __restrict__ U, int64_t ubits, long long* __restrict__ status) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   const uint32_t r = rep[g];
@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) yd_desc_kernel(ColIn in, const uint32_t* 
   d.zend = pos + it.l;
   desc[g] = d;
   gend[g] = (uint32_t)(pos + it.l);
+  gstart[g] = (uint32_t)(pos + 1);
   gstrand[g] = sc;
 }
 
@@ -95,7 +96,8 @@ __device__ __forceinline__ int32_t yd_rank(const uint32_t* __restrict__ U, const
   return (int32_t)(rankpre[w] + (uint32_t)__popc(U[w] & ((1u << (bit & 31)) - 1u)));
 }
 __global__ void __launch_bounds__(256) yd_compact_kernel(const GDesc* __restrict__ desc, int64_t G, const uint32_t* __restrict__ U,
-                                                         const uint32_t* __restrict__ rankpre, int ubase, GDesc* __restrict__ cdesc, uint32_t* __restrict__ cend) {
+                                                         const uint32_t* __restrict__ rankpre, int ubase, GDesc* __restrict__ cdesc, uint32_t* __restrict__ cend,
+                                                         uint32_t* __restrict__ cstart) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   GDesc d = desc[g];
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(256) yd_compact_kernel(const GDesc* __restrict
   d.zend = yd_rank(U, rankpre, (int64_t)d.zend - ubase);
   cdesc[g] = d;
   cend[g] = (uint32_t)d.zend;
+  cstart[g] = (uint32_t)d.start;
 }
 
 // ---- Y3-Y5: chain member lists ---------------------------------------------------------------------------------------
@@ -146,7 +149,8 @@ __global__ void __launch_bounds__(128) yd_colbase_kernel(const unsigned long lon
 }
 // stable scatter of the group ids into the chain lists
 __global__ void __launch_bounds__(128) yd_scatter_kernel(const uint32_t* __restrict__ bits, uint32_t W, int k, int64_t G, const uint8_t* __restrict__ gstrand,
-                                                        const unsigned long long* __restrict__ blkoff, int64_t nblk, uint32_t* __restrict__ chain) {
+                                                        const unsigned long long* __restrict__ blkoff, int64_t nblk, uint32_t* __restrict__ chain,
+                                                        uint16_t* __restrict__ mchain) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= nblk * W) return;
   const int64_t b = warp / W; const uint32_t w = (uint32_t)(warp % W);
@@ -165,32 +169,29 @@ __global__ void __launch_bounds__(128) yd_scatter_kernel(const uint32_t* __restr
       const uint32_t wq = __shfl_sync(0xffffffffu, word, q);
       const int sq = __shfl_sync(0xffffffffu, (int)sc, q);
       if ((wq >> lane) & 1u) {
-        if (sq != '-') chain[pf++] = (uint32_t)(base + q);
-        if (sq != '+') chain[pr++] = (uint32_t)(base + q);
+        if (sq != '-') { chain[pf] = (uint32_t)(base + q); mchain[pf++] = (uint16_t)s; }
+        if (sq != '+') { chain[pr] = (uint32_t)(base + q); mchain[pr++] = (uint16_t)(k + s); }
       }
     }
   }
 }
 
-// sub-chain heads: prefix max of (chain<<32 | end) over the member array is a segmented prefix max (chain ids ascend)
-__device__ __forceinline__ int yd_chain_of(const unsigned long long* __restrict__ colbase, int nchains, int64_t i) {
-  int lo = 0, hi = nchains;  // last c with colbase[c] <= i
-  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (colbase[mid] <= (unsigned long long)i) lo = mid; else hi = mid; }
-  return lo;
-}
+// sub-chain heads: prefix max of (chain<<32 | end) over the member array is a segmented prefix max (chain ids ascend).
+// mchain[i] = chain of member i (written by the scatter); flag[i] = head | chain << 1 for the later stages.
 struct MemberKeyIn {
-  const uint32_t* chain; const uint32_t* gend; const unsigned long long* colbase; int nchains;
-  __device__ unsigned long long operator()(int64_t i) const { return ((unsigned long long)(uint32_t)yd_chain_of(colbase, nchains, i) << 32) | gend[chain[i]]; }
+  const uint32_t* chain; const uint32_t* gend; const uint16_t* mchain;
+  __device__ unsigned long long operator()(int64_t i) const { return ((unsigned long long)mchain[i] << 32) | gend[chain[i]]; }
 };
 struct MemberHeadOut {
-  MemberKeyIn mk; const GDesc* desc; uint32_t* flag;
+  MemberKeyIn mk; const uint32_t* gstart; uint32_t* flag;
   __device__ void operator()(int64_t i, unsigned long long exc, unsigned long long) const {
+    const uint32_t c = mk.mchain[i];
     uint32_t h = 1u;
-    if (i > 0 && (int)(exc >> 32) == yd_chain_of(mk.colbase, mk.nchains, i)) h = (uint32_t)desc[mk.chain[i]].start > (uint32_t)exc ? 1u : 0u;
-    flag[i] = h;
+    if (i > 0 && (uint32_t)(exc >> 32) == c) h = gstart[mk.chain[i]] > (uint32_t)exc ? 1u : 0u;
+    flag[i] = h | (c << 1);
   }
 };
-struct FlagIn { const uint32_t* f; __device__ uint32_t operator()(int64_t i) const { return f[i]; } };
+struct FlagIn { const uint32_t* f; __device__ uint32_t operator()(int64_t i) const { return f[i] & 1u; } };
 struct HeadListOut { uint32_t* heads; __device__ void operator()(int64_t i, uint32_t exc, uint32_t inc) const { if (inc != exc) heads[exc] = (uint32_t)i; } };
 __global__ void yd_subchain_total_kernel(const uint32_t* tot, uint32_t* heads, uint32_t n_members, unsigned long long* work) {
   heads[*tot] = n_members; work[0] = 0; work[1] = *tot;
@@ -281,13 +282,30 @@ __global__ void __launch_bounds__(256) yd_unit_kernel(const uint32_t* __restrict
   ustart[u] = heads[lo];
 }
 
-__global__ void __launch_bounds__(YD_WARPS * 32) yd_frontier_kernel(ColIn in, const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ rep,
-                                                                   const uint32_t* __restrict__ chain, const uint32_t* __restrict__ headflag,
-                                                                   const uint32_t* __restrict__ ustart, uint32_t nunits, unsigned long long* work,
-                                                                   const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre, uint8_t* __restrict__ kept) {
-  __shared__ GDesc s_desc[YD_WARPS][32];
-  __shared__ uint32_t s_g[YD_WARPS][32];
-  __shared__ uint8_t s_r[YD_WARPS][32];
+// asynchronous global -> shared copies (LDGSTS): the gathers of the software pipeline below land in shared memory
+// without holding registers, so the loop body exists once (no unrolled register queues) and stays inside the
+// instruction cache
+__device__ __forceinline__ void yd_cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void yd_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void yd_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void yd_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+constexpr int YD_FWARPS = 4;   // warps per CTA of the frontier kernel (6 KB of shared-memory rings each)
+__global__ void __launch_bounds__(YD_FWARPS * 32) yd_frontier_kernel(ColIn in, const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ rep,
+                                                                    const uint32_t* __restrict__ chain, const uint32_t* __restrict__ headflag,
+                                                                    const uint32_t* __restrict__ ustart, uint32_t nunits, unsigned long long* work,
+                                                                    const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre, uint8_t* __restrict__ kept) {
+  // two-stage pipeline per warp: member ids (group, head flag) are fetched 2*YD_PF steps ahead, descriptors YD_PF steps
+  // ahead, so each of the two dependent gathers has YD_PF steps to land. A lane only ever reads ring entries it
+  // requested itself (except in the replay, which synchronises the warp first).
+  __shared__ __align__(16) GDesc s_ring[YD_FWARPS][YD_PF][32];
+  __shared__ uint32_t s_gid[YD_FWARPS][2 * YD_PF][32];
+  __shared__ uint32_t s_flg[YD_FWARPS][2 * YD_PF][32];
+  __shared__ uint8_t s_r[YD_FWARPS][32];
   const int wl = tb_warp(), lane = tb_lane();
   for (;;) {
     unsigned long long u = 0;
@@ -297,94 +315,104 @@ __global__ void __launch_bounds__(YD_WARPS * 32) yd_frontier_kernel(ColIn in, co
     const uint32_t a = ustart[u], b = ustart[u + 1];
     if (a >= b) continue;
     Frontier F; F.reset();
-    // two-stage software pipeline: member ids (group | head flag << 31) are loaded 2*YD_PF steps ahead, descriptors
-    // YD_PF steps ahead, so each of the two dependent gathers has YD_PF steps to land
-    GDesc dq[YD_PF]; uint32_t gq[2 * YD_PF];
+    // prologue: ids of steps 0..2*YD_PF-1, then descriptors of steps 0..YD_PF-1 (one group each)
 #pragma unroll
     for (int p = 0; p < 2 * YD_PF; ++p) {
-      gq[p] = 0;
       const uint32_t idx = a + (uint32_t)p * 32u + lane;
-      if (idx < b) gq[p] = chain[idx] | (headflag[idx] << 31);
+      if (idx < b) { yd_cp_async4(&s_gid[wl][p][lane], chain + idx); yd_cp_async4(&s_flg[wl][p][lane], headflag + idx); }
     }
+    yd_cp_commit();
+    yd_cp_wait<0>();
 #pragma unroll
     for (int p = 0; p < YD_PF; ++p) {
-      dq[p].start = 0; dq[p].meta = 0; dq[p].e0 = dq[p].s1 = dq[p].e1 = dq[p].s2 = dq[p].e2 = dq[p].zend = 0;
-      if (a + (uint32_t)p * 32u + lane < b) dq[p] = cdesc[gq[p] & 0x7fffffffu];
+      if (a + (uint32_t)p * 32u + lane < b) {
+        const GDesc* src = cdesc + s_gid[wl][p][lane];
+        yd_cp_async16(&s_ring[wl][p][lane], src); yd_cp_async16(reinterpret_cast<char*>(&s_ring[wl][p][lane]) + 16, reinterpret_cast<const char*>(src) + 16);
+      }
+      yd_cp_commit();
     }
-    for (uint32_t cb0 = a; cb0 < b; cb0 += 32u * 2 * YD_PF) {
+    uint32_t step = 0;
+#pragma unroll 1
+    for (uint32_t cb = a; cb < b; cb += 32u, ++step) {
+      const int slot = (int)(step % YD_PF), islot = (int)(step % (2 * YD_PF)), nslot = (int)((step + YD_PF) % (2 * YD_PF));
+      yd_cp_wait<YD_PF - 1>();   // this step's descriptors and the ids of step + YD_PF have landed
+      const int cnt = (int)((b - cb) < 32u ? (b - cb) : 32u);
+      const bool live = lane < cnt;
+      GDesc dm; dm.start = 0; dm.meta = 0; dm.e0 = dm.s1 = dm.e1 = dm.s2 = dm.e2 = dm.zend = 0;
+      uint32_t g = 0; int head = 0;
+      if (live) { dm = s_ring[wl][slot][lane]; g = s_gid[wl][islot][lane]; head = (int)(s_flg[wl][islot][lane] & 1u); }
+      const int ne = (int)(dm.meta & 0xffffu);
+      // For a frontier E >= start the step is  E' = max(E, end of the last exon whose start <= E)  and exactly the
+      // exons up to that one are kept (exon starts lie beyond the previous exon's end); for E < start every exon is
+      // kept and E' = last end. So, GIVEN each member's class (bulk, or index jx of the exon that E reaches), the
+      // frontier is a segmented prefix max of one value per member. Guess the classes (heads: bulk, others: jx = 0,
+      // i.e. later exons dropped), scan, re-derive the classes from the frontier each member then sees, and repeat
+      // until nothing changes: a fixed point satisfies the recurrence member by member, hence is the exact result.
+      int jx = 0; bool bulk = head != 0;
+      int contrib = live ? (bulk ? dm.zend : dm.e0) : -1;
+      int e_after = F.E;
+      bool replay = false;
+#pragma unroll 1
+      for (int iter = 0;; ++iter) {
+        int v = contrib, h = head;
 #pragma unroll
-      for (int p2 = 0; p2 < 2 * YD_PF; ++p2) {
-        const int p = p2 % YD_PF;
-        const uint32_t cb = cb0 + (uint32_t)p2 * 32u;
-        if (cb < b) {   // warp-uniform
-          const GDesc dm = dq[p]; const uint32_t g = gq[p2] & 0x7fffffffu; const int head = (int)(gq[p2] >> 31);
-          { const uint32_t idx = cb + 32u * YD_PF + lane; if (idx < b) dq[p] = cdesc[gq[(p2 + YD_PF) % (2 * YD_PF)] & 0x7fffffffu]; }      // step +YD_PF
-          { const uint32_t idx = cb + 32u * 2 * YD_PF + lane; gq[p2] = idx < b ? (chain[idx] | (headflag[idx] << 31)) : 0u; }              // step +2*YD_PF
-          const int cnt = (int)((b - cb) < 32u ? (b - cb) : 32u);
-          const bool live = lane < cnt;
-          const int ne = (int)(dm.meta & 0xffffu);
-          // For a frontier E >= start the step is  E' = max(E, end of the last exon whose start <= E)  and exactly the
-          // exons up to that one are kept (exon starts lie beyond the previous exon's end); for E < start every exon is
-          // kept and E' = last end. So, GIVEN each member's class (bulk, or index jx of the exon that E reaches), the
-          // frontier is a segmented prefix max of one value per member. Guess the classes (heads: bulk, others: jx = 0,
-          // i.e. later exons dropped), scan, re-derive the classes from the frontier each member then sees, and repeat
-          // until nothing changes: a fixed point satisfies the recurrence member by member, hence is the exact result.
-          int jx = 0; bool bulk = head != 0;
-          int contrib = live ? (bulk ? dm.zend : dm.e0) : -1;
-          int e_after = F.E;
-          bool replay = false;
-          for (int iter = 0;; ++iter) {
-            int v = contrib, h = head;
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-              const int v2 = __shfl_up_sync(0xffffffffu, v, dd), h2 = __shfl_up_sync(0xffffffffu, h, dd);
-              if (lane >= dd) { if (!h) v = max(v, v2); h |= h2; }
-            }
-            if (!h) v = max(v, F.E);                     // no head at or before this lane: the carried sub-chain continues
-            int pm = __shfl_up_sync(0xffffffffu, v, 1);
-            if (lane == 0) pm = F.E;
-            bool nb = bulk; int nj = jx, nc = contrib;
-            if (live && !head) {
-              nb = pm < dm.start;
-              if (nb) { nj = 0; nc = dm.zend; }
-              else if (ne <= YD_INLINE_EX) {
-                nj = (ne >= 3 && pm >= dm.s2) ? 2 : ((ne >= 2 && pm >= dm.s1) ? 1 : 0);
-                nc = nj == 2 ? dm.e2 : (nj == 1 ? dm.e1 : dm.e0);
-              } else nj = yd_reach(in, rep[g], pm, U, rankpre, &nc);
-            }
-            const bool changed = nb != bulk || nj != jx;
-            bulk = nb; jx = nj; contrib = nc;
-            if (!__any_sync(0xffffffffu, changed)) { e_after = __shfl_sync(0xffffffffu, v, cnt - 1); break; }
-            if (iter >= 8) { replay = true; break; }
-          }
-          uint32_t r = bulk ? (uint32_t)ne : (uint32_t)jx + 1u;
-          if (replay) {   // no fixed point within a few rounds: one lane walks the step in order
-            s_desc[wl][lane] = dm; s_g[wl][lane] = g | ((uint32_t)head << 31);
-            __syncwarp();
-            if (lane == 0) {
-              for (int t = 0; t < cnt; ++t) {
-                const GDesc& d = s_desc[wl][t];
-                const uint32_t gg = s_g[wl][t];
-                if (gg >> 31) F.reset();
-                const uint32_t rr = ((d.meta & 0xffffu) > (uint32_t)YD_INLINE_EX) ? rep[gg & 0x7fffffffu] : 0u;
-                s_r[wl][t] = (uint8_t)F.step(in, d, rr, U, rankpre);
-              }
-            }
-            F.E = __shfl_sync(0xffffffffu, F.E, 0);
-            __syncwarp();
-            r = s_r[wl][lane];
-            __syncwarp();
-          } else F.E = e_after;
-          if (live) kept[cb + lane] = (uint8_t)r;
+        for (int dd = 1; dd < 32; dd <<= 1) {
+          const int v2 = __shfl_up_sync(0xffffffffu, v, dd), h2 = __shfl_up_sync(0xffffffffu, h, dd);
+          if (lane >= dd) { if (!h) v = max(v, v2); h |= h2; }
         }
+        if (!h) v = max(v, F.E);                     // no head at or before this lane: the carried sub-chain continues
+        int pm = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 0) pm = F.E;
+        bool nb = bulk; int nj = jx, nc = contrib;
+        if (live && !head) {
+          nb = pm < dm.start;
+          if (nb) { nj = 0; nc = dm.zend; }
+          else if (ne <= YD_INLINE_EX) {
+            nj = (ne >= 3 && pm >= dm.s2) ? 2 : ((ne >= 2 && pm >= dm.s1) ? 1 : 0);
+            nc = nj == 2 ? dm.e2 : (nj == 1 ? dm.e1 : dm.e0);
+          } else nj = yd_reach(in, rep[g], pm, U, rankpre, &nc);
+        }
+        const bool changed = nb != bulk || nj != jx;
+        bulk = nb; jx = nj; contrib = nc;
+        if (!__any_sync(0xffffffffu, changed)) { e_after = __shfl_sync(0xffffffffu, v, cnt - 1); break; }
+        if (iter >= 8) { replay = true; break; }
+      }
+      uint32_t r = bulk ? (uint32_t)ne : (uint32_t)jx + 1u;
+      if (replay) {   // no fixed point within a few rounds: one lane walks the step in order (ring entries of all lanes)
+        __syncwarp();
+        if (lane == 0) {
+          for (int t = 0; t < cnt; ++t) {
+            const GDesc& d = s_ring[wl][slot][t];
+            if (s_flg[wl][islot][t] & 1u) F.reset();
+            const uint32_t rr = ((d.meta & 0xffffu) > (uint32_t)YD_INLINE_EX) ? rep[s_gid[wl][islot][t]] : 0u;
+            s_r[wl][t] = (uint8_t)F.step(in, d, rr, U, rankpre);
+          }
+        }
+        F.E = __shfl_sync(0xffffffffu, F.E, 0);
+        __syncwarp();
+        r = s_r[wl][lane];
+        __syncwarp();
+      } else F.E = e_after;
+      if (live) kept[cb + lane] = (uint8_t)r;
+      // refill: descriptors of step + YD_PF into this step's ring slot, ids of step + 2*YD_PF into this step's id slot
+      {
+        const uint32_t idx = cb + 32u * YD_PF + lane;
+        if (idx < b) {
+          const GDesc* src = cdesc + s_gid[wl][nslot][lane];
+          yd_cp_async16(&s_ring[wl][slot][lane], src); yd_cp_async16(reinterpret_cast<char*>(&s_ring[wl][slot][lane]) + 16, reinterpret_cast<const char*>(src) + 16);
+        }
+        const uint32_t idx2 = cb + 32u * 2 * YD_PF + lane;
+        if (idx2 < b) { yd_cp_async4(&s_gid[wl][islot][lane], chain + idx2); yd_cp_async4(&s_flg[wl][islot][lane], headflag + idx2); }
+        yd_cp_commit();
       }
     }
+    yd_cp_wait<0>();
   }
 }
 
 // Y7: kept exons OR their links into the chain bitmaps; compact start per member for the lookup
 __global__ void __launch_bounds__(256) yd_link_kernel(ColIn in, const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ rep, const uint32_t* __restrict__ chain,
-                                                      const uint8_t* __restrict__ kept, int64_t n_members, const unsigned long long* __restrict__ colbase, int nchains,
+                                                      const uint8_t* __restrict__ kept, int64_t n_members, const uint32_t* __restrict__ flag,
                                                       const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre,
                                                       unsigned long long* __restrict__ bm, int64_t lpad, int32_t* __restrict__ mstart) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,7 +420,7 @@ __global__ void __launch_bounds__(256) yd_link_kernel(ColIn in, const GDesc* __r
   const uint32_t g = chain[i];
   const GDesc d = cdesc[g];
   const uint32_t r = kept[i];
-  const int64_t base = (int64_t)yd_chain_of(colbase, nchains, i) * lpad;
+  const int64_t base = (int64_t)(flag[i] >> 1) * lpad;
   yd_emit_links(in, d, r, r > (uint32_t)YD_INLINE_EX ? rep[g] : 0u, U, rankpre, bm, base);
   mstart[i] = d.start;
 }
@@ -413,14 +441,14 @@ struct LastZeroOut { long long* lz; __device__ void operator()(int64_t b, long l
 
 // ---- Y9: d = number of consecutive set links ending at start-1 --------------------------------------------------------
 __global__ void __launch_bounds__(256) yd_lookup_kernel(const int32_t* __restrict__ mstart, const uint32_t* __restrict__ chain, int64_t n_members,
-                                                        const unsigned long long* __restrict__ colbase, int nchains, const unsigned long long* __restrict__ bm,
+                                                        const uint32_t* __restrict__ flag, const unsigned long long* __restrict__ bm,
                                                         const long long* __restrict__ lz, int64_t lpad, int32_t* __restrict__ yd) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_members) return;
   const int x = mstart[i];
   if (x <= 0) return;
   const uint32_t g = chain[i];
-  const int64_t base = (int64_t)yd_chain_of(colbase, nchains, i) * lpad;
+  const int64_t base = (int64_t)(flag[i] >> 1) * lpad;
   const int64_t q = base + x - 1;
   int64_t w = q >> 6; const int b = (int)(q & 63);
   const unsigned long long word = bm[w];
@@ -603,7 +631,7 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
   const int64_t nuw = (ubits + 31) / 32 + 1;
   const int ubase = in.pos_lo + 1;
   TB_CUDA(B[XB_GDESC].ensure(sizeof(GDesc) * (size_t)G * 2));
-  TB_CUDA(B[XB_YDPM].ensure(sizeof(uint32_t) * (size_t)G * 2 + (size_t)G + 64));
+  TB_CUDA(B[XB_YDPM].ensure(sizeof(uint32_t) * (size_t)G * 4 + (size_t)G + 64));
   TB_CUDA(B[XB_YDBLK].ensure(sizeof(uint32_t) * (size_t)nblk * nchains + sizeof(uint64_t) * ((size_t)nblk * nchains + nchains + 16)));
   TB_CUDA(B[XB_WORK].ensure(256));
   TB_CUDA(B[XB_YDC].ensure(sizeof(int32_t) * (size_t)G));
@@ -611,7 +639,9 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
   GDesc* cdesc = desc + G;
   uint32_t* gend = B[XB_YDPM].as<uint32_t>();
   uint32_t* cend = gend + G;
-  uint8_t* gstrand = (uint8_t*)(cend + G);
+  uint32_t* gstart = cend + G;
+  uint32_t* cstart = gstart + G;
+  uint8_t* gstrand = (uint8_t*)(cstart + G);
   unsigned long long* blkoff = B[XB_YDBLK].as<unsigned long long>();            // [nchains*nblk] exclusive member offsets, chain-major
   unsigned long long* colbase = blkoff + (size_t)nblk * nchains;                // [nchains+1]
   uint32_t* blkcnt = (uint32_t*)(colbase + nchains + 16);                       // [nchains*nblk]
@@ -629,7 +659,7 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
   int64_t agg_need = tb_scan_blocks((int64_t)nblk * nchains); if (tb_scan_blocks(nuw) > agg_need) agg_need = tb_scan_blocks(nuw);
   TB_CUDA(B[XB_AGG].ensure((size_t)(agg_need + 8) * sizeof(uint64_t)));
   // ---- Y1, Y2 ----
-  yd_desc_kernel<<<tb_grid_for(G, 256), 256, 0, st>>>(in, grp.rep, G, desc, gend, gstrand, U, ubits, g.d_status);
+  yd_desc_kernel<<<tb_grid_for(G, 256), 256, 0, st>>>(in, grp.rep, G, desc, gend, gstart, gstrand, U, ubits, g.d_status);
   ctx->launches++;
   if (parallel) {
     TB_CUDA((tb_device_scan<OpSumU32>(ctx, UPopIn{U}, nuw, B[XB_AGG].as<uint32_t>(), UPopOut{rankpre})));
@@ -655,22 +685,23 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
   if (n_members > 0) {
     TB_CUDA(B[XB_YDCHAIN].ensure(sizeof(uint32_t) * ((size_t)n_members + 32)));
     TB_CUDA(B[XB_BHEAD].ensure(sizeof(uint32_t) * ((size_t)n_members + 32)));
-    TB_CUDA(B[XB_YDFLAG].ensure(sizeof(uint32_t) * ((size_t)n_members + 32)));
+    TB_CUDA(B[XB_YDFLAG].ensure((sizeof(uint32_t) + sizeof(uint16_t)) * ((size_t)n_members + 32)));
     const int64_t lpad = ((Lc + 1 + 511) / 512) * 512;            // bits per chain, at least one clear padding bit
     const int64_t nwords = lpad / 64 * nchains, nblocks512 = nwords / 8;
     TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks(nblocks512 > n_members ? nblocks512 : n_members) + 8) * sizeof(uint64_t)));
     uint32_t* chain = B[XB_YDCHAIN].as<uint32_t>(); uint32_t* heads = B[XB_BHEAD].as<uint32_t>(); uint32_t* flag = B[XB_YDFLAG].as<uint32_t>();
-    yd_scatter_kernel<<<tb_grid_for(nwarps * 32, 128), 128, 0, st>>>(grp.bits, W, k, G, gstrand, blkoff, nblk, chain);
+    uint16_t* mchain = (uint16_t*)(flag + n_members + 32);
+    yd_scatter_kernel<<<tb_grid_for(nwarps * 32, 128), 128, 0, st>>>(grp.bits, W, k, G, gstrand, blkoff, nblk, chain, mchain);
     ctx->launches++;
-    const GDesc* hd = desc; const uint32_t* he = gend;
+    const uint32_t* hs = gstart; const uint32_t* he = gend;
     if (parallel) {
-      yd_compact_kernel<<<tb_grid_for(G, 256), 256, 0, st>>>(desc, G, U, rankpre, ubase, cdesc, cend);
+      yd_compact_kernel<<<tb_grid_for(G, 256), 256, 0, st>>>(desc, G, U, rankpre, ubase, cdesc, cend, cstart);
       ctx->launches++;
-      hd = cdesc; he = cend;
+      hs = cstart; he = cend;
     }
     // ---- Y5: sub-chain heads ----
-    MemberKeyIn mk{chain, he, colbase, nchains};
-    TB_CUDA((tb_device_scan<OpMaxU64>(ctx, mk, n_members, B[XB_AGG].as<unsigned long long>(), MemberHeadOut{mk, hd, flag})));
+    MemberKeyIn mk{chain, he, mchain};
+    TB_CUDA((tb_device_scan<OpMaxU64>(ctx, mk, n_members, B[XB_AGG].as<unsigned long long>(), MemberHeadOut{mk, hs, flag})));
     TB_CUDA((tb_device_scan<OpSumU32>(ctx, FlagIn{flag}, n_members, B[XB_AGG].as<uint32_t>(), HeadListOut{heads})));
     yd_subchain_total_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(n_members), heads, (uint32_t)n_members, work);
     ctx->launches++;
@@ -688,12 +719,12 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
       TB_CUDA(B[XB_YDUNIT].ensure(sizeof(uint32_t) * ((size_t)nunits + 2)));
       uint32_t* ustart = B[XB_YDUNIT].as<uint32_t>();
       yd_unit_kernel<<<tb_grid_for((int64_t)nunits + 1, 256), 256, 0, st>>>(heads, B[XB_AGG].as<uint32_t>() + tb_scan_blocks(n_members), (uint32_t)n_members, nunits, ustart);
-      yd_frontier_kernel<<<(unsigned)ctx->sm_count * 8, YD_WARPS * 32, 0, st>>>(in, cdesc, grp.rep, chain, flag, ustart, nunits, work, U, rankpre, kept);
+      yd_frontier_kernel<<<(unsigned)ctx->sm_count * 16, YD_FWARPS * 32, 0, st>>>(in, cdesc, grp.rep, chain, flag, ustart, nunits, work, U, rankpre, kept);
       ctx->launches++;
-      yd_link_kernel<<<tb_grid_for(n_members, 256), 256, 0, st>>>(in, cdesc, grp.rep, chain, kept, n_members, colbase, nchains, U, rankpre, bm, lpad, mstart);
+      yd_link_kernel<<<tb_grid_for(n_members, 256), 256, 0, st>>>(in, cdesc, grp.rep, chain, kept, n_members, flag, U, rankpre, bm, lpad, mstart);
       ctx->launches += 2;
       TB_CUDA((tb_device_scan<OpMaxI64>(ctx, LastZeroIn{bm}, nblocks512, B[XB_AGG].as<long long>(), LastZeroOut{lz})));
-      yd_lookup_kernel<<<tb_grid_for(n_members, 256), 256, 0, st>>>(mstart, chain, n_members, colbase, nchains, bm, lz, lpad, ydc);
+      yd_lookup_kernel<<<tb_grid_for(n_members, 256), 256, 0, st>>>(mstart, chain, n_members, flag, bm, lz, lpad, ydc);
       ctx->launches++;
     } else {
       const size_t smem = (size_t)YD_WARPS * 2 * YD_CAP_SMEM * 32 * sizeof(uint32_t);
