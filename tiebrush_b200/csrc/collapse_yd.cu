@@ -149,8 +149,7 @@ __global__ void __launch_bounds__(128) yd_colbase_kernel(const unsigned long lon
 }
 // stable scatter of the group ids into the chain lists
 __global__ void __launch_bounds__(128) yd_scatter_kernel(const uint32_t* __restrict__ bits, uint32_t W, int k, int64_t G, const uint8_t* __restrict__ gstrand,
-                                                        const unsigned long long* __restrict__ blkoff, int64_t nblk, uint32_t* __restrict__ chain,
-                                                        uint16_t* __restrict__ mchain) {
+                                                        const unsigned long long* __restrict__ blkoff, int64_t nblk, uint32_t* __restrict__ chain) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= nblk * W) return;
   const int64_t b = warp / W; const uint32_t w = (uint32_t)(warp % W);
@@ -169,11 +168,18 @@ __global__ void __launch_bounds__(128) yd_scatter_kernel(const uint32_t* __restr
       const uint32_t wq = __shfl_sync(0xffffffffu, word, q);
       const int sq = __shfl_sync(0xffffffffu, (int)sc, q);
       if ((wq >> lane) & 1u) {
-        if (sq != '-') { chain[pf] = (uint32_t)(base + q); mchain[pf++] = (uint16_t)s; }
-        if (sq != '+') { chain[pr] = (uint32_t)(base + q); mchain[pr++] = (uint16_t)(k + s); }
+        if (sq != '-') chain[pf++] = (uint32_t)(base + q);
+        if (sq != '+') chain[pr++] = (uint32_t)(base + q);
       }
     }
   }
+}
+
+// chain id of every member: chain c owns members [colbase[c], colbase[c+1]) (coalesced fill, blockIdx.y = chain)
+constexpr int YD_FILL = 16384;
+__global__ void __launch_bounds__(256) yd_fill_mchain_kernel(const unsigned long long* __restrict__ colbase, uint16_t* __restrict__ mchain) {
+  const unsigned long long a = colbase[blockIdx.y] + (unsigned long long)blockIdx.x * YD_FILL, e = colbase[blockIdx.y + 1];
+  for (unsigned long long i = a + threadIdx.x; i < e && i < a + YD_FILL; i += 256) mchain[i] = (uint16_t)blockIdx.y;
 }
 
 // sub-chain heads: prefix max of (chain<<32 | end) over the member array is a segmented prefix max (chain ids ascend).
@@ -298,7 +304,8 @@ constexpr int YD_FWARPS = 4;   // warps per CTA of the frontier kernel (6 KB of 
 __global__ void __launch_bounds__(YD_FWARPS * 32) yd_frontier_kernel(ColIn in, const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ rep,
                                                                     const uint32_t* __restrict__ chain, const uint32_t* __restrict__ headflag,
                                                                     const uint32_t* __restrict__ ustart, uint32_t nunits, unsigned long long* work,
-                                                                    const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre, uint8_t* __restrict__ kept) {
+                                                                    const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre,
+                                                                    unsigned long long* __restrict__ bm, int64_t lpad, int32_t* __restrict__ mstart) {
   // two-stage pipeline per warp: member ids (group, head flag) are fetched 2*YD_PF steps ahead, descriptors YD_PF steps
   // ahead, so each of the two dependent gathers has YD_PF steps to land. A lane only ever reads ring entries it
   // requested itself (except in the replay, which synchronises the warp first).
@@ -393,7 +400,12 @@ __global__ void __launch_bounds__(YD_FWARPS * 32) yd_frontier_kernel(ColIn in, c
         r = s_r[wl][lane];
         __syncwarp();
       } else F.E = e_after;
-      if (live) kept[cb + lane] = (uint8_t)r;
+      // Y7 fused: the kept exons OR their links into the chain's bitmap; compact start per member for the lookup
+      if (live) {
+        const int64_t base = (int64_t)(s_flg[wl][islot][lane] >> 1) * lpad;
+        yd_emit_links(in, dm, r, r > (uint32_t)YD_INLINE_EX ? rep[g] : 0u, U, rankpre, bm, base);
+        mstart[cb + lane] = dm.start;
+      }
       // refill: descriptors of step + YD_PF into this step's ring slot, ids of step + 2*YD_PF into this step's id slot
       {
         const uint32_t idx = cb + 32u * YD_PF + lane;
@@ -408,21 +420,6 @@ __global__ void __launch_bounds__(YD_FWARPS * 32) yd_frontier_kernel(ColIn in, c
     }
     yd_cp_wait<0>();
   }
-}
-
-// Y7: kept exons OR their links into the chain bitmaps; compact start per member for the lookup
-__global__ void __launch_bounds__(256) yd_link_kernel(ColIn in, const GDesc* __restrict__ cdesc, const uint32_t* __restrict__ rep, const uint32_t* __restrict__ chain,
-                                                      const uint8_t* __restrict__ kept, int64_t n_members, const uint32_t* __restrict__ flag,
-                                                      const uint32_t* __restrict__ U, const uint32_t* __restrict__ rankpre,
-                                                      unsigned long long* __restrict__ bm, int64_t lpad, int32_t* __restrict__ mstart) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_members) return;
-  const uint32_t g = chain[i];
-  const GDesc d = cdesc[g];
-  const uint32_t r = kept[i];
-  const int64_t base = (int64_t)(flag[i] >> 1) * lpad;
-  yd_emit_links(in, d, r, r > (uint32_t)YD_INLINE_EX ? rep[g] : 0u, U, rankpre, bm, base);
-  mstart[i] = d.start;
 }
 
 // ---- Y8: position of the last clear link before every 512-bit block ---------------------------------------------------
@@ -691,8 +688,9 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
     TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks(nblocks512 > n_members ? nblocks512 : n_members) + 8) * sizeof(uint64_t)));
     uint32_t* chain = B[XB_YDCHAIN].as<uint32_t>(); uint32_t* heads = B[XB_BHEAD].as<uint32_t>(); uint32_t* flag = B[XB_YDFLAG].as<uint32_t>();
     uint16_t* mchain = (uint16_t*)(flag + n_members + 32);
-    yd_scatter_kernel<<<tb_grid_for(nwarps * 32, 128), 128, 0, st>>>(grp.bits, W, k, G, gstrand, blkoff, nblk, chain, mchain);
-    ctx->launches++;
+    yd_scatter_kernel<<<tb_grid_for(nwarps * 32, 128), 128, 0, st>>>(grp.bits, W, k, G, gstrand, blkoff, nblk, chain);
+    yd_fill_mchain_kernel<<<dim3((unsigned)((n_members + YD_FILL - 1) / YD_FILL), (unsigned)nchains), 256, 0, st>>>(colbase, mchain);
+    ctx->launches += 2;
     const uint32_t* hs = gstart; const uint32_t* he = gend;
     if (parallel) {
       yd_compact_kernel<<<tb_grid_for(G, 256), 256, 0, st>>>(desc, G, U, rankpre, ubase, cdesc, cend, cstart);
@@ -707,11 +705,10 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
     ctx->launches++;
     if (parallel) {
       // ---- Y6-Y9 ----
-      TB_CUDA(B[XB_YDKEPT].ensure(sizeof(int32_t) * (size_t)n_members + (size_t)n_members + 128));
+      TB_CUDA(B[XB_YDKEPT].ensure(sizeof(int32_t) * (size_t)n_members + 128));
       TB_CUDA(B[XB_YDBM].ensure(sizeof(uint64_t) * (size_t)nwords + 64));
       TB_CUDA(B[XB_YDLZ].ensure(sizeof(int64_t) * (size_t)nblocks512 + 64));
       int32_t* mstart = B[XB_YDKEPT].as<int32_t>();
-      uint8_t* kept = (uint8_t*)(mstart + n_members + 8);
       unsigned long long* bm = B[XB_YDBM].as<unsigned long long>();
       long long* lz = B[XB_YDLZ].as<long long>();
       TB_CUDA(cudaMemsetAsync(bm, 0, sizeof(uint64_t) * (size_t)nwords, st));
@@ -719,9 +716,8 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
       TB_CUDA(B[XB_YDUNIT].ensure(sizeof(uint32_t) * ((size_t)nunits + 2)));
       uint32_t* ustart = B[XB_YDUNIT].as<uint32_t>();
       yd_unit_kernel<<<tb_grid_for((int64_t)nunits + 1, 256), 256, 0, st>>>(heads, B[XB_AGG].as<uint32_t>() + tb_scan_blocks(n_members), (uint32_t)n_members, nunits, ustart);
-      yd_frontier_kernel<<<(unsigned)ctx->sm_count * 16, YD_FWARPS * 32, 0, st>>>(in, cdesc, grp.rep, chain, flag, ustart, nunits, work, U, rankpre, kept);
+      yd_frontier_kernel<<<(unsigned)ctx->sm_count * 16, YD_FWARPS * 32, 0, st>>>(in, cdesc, grp.rep, chain, flag, ustart, nunits, work, U, rankpre, bm, lpad, mstart);
       ctx->launches++;
-      yd_link_kernel<<<tb_grid_for(n_members, 256), 256, 0, st>>>(in, cdesc, grp.rep, chain, kept, n_members, flag, U, rankpre, bm, lpad, mstart);
       ctx->launches += 2;
       TB_CUDA((tb_device_scan<OpMaxI64>(ctx, LastZeroIn{bm}, nblocks512, B[XB_AGG].as<long long>(), LastZeroOut{lz})));
       yd_lookup_kernel<<<tb_grid_for(n_members, 256), 256, 0, st>>>(mstart, chain, n_members, flag, bm, lz, lpad, ydc);
