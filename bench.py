@@ -84,6 +84,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def traffic_per_record(kernel):
+    """DRAM bytes per record of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return float(json.load(open(p))[kernel]["bytes_per_record"])
+    except Exception:
+        return None
+
+
 def host_slice_sample(host, run_off, target):
     """A coordinate slice [lo,hi) of the window holding ~target records: all files, whole positions."""
     n = len(host["pos"])
@@ -219,7 +228,9 @@ def main():
         tiecov_line = {"metric": "coverage_bases_per_sec", "value": world * mbases / (cov_ms / 1000.0), "unit": "bases/s",
                           "records_per_sec": world * ncov / (cov_ms / 1000.0), "ms_per_step": cov_ms, "records": ncov, "runs": r["n_runs"], "juncs": r["n_juncs"],
                           "roofline": {"bound": "hbm", "kernel": "cov_accumulate_kernel", "achieved": a_cov / (np.mean(cms) / 1000.0) / 1e9, "peak": peak,
-                                       "unit": "GB/s", "frac": a_cov / (np.mean(cms) / 1000.0) / 1e9 / peak, "kernel_ms": float(np.mean(cms)), "traffic": None},
+                                       "unit": "GB/s", "frac": a_cov / (np.mean(cms) / 1000.0) / 1e9 / peak, "kernel_ms": float(np.mean(cms)),
+                                       "traffic": (lambda t: None if t is None else t * ncov)(traffic_per_record("cov_accumulate_kernel")),
+                                       "traffic_source": "ncu dram bytes per record (profiles/traffic.json) x records of this launch"},
                           "stage_ms": dict(zip(("bundles", "accumulate", "runs"), [float(x) for x in cstages]))}
         del cov, ocov, r
         cctx.close()
@@ -274,7 +285,9 @@ def main():
     kernel_ms = float(np.mean(kms))
     achieved = a_col / (kernel_ms / 1000.0) / 1e9
     roofline = {"bound": "hbm", "kernel": "col_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms, "algorithmic_bytes": a_col,
+                "traffic": (lambda t: None if t is None else t * n)(traffic_per_record("col_tile_kernel")),
+                "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum per record at 100x2M (profiles/traffic.json) x records of this launch",
+                "peak_source": peak_src, "kernel_ms": kernel_ms, "algorithmic_bytes": a_col,
                 "layout_bytes": n * (14 + 4 * cbar) + 16 * G}
     line = {"metric": "alignments_collapsed_per_sec", "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -1,0 +1,200 @@
+// tiebrush_gpu — the reference `tiebrush` command line with its hot loop running on a B200.
+//
+// This translation unit compiles the UNMODIFIED reference source (src/tiebrush.cpp, from where it lies under the
+// reference checkout given with -I) with its main() renamed, and supplies a new main() that keeps everything the
+// reference keeps on the host — option parsing (processOptions, tiebrush.cpp:603-680), header merge and the
+// TieBrush-made-input detection (TInputFiles::start, tmerge.cpp:288-329), BGZF/BAM decode (GSamReader), tag patching
+// (GSamRecord::add_*_tag -> bam_aux_update_*), BAM write (GSamWriter) and the final summary line — and replaces
+//     TInputFiles::next() order + passes_options() + addPData() + flushPData()      (tiebrush.cpp:570-592)
+// by a WINDOW PACKER and one tb_collapse_window() call per window (include/tiebrush_b200.h).
+//
+// Window = consecutive records of the merged stream on one tid, cut only where the next read starts beyond the end
+// of every read seen so far on that tid (a global coverage gap): collapse groups never span a start position and
+// every per-sample YD segment list is provably empty after the first read past such a gap (tiebrush.cpp:237-242), so
+// a window needs no state from its predecessor. Records are handed over FILE-MAJOR (the device does the k-way
+// merge itself); the raw GSamRecords of a window stay alive until rep_index[] comes back, then the representatives
+// get their tags and are written, the rest are freed.
+//
+// No CPU fallback: without a CUDA device tb_create() fails and the tool exits 1 like any other GError.
+#define main tb_reference_main_unused
+#include "src/tiebrush.cpp"
+#undef main
+
+#include <vector>
+#include <chrono>
+#include "tiebrush_b200.h"
+
+namespace {
+
+struct TbWindowPacker {
+  int k = 0;
+  std::vector<std::vector<GSamRecord*>> per_file;   // records of the open window, per input file, in file order
+  std::vector<uint8_t> file_merged;
+  size_t n = 0;
+  // SoA staging (reused between windows)
+  std::vector<int64_t> run_off;
+  std::vector<int32_t> pos, yx_in, yd_in;
+  std::vector<uint16_t> flag, nh;
+  std::vector<uint8_t> mapq, strand, md;
+  std::vector<uint32_t> cig_off, cigar, md_off;
+  std::vector<uint64_t> qhash;
+  std::vector<float> yc_in;
+  std::vector<GSamRecord*> held;                    // window index -> record
+  std::vector<uint32_t> o_rep, o_yx; std::vector<float> o_yc; std::vector<int32_t> o_yd;
+  double t_pack = 0, t_device = 0, t_write = 0;
+  int64_t n_windows = 0;
+
+  void init(int nfiles) { k = nfiles; per_file.assign(k, {}); file_merged.assign(k, 0); }
+
+  static uint64_t fnv1a(const char* s) {
+    uint64_t h = 1469598103934665603ULL;
+    for (; *s; ++s) { h ^= (unsigned char)*s; h *= 1099511628211ULL; }
+    return h;
+  }
+
+  void add(TInputRecord* irec) {
+    per_file[irec->fidx].push_back(irec->brec);
+    file_merged[irec->fidx] = irec->tbMerged ? 1 : 0;
+    irec->disown();   // the window owns the record now (TInputFiles::next deletes its current record otherwise)
+    ++n;
+  }
+
+  void flush(tb_ctx* ctx, int tid) {
+    if (n == 0) return;
+    using clk = std::chrono::steady_clock;
+    auto t0 = clk::now();
+    const bool want_md = mrgStrategy == tMrgStratFull;
+    const bool want_q = options.collapse_same;
+    bool any_merged = false;
+    for (int f = 0; f < k; ++f) any_merged |= file_merged[f] != 0;
+    run_off.assign(k + 1, 0);
+    pos.resize(n); flag.resize(n); mapq.resize(n); strand.resize(n); nh.resize(n); cig_off.resize(n + 1);
+    cigar.clear(); held.resize(n);
+    if (want_md) { md_off.resize(n + 1); md.clear(); }
+    if (want_q) qhash.resize(n);
+    if (any_merged) { yc_in.resize(n); yx_in.resize(n); yd_in.resize(n); }
+    size_t i = 0;
+    int32_t pos_lo = 0x7fffffff, pos_hi = 0;
+    for (int f = 0; f < k; ++f) {
+      run_off[f] = (int64_t)i;
+      for (GSamRecord* r : per_file[f]) {
+        bam1_t* b = r->get_b();
+        held[i] = r;
+        pos[i] = (int32_t)b->core.pos;
+        if (pos[i] < pos_lo) pos_lo = pos[i];
+        if (pos[i] >= pos_hi) pos_hi = pos[i] + 1;
+        flag[i] = b->core.flag;
+        mapq[i] = b->core.qual;
+        strand[i] = (uint8_t)r->spliceStrand();                      // GSam.cpp:464-475
+        int64_t v = r->tag_int("NH", 0);                             // passes_options, tiebrush.cpp:537
+        nh[i] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+        cig_off[i] = (uint32_t)cigar.size();
+        const uint32_t* c = bam_get_cigar(b);
+        cigar.insert(cigar.end(), c, c + b->core.n_cigar);
+        if (want_md) {
+          md_off[i] = (uint32_t)md.size();
+          const char* m = r->tag_str("MD");                          // cmpFull, tiebrush.cpp:285-304
+          if (m) md.insert(md.end(), (const uint8_t*)m, (const uint8_t*)m + strlen(m) + 1);
+        }
+        if (want_q) qhash[i] = fnv1a(r->name());
+        if (any_merged) {
+          yc_in[i] = file_merged[f] ? (float)r->tag_float("YC") : 0.f;  // SPData::settle, tiebrush.cpp:389-395
+          yx_in[i] = file_merged[f] ? (int32_t)r->tag_int("YX", 1) : 1;
+          yd_in[i] = file_merged[f] ? (int32_t)r->tag_int("YD", 0) : 0;
+        }
+        ++i;
+      }
+    }
+    run_off[k] = (int64_t)i;
+    cig_off[n] = (uint32_t)cigar.size();
+    if (want_md) md_off[n] = (uint32_t)md.size();
+    if (cigar.empty()) cigar.push_back(0);
+    if (want_md && md.empty()) md.push_back(0);
+
+    tb_soa_in in; memset(&in, 0, sizeof(in));
+    in.n = (int64_t)n; in.n_files = k; in.tid = tid; in.run_off = run_off.data(); in.file_merged = any_merged ? file_merged.data() : NULL;
+    in.pos = pos.data(); in.flag = flag.data(); in.mapq = mapq.data(); in.strand = strand.data(); in.nh = nh.data();
+    in.cig_off = cig_off.data(); in.cigar = cigar.data(); in.n_cig = (int64_t)cig_off[n];
+    if (want_md) { in.md_off = md_off.data(); in.md = md.data(); in.n_md = (int64_t)md_off[n]; }
+    if (want_q) in.qhash = qhash.data();
+    if (any_merged) { in.yc_in = yc_in.data(); in.yx_in = yx_in.data(); in.yd_in = yd_in.data(); }
+    in.on_device = 0; in.pos_lo = pos_lo; in.pos_hi = pos_hi;
+    o_rep.resize(n); o_yc.resize(n); o_yx.resize(n); o_yd.resize(n);
+    tb_groups_out out; memset(&out, 0, sizeof(out));
+    out.capacity = (int64_t)n; out.rep_index = o_rep.data(); out.yc = o_yc.data(); out.yx = o_yx.data(); out.yd = o_yd.data();
+    auto t1 = clk::now();
+    if (tb_collapse_window(ctx, &in, &out)) GError("%s\n", tb_last_error(ctx));
+    auto t2 = clk::now();
+    inCounter += (uint64_t)out.n_kept;                               // tiebrush.cpp:573
+    for (int64_t g = 0; g < out.n_groups; ++g) {                     // flushPData, tiebrush.cpp:506-527
+      GSamRecord* r = held[o_rep[g]];
+      r->add_double_tag("YC", (double)o_yc[g]);
+      r->add_int_tag("YX", (int64_t)o_yx[g]);
+      if (o_yd[g] > 0) r->add_int_tag("YD", o_yd[g]); else r->remove_tag("YD");
+      outfile->write(r);
+      outCounter++;
+    }
+    for (GSamRecord* r : held) delete r;
+    for (int f = 0; f < k; ++f) per_file[f].clear();
+    n = 0; ++n_windows;
+    auto t3 = clk::now();
+    t_pack += std::chrono::duration<double>(t1 - t0).count();
+    t_device += std::chrono::duration<double>(t2 - t1).count();
+    t_write += std::chrono::duration<double>(t3 - t2).count();
+  }
+};
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+  using clk = std::chrono::steady_clock;
+  auto t_begin = clk::now();
+  inRecords.setup(VERSION, argc, argv);
+  processOptions(argc, argv);
+  int numSamples = inRecords.start();
+  outfile = new GSamWriter(outfname, inRecords.header(), GSamFile_BAM);
+
+  const int keep = (options.keep_supplementary ? TB_KEEP_SUPP : 0) | (options.keep_secondary ? TB_KEEP_SECONDARY : 0) |
+                   (options.keep_unmapped ? TB_KEEP_UNMAP : 0) | (options.store_frac ? TB_STORE_FRAC : 0);
+  const int mode = mrgStrategy == tMrgStratFull ? TB_MODE_FULL : mrgStrategy == tMrgStratClip ? TB_MODE_CLIP :
+                   mrgStrategy == tMrgStratExon ? TB_MODE_EXON : TB_MODE_CIGAR;
+  const char* dev_env = getenv("TB_DEVICE");
+  tb_ctx* ctx = tb_create(dev_env ? atoi(dev_env) : 0, numSamples, mode, options.flags, options.max_nh, options.min_qual, keep,
+                          options.collapse_same ? 1 : 0);
+  if (!ctx) GError("%s\n", tb_last_error(NULL));
+  // records buffered before a coverage gap closes the window (TB_WINDOW_RECORDS; host memory ~ 400 B per record)
+  size_t window_min = 4u << 20;
+  if (const char* e = getenv("TB_WINDOW_RECORDS")) { long v = atol(e); if (v > 0) window_min = (size_t)v; }
+
+  TbWindowPacker packer; packer.init(numSamples);
+  TInputRecord* irec = NULL;
+  int cur_tid = -2; uint max_end = 0;
+  double t_read = 0;
+  auto tr0 = clk::now();
+  while ((irec = inRecords.next()) != NULL) {
+    GSamRecord* brec = irec->brec;
+    const int tid = brec->refId();
+    if (brec->isUnmapped() || tid < 0)   // the reference's own loop does not survive these either
+      GError("Error: unmapped read %s in the input (not supported by tiebrush)\n", brec->name());
+    if (tid != cur_tid || (packer.n >= window_min && brec->start > max_end)) {
+      t_read += std::chrono::duration<double>(clk::now() - tr0).count();
+      packer.flush(ctx, cur_tid);
+      tr0 = clk::now();
+      if (tid != cur_tid) { cur_tid = tid; max_end = 0; }
+    }
+    if (brec->end > max_end) max_end = brec->end;
+    packer.add(irec);
+  }
+  t_read += std::chrono::duration<double>(clk::now() - tr0).count();
+  packer.flush(ctx, cur_tid);
+  inRecords.stop();
+  delete outfile;
+  tb_destroy(ctx);
+
+  double p = 100.00 - (double)(outCounter * 100.00) / (double)inCounter;
+  GMessage("%ld input records written as %ld (%.2f%% reduction)\n", inCounter, outCounter, p);
+  if (getenv("TB_TIMING"))
+    fprintf(stderr, "tb_b200 timing: total %.3f s | decode+merge %.3f | pack %.3f | device (H2D+kernels+D2H) %.3f | tag+write %.3f | windows %ld\n",
+            std::chrono::duration<double>(clk::now() - t_begin).count(), t_read, packer.t_pack, packer.t_device, packer.t_write, (long)packer.n_windows);
+  return 0;
+}
