@@ -1,0 +1,136 @@
+// tiecov_gpu — the reference `tiecov` command line (-c coverage bedGraph, -j junction BED) with its hot loop on a B200.
+//
+// Compiles the UNMODIFIED reference source (src/tiecov.cpp, from where it lies under the reference checkout given with
+// -I) with its main() renamed, and supplies a new main() that keeps option parsing (processOptions, tiecov.cpp:533-581),
+// BAM decode (GSamReader), output file naming / track lines (tiecov.cpp:352-411) and the text formatting
+// ("%s\t%d\t%d\t%.3f", "JUNC%08d") on the host, and replaces
+//     bundle logic + addCov + flushCoverage + addJunction + flushJuncs           (tiecov.cpp:435-512)
+// by a window packer and one tc_coverage_window() call per window (include/tiebrush_b200.h).
+// A window is cut only where a new bundle starts (tid change or start > running max end, tiecov.cpp:443), so windows
+// hold whole bundles. -s (sample heat-map) and -W (BigWig) are not on the device path: asking for them
+// exits with an error rather than silently running the CPU code.
+#define main tc_reference_main_unused
+#include "src/tiecov.cpp"
+#undef main
+
+#include <vector>
+#include <chrono>
+#include "tiebrush_b200.h"
+
+namespace {
+
+struct TcWindowPacker {
+  std::vector<int32_t> tid, pos;
+  std::vector<float> yc;
+  std::vector<uint8_t> strand;
+  std::vector<uint32_t> cig_off, cigar;
+  std::vector<int32_t> r_tid, r_start, r_end, j_tid, j_start, j_end; std::vector<double> r_val, j_val; std::vector<uint8_t> j_strand;
+  double t_device = 0, t_print = 0; int64_t n_windows = 0;
+
+  size_t n() const { return pos.size(); }
+
+  void add(GSamRecord& brec) {
+    bam1_t* b = brec.get_b();
+    tid.push_back(b->core.tid); pos.push_back((int32_t)b->core.pos);
+    double w = 1.0;                                                  // tiecov.cpp:482-485
+    if (brec.find_tag("YC") != NULL) w = brec.tag_float("YC");
+    yc.push_back((float)w);
+    strand.push_back((uint8_t)brec.spliceStrand());
+    cig_off.push_back((uint32_t)cigar.size());
+    const uint32_t* c = bam_get_cigar(b);
+    cigar.insert(cigar.end(), c, c + b->core.n_cigar);
+  }
+
+  void flush(tb_ctx* ctx, sam_hdr_t* hdr) {
+    const size_t m = n();
+    if (m == 0) return;
+    using clk = std::chrono::steady_clock;
+    auto t0 = clk::now();
+    cig_off.push_back((uint32_t)cigar.size());
+    const int64_t ncig = (int64_t)cigar.size();
+    if (cigar.empty()) cigar.push_back(0);
+    tc_soa_in in; memset(&in, 0, sizeof(in));
+    in.n = (int64_t)m; in.tid = tid.data(); in.pos = pos.data(); in.yc = yc.data(); in.strand = strand.data();
+    in.cig_off = cig_off.data(); in.cigar = cigar.data(); in.on_device = 0; in.n_cig = ncig;
+    const int64_t cap_r = 2 * ncig + 16, cap_j = ncig + 16;
+    tc_runs_out runs; memset(&runs, 0, sizeof(runs));
+    tc_juncs_out js; memset(&js, 0, sizeof(js));
+    if (coutf) {
+      r_tid.resize(cap_r); r_start.resize(cap_r); r_end.resize(cap_r); r_val.resize(cap_r);
+      runs.capacity = cap_r; runs.tid = r_tid.data(); runs.start0 = r_start.data(); runs.end0 = r_end.data(); runs.value = r_val.data();
+    }
+    if (joutf) {
+      j_tid.resize(cap_j); j_start.resize(cap_j); j_end.resize(cap_j); j_val.resize(cap_j); j_strand.resize(cap_j);
+      js.capacity = cap_j; js.tid = j_tid.data(); js.start = j_start.data(); js.end = j_end.data(); js.strand = j_strand.data(); js.value = j_val.data();
+    }
+    const int rc = tc_coverage_window(ctx, &in, coutf ? &runs : NULL, joutf ? &js : NULL);
+    if (rc) GError("%s\n", tb_last_error(ctx));                      // incl. the "unknown opcode" abort of tiecov.cpp:219-220
+    auto t1 = clk::now();
+    if (coutf)
+      for (int64_t i = 0; i < runs.n_runs; ++i)                      // flushCoverage, tiecov.cpp:237
+        fprintf(coutf, "%s\t%d\t%d\t%.3f\n", hdr->target_name[r_tid[i]], r_start[i], r_end[i], r_val[i]);
+    if (joutf)
+      for (int64_t i = 0; i < js.n_juncs; ++i) {                     // CJunc::write, tiecov.cpp:91-95
+        juncCount++;
+        fprintf(joutf, "%s\t%d\t%d\tJUNC%08d\t%.3f\t%c\n", hdr->target_name[j_tid[i]], j_start[i] - 1, j_end[i], juncCount, j_val[i], (char)j_strand[i]);
+      }
+    tid.clear(); pos.clear(); yc.clear(); strand.clear(); cig_off.clear(); cigar.clear();
+    ++n_windows;
+    auto t2 = clk::now();
+    t_device += std::chrono::duration<double>(t1 - t0).count();
+    t_print += std::chrono::duration<double>(t2 - t1).count();
+  }
+};
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+  using clk = std::chrono::steady_clock;
+  auto t_begin = clk::now();
+  processOptions(argc, argv);
+  if (bigwig) GError("Error: -W (BigWig) is not available in tiecov_gpu (libBigWig is not part of the device path)\n");
+  if (!sfname.is_empty()) GError("Error: -s (sample heat-map) is not available in tiecov_gpu yet; use -c / -j\n");
+  GSamReader samreader(infname.chars(), SAM_QNAME | SAM_FLAG | SAM_RNAME | SAM_POS | SAM_CIGAR | SAM_AUX);
+  // output files: names, suffixes and track lines exactly as tiecov.cpp:352-411
+  if (!covfname.is_empty()) {
+    if (covfname == "-" || covfname == "stdout") coutf = stdout;
+    else {
+      if (std::strcmp(covfname.substr(covfname.length() - 9, 9).chars(), ".bedgraph") != 0) covfname.append(".bedgraph");
+      coutf = fopen(covfname.chars(), "w");
+      if (coutf == NULL) GError("Error creating file %s\n", covfname.chars());
+      fprintf(coutf, "track type=bedGraph\n");
+    }
+  }
+  if (!jfname.is_empty()) {
+    if (std::strcmp(jfname.substr(jfname.length() - 4, 4).chars(), ".bed") != 0) jfname.append(".bed");
+    joutf = fopen(jfname.chars(), "w");
+    if (joutf == NULL) GError("Error creating file %s\n", jfname.chars());
+    fprintf(joutf, "track name=junctions\n");
+  }
+  const char* dev_env = getenv("TB_DEVICE");
+  tb_ctx* ctx = tb_create(dev_env ? atoi(dev_env) : 0, 1, TB_MODE_CIGAR, 0, TB_NO_MAX_NH, -1, 0, 0);
+  if (!ctx) GError("%s\n", tb_last_error(NULL));
+  size_t window_min = 8u << 20;   // records buffered before a bundle boundary closes the window (TB_WINDOW_RECORDS)
+  if (const char* e = getenv("TB_WINDOW_RECORDS")) { long v = atol(e); if (v > 0) window_min = (size_t)v; }
+
+  TcWindowPacker packer;
+  int prev_tid = -1, b_end = 0;
+  GSamRecord brec;
+  while (samreader.next(brec)) {
+    if (brec.isUnmapped()) continue;                                 // tiecov.cpp:436-438
+    const bool new_bundle = brec.refId() != prev_tid || (int)brec.start > b_end;   // tiecov.cpp:443
+    if (new_bundle) {
+      if (packer.n() >= window_min) packer.flush(ctx, samreader.header());
+      b_end = brec.end; prev_tid = brec.refId();
+    } else if (b_end < (int)brec.end) b_end = brec.end;
+    packer.add(brec);
+  }
+  packer.flush(ctx, samreader.header());
+  if (coutf && coutf != stdout) fclose(coutf);
+  if (joutf) fclose(joutf);
+  tb_destroy(ctx);
+  if (getenv("TB_TIMING"))
+    fprintf(stderr, "tb_b200 timing: total %.3f s | device (H2D+kernels+D2H) %.3f | print %.3f | windows %ld\n",
+            std::chrono::duration<double>(clk::now() - t_begin).count(), packer.t_device, packer.t_print, (long)packer.n_windows);
+  return 0;
+}
