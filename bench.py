@@ -39,6 +39,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("TB_BENCH_CPU_SAMPLE", 20_000_000)),
                     help="records of the cohort fed to the CPU baseline (bounded sample)")
+    ap.add_argument("--cli-reads", type=int, default=int(os.environ.get("TB_BENCH_CLI_READS", 20_000)),
+                    help="reads per sample file of the host command-line leg (0 = skip)")
     ap.add_argument("--ref-reads", type=int, default=int(os.environ.get("TB_BENCH_REF_READS", 20_000)),
                     help="--impl reference: reads per sample file written as SAM for the reference binary")
     return ap.parse_args()
@@ -172,6 +174,36 @@ def run_reference_arm(args):
                                   "sample": f"{args.samples} files x {args.ref_reads} reads of the C2 cohort model as SAM text, reference tiebrush -O2, 1 thread (the reference is single-threaded)"},
                  "e2e": {"value": v, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line))
+
+
+def run_host_cli(args):
+    """tiebrush_gpu (reference main loop replaced by the window packer + tb_collapse_window) on SAM files of the cohort."""
+    import re
+    from tiebrush_b200 import synth
+    exe = os.path.join(ROOT, "tiebrush_b200", "host", "_build", "tiebrush_gpu")
+    if not os.path.exists(exe):
+        return {"unavailable": "tiebrush_b200/host/_build/tiebrush_gpu not built (needs /root/reference at build time)"}
+    cols, run_off, _ = synth.cohort_window(args.samples, args.cli_reads, seed=0, device="cpu")
+    host = synth.to_host(cols)
+    n = len(host["pos"])
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = write_sam_files(host, run_off, tmp)
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, "-o", os.path.join(tmp, "o.bam")] + paths, capture_output=True, text=True, env=dict(os.environ, TB_TIMING="1"))
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                return {"unavailable": "tiebrush_gpu failed: " + r.stderr[-200:]}
+            if best is None or dt < best[0]:
+                best = (dt, r.stderr)
+    m = re.search(r"total ([0-9.]+) s \| decode\+merge ([0-9.]+) \| pack ([0-9.]+) \| device \(H2D\+kernels\+D2H\) ([0-9.]+) \| tag\+write ([0-9.]+) \| windows (\d+)", best[1])
+    out = {"value": n / best[0], "unit": "alignments/s", "wall_s": best[0], "records": n,
+           "sample": f"{args.samples} SAM files x {args.cli_reads} reads of the C2 cohort model (same sample as --impl reference), best of 3, process start to exit"}
+    if m:
+        out.update({"in_process_s": float(m.group(1)), "decode_merge_s": float(m.group(2)), "pack_s": float(m.group(3)),
+                    "device_s": float(m.group(4)), "tag_write_s": float(m.group(5)), "windows": int(m.group(6))})
+    return out
 
 
 def main():
@@ -351,6 +383,10 @@ def main():
         ns = len(sub["pos"])
         line["cpu_baseline"] = {"value": ns / dt, "unit": "alignments/s", "cores": 1, "kind": "port",
                                 "sample": f"coordinate slice of the same window: {ns} records of all {k} samples ({dt:.1f} s); C port of the reference algorithm (oracle/tb_oracle.c), no BAM decode"}
+    # ---- the reference's command line over the C ABI (tiebrush_b200/host), same bounded SAM sample as --impl reference:
+    #      wall time with host decode / pack / device / tag+write broken out (rank 0, N=1 only) ----
+    if rank == 0 and world == 1 and args.cli_reads > 0:
+        line["host_cli"] = run_host_cli(args)
     if rank == 0:
         print(json.dumps(line))
     ctx.close()
