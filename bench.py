@@ -33,9 +33,13 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=int(os.environ.get("TB_BENCH_SAMPLES", 100)))
     ap.add_argument("--reads", type=int, default=int(os.environ.get("TB_BENCH_READS", 10_000_000)), help="reads per sample")
-    ap.add_argument("--mode", type=int, default=0)
+    ap.add_argument("--mode", type=int, default=0, help="0 default CIGAR, 1 -L (CIGAR+MD), 2 -P (clip), 3 -E (exon boundaries)")
+    ap.add_argument("--max-nh", type=int, default=0x7fffffff, help="-N (C3 filters)")
+    ap.add_argument("--min-qual", type=int, default=-1, help="-Q")
+    ap.add_argument("--flag-mask", type=int, default=0, help="-F (uses the paired-end cohort so the mask has bits to bite on)")
     ap.add_argument("--cov-records", type=int, default=int(os.environ.get("TB_BENCH_COV", 100_000_000)),
                     help="records of the secondary tiecov leg (0 = skip)")
+    ap.add_argument("--cov-chroms", type=int, default=1, help="chromosomes of the tiecov leg's stream (C4 whole genome: 24)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("TB_BENCH_CPU_SAMPLE", 20_000_000)),
                     help="records of the cohort fed to the CPU baseline (bounded sample)")
@@ -114,6 +118,8 @@ def host_slice_sample(host, run_off, target):
     idx = np.concatenate(idx)
     sub = {k: host[k][idx] for k in ("pos", "flag", "mapq", "strand", "nh")}
     sub["cig_off"], sub["cigar"] = sam._gather_csr(host["cig_off"], host["cigar"], idx)
+    if "md_off" in host:
+        sub["md_off"], sub["md"] = sam._gather_csr(host["md_off"], host["md"], idx)
     return sub, np.asarray(new_off, np.int64)
 
 
@@ -236,7 +242,7 @@ def main():
     if args.cov_records > 0:
         cctx = api.Context(device=local, n_samples=1)
         cctx.set_stream(stream.cuda_stream); cctx.set_profiling(True)
-        cov = synth.coverage_stream(args.cov_records, seed=rank, chroms=1, device=dev)
+        cov = synth.coverage_stream(args.cov_records, seed=rank, chroms=args.cov_chroms, device=dev)
         ncov = args.cov_records
         capr, capj = 2 * int(cov["n_cig"]) + 16, int(cov["n_cig"]) + 16
         i32 = lambda m: torch.empty(m, dtype=torch.int32, device=dev)
@@ -275,11 +281,14 @@ def main():
     n = k * reads
     # ---- synthetic cohort straight into HBM; rank r owns an independent coordinate shard (weak scaling) ----
     t_gen = time.perf_counter()
-    cols, run_off, pr = synth.cohort_window(k, reads, seed=rank, device=dev)
+    cols, run_off, pr = synth.cohort_window(k, reads, seed=rank, device=dev, with_md=(args.mode == 1), paired=(args.flag_mask != 0))
+    if args.mode == 1:
+        cols["md_off"], cols["md"], cols["n_md"] = synth.md_columns_torch(cols)
+        del cols["md_mm"], cols["md_a"]
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
     n_cig = cols["n_cig"]
-    ctx = api.Context(device=local, n_samples=k, mode=args.mode)
+    ctx = api.Context(device=local, n_samples=k, mode=args.mode, flag_mask=args.flag_mask, max_nh=args.max_nh, min_qual=args.min_qual)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_profiling(True)
     out = dict(rep_index=torch.empty(n, dtype=torch.int32, device=dev), yc=torch.empty(n, dtype=torch.float32, device=dev),
@@ -316,18 +325,25 @@ def main():
     clocks = sampler
     # ---- roofline of the dominant kernel (collapse tile kernel) ----
     cbar = n_cig / n
-    a_col = n * (30 + 4 * cbar) + 12 * G            # SURVEY §8d algorithmic bytes (default mode: m = 0)
+    mbar = (int(cols["n_md"]) / n) if (args.mode == 1 and "n_md" in cols) else 0.0
+    a_col = n * (30 + 4 * cbar + mbar) + 12 * G     # SURVEY §8d algorithmic bytes (m = mean MD bytes, -L only)
     kernel_ms = float(np.mean(kms))
+    roof_kernel = "col_tile_kernel"
+    if kernel_ms <= 0.0:   # ordered front end (-F / -A / TieBrush-made inputs / --store-frac): no tile kernel ran; quote the whole step
+        kernel_ms, roof_kernel = ms_step, "whole step (ordered front end, col_ordered_kernel dominant)"
     achieved = a_col / (kernel_ms / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "kernel": "col_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (lambda t: None if t is None else t * n)(traffic_per_record("col_tile_kernel")),
+    roofline = {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (lambda t: None if (t is None or roof_kernel != "col_tile_kernel" or args.mode != 0) else t * n)(traffic_per_record("col_tile_kernel")),
                 "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum per record at 100x2M (profiles/traffic.json) x records of this launch",
                 "peak_source": peak_src, "kernel_ms": kernel_ms, "algorithmic_bytes": a_col,
                 "layout_bytes": n * (14 + 4 * cbar) + 16 * G}
     line = {"metric": "alignments_collapsed_per_sec", "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"C2: {k} RNA-seq samples x {reads} spliced 150bp reads on chr1, tiebrush mode {args.mode} (0=default CIGAR), one window per GPU",
+            "config": {"workload": f"{'C2' if (args.mode == 0 and args.flag_mask == 0 and args.min_qual < 0 and args.max_nh == 0x7fffffff) else 'C3'}: {k} RNA-seq samples x {reads} spliced 150bp reads on chr1, tiebrush mode {args.mode} (0=default CIGAR, 1=-L, 2=-P, 3=-E)"
+                                   + (f", -N {args.max_nh}" if args.max_nh != 0x7fffffff else "") + (f", -Q {args.min_qual}" if args.min_qual >= 0 else "")
+                                   + (f", -F {args.flag_mask}" if args.flag_mask else "") + ", one window per GPU",
+                       "front_end_path": int(ctx.last_path()) if hasattr(ctx, "last_path") else None,
                        "records_per_step_per_gpu": n, "groups_out": G, "mean_cigar_ops": cbar, "l2": "inputs (>=20 GB at full size) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"coordinate shards x{world}, no data-path collective", "gen_seconds": t_gen},
             "roofline": roofline, "gpu_launches": int(launches),
@@ -340,13 +356,15 @@ def main():
     if not args.no_e2e:
         host = {}
         h2d = 0
-        for name in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar"):
+        for name in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar") + (("md_off", "md") if args.mode == 1 else ()):
             t = cols[name]
             ht = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             ht.copy_(t)
-            host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32, "flag": np.uint16, "nh": np.uint16}.get(name, ht.numpy().dtype))
+            host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32, "md_off": np.uint32, "flag": np.uint16, "nh": np.uint16}.get(name, ht.numpy().dtype))
             h2d += ht.numel() * ht.element_size()
         host["n_cig"] = n_cig
+        if args.mode == 1:
+            host["n_md"] = int(cols["n_md"])
         # the device-resident copy is not needed any more: the host path stages its own (full size: 25 GB each)
         del cols, out, res
         torch.cuda.empty_cache()
@@ -378,7 +396,7 @@ def main():
     # ---- CPU baseline: the oracle port on a bounded coordinate slice of the same window (rank 0, N=1 only) ----
     if rank == 0 and world == 1 and args.cpu_sample > 0:
         from oracle import oracle
-        hostc = host if host is not None else synth.to_host({kk: cols[kk] for kk in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar")})
+        hostc = host if host is not None else synth.to_host({kk: cols[kk] for kk in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar") + (("md_off", "md") if args.mode == 1 else ())})
         sub, sub_off = host_slice_sample(hostc, run_off, args.cpu_sample)
         t0 = time.perf_counter()
         ro = oracle.collapse(sub, sub_off, mode=args.mode)

@@ -119,10 +119,11 @@ struct TileSmem {
   uint32_t* soff;             // [k+1] exclusive prefix of slice lengths
   uint16_t* rbase;            // [E]  region base of the entry's position (segment id in the epilogue)
   uint16_t* occ;              // [E]  compacted entry indices
+  uint16_t* tmp;              // [E]  epilogue: rank inside the position (bits 0-12) | saturated key (14) | tied (15)
 };
 
 static size_t tile_smem_bytes(uint32_t k, uint32_t E, uint32_t W) {
-  return (size_t)E * (8 + 8 + 4 + 4 * (size_t)W + 2 + 2) + (size_t)(6 * k + 1) * 4 + 64;
+  return (size_t)E * (8 + 8 + 4 + 4 * (size_t)W + 2 + 2 + 2) + (size_t)(6 * k + 1) * 4 + 64;
 }
 
 // 64-bit epilogue sort key: strand(2) | ref_len(30) | key length(8, saturated) | first key word, byte order of memcmp (24).
@@ -150,15 +151,72 @@ __device__ unsigned long long tile_sort_key(const ColIn& in, uint32_t o, unsigne
   return ((unsigned long long)sc << 62) | ((unsigned long long)(reflen & 0x3fffffffu) << 32) | ((unsigned long long)len8 << 24) | w24;
 }
 
+// Bytes [off, off+6) of the comparison string that FOLLOWS the 64-bit sort key, big-endian in the low 48 bits (zero beyond
+// its end). The string continues the reference's order exactly: default / -P / -L: the rest of the memcmp over the raw
+// little-endian CIGAR words (byte 3 of the first word onwards; equal n_cigar is part of the key), then for -L the MD tag as
+// one presence byte (absent < present, cmpFull :298-302) and its characters (strcmp); -E: the exon coordinates as big-endian
+// integers (first exon end, then start,end of every later exon; equal exon count is part of the key).
+__device__ __noinline__ unsigned long long tile_tail_chunk(const ColIn& in, uint32_t o, uint32_t off) {
+  const uint32_t c0 = in.cig_off[o], c1 = in.cig_off[o + 1];
+  unsigned long long v = 0;
+  if (in.mode == TB_MODE_EXON) {
+    const uint32_t first = off >> 2, last = (off + 5) >> 2;   // integers of the stream touched by the chunk: first..last (<= first+2)
+    uint32_t vals[3] = {0u, 0u, 0u};
+    ExonIter it; it.init(in.cigar, c0, c1, in.pos[o]);
+    int sx, ex; uint32_t j = 0;
+    while (it.next(sx, ex)) {   // exon j holds stream integers 2j-1 (start, j > 0) and 2j (end)
+      if (j > 0 && 2 * j - 1 >= first && 2 * j - 1 <= first + 2) vals[2 * j - 1 - first] = (uint32_t)sx;
+      if (2 * j >= first && 2 * j <= first + 2) vals[2 * j - first] = (uint32_t)ex;
+      if (2 * j >= last) break;
+      ++j;
+    }
+#pragma unroll
+    for (uint32_t bi = 0; bi < 6; ++bi) {
+      const uint32_t t = off + bi;
+      v = (v << 8) | ((vals[(t >> 2) - first] >> ((3u - (t & 3u)) * 8u)) & 0xffu);
+    }
+    return v;
+  }
+  uint32_t a = c0, b = c1;
+  if (in.mode == TB_MODE_CLIP) tb_clip_range(in.cigar, a, b);
+  const uint32_t nc = b - a, ncb = nc ? 4u * nc - 3u : 0u;   // CIGAR bytes after the three the sort key holds
+  uint32_t m0 = 0, m1 = 0;
+  if (in.mode == TB_MODE_FULL) { m0 = in.md_off[o]; m1 = in.md_off[o + 1]; }
+  for (uint32_t bi = 0; bi < 6; ++bi) {
+    const uint32_t t = off + bi;
+    uint32_t byte = 0;
+    if (t < ncb) { const uint32_t g = t + 3u; byte = (in.cigar[a + (g >> 2)] >> ((g & 3u) * 8u)) & 0xffu; }
+    else if (in.mode == TB_MODE_FULL && m1 > m0) {
+      const uint32_t u = t - ncb;
+      if (u == 0) byte = 1u;
+      else if (m0 + u - 1u < m1) byte = in.md[m0 + u - 1u];
+    }
+    v = (v << 8) | byte;
+  }
+  return v;
+}
+
 // is record i (own CIGAR range [c0,c1)) the same alignment as the table owner o? Same position by construction, same
-// strand by the tag. The default mode is compared inline; the other modes go through the general comparator.
+// strand by the tag. Identical raw CIGARs decide every mode but -L at once (identical CIGAR at one position => identical
+// clipped CIGAR and identical exon chain); -L then compares the MD bytes inline. Only records whose raw CIGARs differ
+// (or whose MD lengths differ) go through the general comparator, which is exact for every mode.
 __device__ __forceinline__ bool tile_same_key(const ColIn& in, uint32_t i, uint32_t c0, uint32_t c1, uint32_t o) {
-  if (in.mode != TB_MODE_CIGAR) return tb_mode_cmp(in, i, o) == 0;
   const uint32_t o0 = in.cig_off[o], o1 = in.cig_off[o + 1];
   const uint32_t nc = c1 - c0;
-  if (o1 - o0 != nc) return false;
-  for (uint32_t q = 0; q < nc; ++q) if (in.cigar[c0 + q] != in.cigar[o0 + q]) return false;
-  return true;
+  bool same_cigar = (o1 - o0 == nc);
+  if (same_cigar)
+    for (uint32_t q = 0; q < nc; ++q) if (in.cigar[c0 + q] != in.cigar[o0 + q]) { same_cigar = false; break; }
+  if (in.mode == TB_MODE_CIGAR) return same_cigar;
+  if (same_cigar) {
+    if (in.mode != TB_MODE_FULL) return true;
+    const uint32_t ma = in.md_off[i], na = in.md_off[i + 1] - ma, mb = in.md_off[o], nb = in.md_off[o + 1] - mb;
+    if (na == nb) {
+      bool eq = true;
+      for (uint32_t q = 0; q < na; ++q) if (in.md[ma + q] != in.md[mb + q]) { eq = false; break; }
+      if (eq) return true;
+    }
+  }
+  return tb_mode_cmp(in, i, o) == 0;
 }
 
 template <int THREADS>
@@ -319,26 +377,65 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
     sm.rep[e] = ((unsigned long long)o << 32) | (uint32_t)sm.rep[e];
   }
   __syncthreads();
-  // ---- epilogue C: rank inside the position (one walk to the left, one to the right), write in final order ----
+  // ---- epilogue C: rank inside the position. Ranks come from the 64-bit keys in shared memory; groups whose keys tie are
+  // refined by re-keying with (rank so far, next 6 bytes of the comparison string) — one global read per tied group and
+  // round instead of one comparator call per tied PAIR (a pile-up position in -L mode holds hundreds of groups that differ
+  // only in MD) — and only what still ties after TILE_REFINE rounds goes through the general comparator ----
+  constexpr int TILE_REFINE = 6;
+  for (int round = 0;; ++round) {
+    int any_tie = 0;
+    for (uint32_t r = tid; r < G; r += THREADS) {
+      const uint32_t e = sm.occ[r];
+      const uint16_t rb = sm.rbase[e];
+      const unsigned long long ki = sm.word[e];
+      uint32_t rank = 0, ties = 0;
+      for (uint32_t q = r; q > 0;) {
+        const uint32_t eq = sm.occ[--q];
+        if (!single && sm.rbase[eq] != rb) break;
+        const unsigned long long kq = sm.word[eq];
+        rank += kq < ki; ties += kq == ki;
+      }
+      for (uint32_t q = r + 1; q < G; ++q) {
+        const uint32_t eq = sm.occ[q];
+        if (!single && sm.rbase[eq] != rb) break;
+        const unsigned long long kq = sm.word[eq];
+        rank += kq < ki; ties += kq == ki;
+      }
+      uint16_t sat = round == 0 ? ((((uint32_t)(ki >> 24) & 0xffu) == 255u) ? 0x4000u : 0u) : (sm.tmp[e] & 0x4000u);
+      sm.tmp[e] = (uint16_t)(rank | sat | (ties ? 0x8000u : 0u));
+      any_tie |= (ties != 0 && !sat);
+    }
+    if (round >= TILE_REFINE || in.mode == TB_MODE_CIGAR) { __syncthreads(); break; }   // default mode: ties are rare, one round
+    if (!__syncthreads_or(any_tie)) break;
+    for (uint32_t r = tid; r < G; r += THREADS) {
+      const uint32_t e = sm.occ[r];
+      const uint32_t t = sm.tmp[e];
+      unsigned long long chunk = 0;
+      if ((t & 0xC000u) == 0x8000u) chunk = tile_tail_chunk(in, (uint32_t)(sm.rep[e] >> 32), (uint32_t)round * 6u);
+      sm.word[e] = ((unsigned long long)(t & 0x1fffu) << 48) | chunk;
+    }
+    __syncthreads();
+  }
   for (uint32_t r = tid; r < G; r += THREADS) {
     const uint32_t e = sm.occ[r];
     const uint16_t rb = sm.rbase[e];
+    const uint32_t t = sm.tmp[e];
+    uint32_t rank = t & 0x1fffu, a = r;
+    const bool tied = (t & 0x8000u) != 0;
     const unsigned long long ki = sm.word[e];
     const uint32_t oi = (uint32_t)(sm.rep[e] >> 32);
-    uint32_t rank = 0, a = r;
     while (a > 0) {
       const uint32_t eq = sm.occ[a - 1];
       if (!single && sm.rbase[eq] != rb) break;
       --a;
-      const unsigned long long kq = sm.word[eq];
-      if (kq < ki || (kq == ki && tb_mode_cmp(in, (uint32_t)(sm.rep[eq] >> 32), oi) < 0)) ++rank;
+      if (tied && sm.word[eq] == ki && tb_mode_cmp(in, (uint32_t)(sm.rep[eq] >> 32), oi) < 0) ++rank;
     }
-    for (uint32_t q = r + 1; q < G; ++q) {
-      const uint32_t eq = sm.occ[q];
-      if (!single && sm.rbase[eq] != rb) break;
-      const unsigned long long kq = sm.word[eq];
-      if (kq < ki || (kq == ki && tb_mode_cmp(in, (uint32_t)(sm.rep[eq] >> 32), oi) < 0)) ++rank;
-    }
+    if (tied)
+      for (uint32_t q = r + 1; q < G; ++q) {
+        const uint32_t eq = sm.occ[q];
+        if (!single && sm.rbase[eq] != rb) break;
+        if (sm.word[eq] == ki && tb_mode_cmp(in, (uint32_t)(sm.rep[eq] >> 32), oi) < 0) ++rank;
+      }
     const uint64_t o = outbase + a + rank;
     tp.st_rep[o] = (uint32_t)sm.rep[e];
     tp.st_yc[o] = (float)sm.cnt[e];
@@ -370,6 +467,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) col_tile_kernel(ColIn
   sm.soff = sm.c + k;
   sm.rbase = (uint16_t*)(sm.soff + k + 1);
   sm.occ = sm.rbase + E;
+  sm.tmp = sm.occ + E;
   uint32_t kept_total = 0;   // thread 0 only
   auto fetch_meta = [&](SlotMeta& d) {   // one thread: claim the next slot and read its geometry
     SlotMeta t; t.m = atomicAdd(tp.slot_counter, 1u); t.rank0 = t.rank1 = t.p0 = t.p1 = 0;

@@ -112,7 +112,14 @@ __device__ __forceinline__ void tb_parse_record32(const ColIn& in, int64_t i, in
     if (in.mode == TB_MODE_FULL) {
       const uint32_t m0 = in.md_off[i], m1 = in.md_off[i + 1];
       tb_fold2(h1, h2, (uint32_t)(m1 > m0));
-      for (uint32_t q = m0; q < m1; ++q) { const uint8_t ch = in.md[q]; if (ch == 0) break; tb_fold2(h1, h2, ch); }
+      uint32_t acc = 0, nb = 0;   // bytes up to the NUL, four per fold
+      for (uint32_t q = m0; q < m1; ++q) {
+        const uint32_t ch = in.md[q];
+        if (ch == 0) break;
+        acc = (acc << 8) | ch;
+        if (++nb == 4) { tb_fold2(h1, h2, acc); acc = 0; nb = 0; }
+      }
+      tb_fold2(h1, h2, acc ^ (nb << 29));
     }
   }
   reflen = l; h1o = h1; h2o = h2;

@@ -158,6 +158,44 @@ def md_columns(cols):
     return off, np.frombuffer(b"".join(strs), np.uint8).copy()
 
 
+def md_columns_torch(cols, chunk=32_000_000):
+    """Same arena as md_columns, vectorised on the columns' device (bench sizes): returns (md_off u32-as-int32 [n+1], md u8, n_md)."""
+    mm_all, a_all = cols["md_mm"], cols["md_a"]
+    dev = mm_all.device
+    n = mm_all.numel()
+    lens_parts, byte_parts = [], []
+
+    def digits(x):   # left-aligned decimal digits of 0..199: ([m,3] uint8 chars, [m] lengths)
+        d = torch.stack([x // 100, (x // 10) % 10, x % 10], 1)
+        ln = 1 + (x >= 10).to(torch.int64) + (x >= 100).to(torch.int64)
+        shift = 3 - ln
+        idx = (torch.arange(3, device=dev)[None, :] + shift[:, None]).clamp_(max=2)
+        return (torch.gather(d, 1, idx) + 48).to(torch.uint8), ln
+
+    for c0 in range(0, n, chunk):
+        mm = mm_all[c0:c0 + chunk].to(torch.bool); a = a_all[c0:c0 + chunk].to(torch.int64)
+        m = a.numel()
+        da, la = digits(a); db, lb = digits(149 - a)
+        row = torch.zeros((m, 8), dtype=torch.uint8, device=dev)
+        col = torch.arange(8, device=dev)[None, :]
+        # mismatch rows: <a> T <149-a> NUL
+        for j in range(3):
+            row = torch.where((col == j) & (j < la)[:, None], da[:, j:j + 1], row)
+            row = torch.where((col == (la + 1 + j)[:, None]) & (j < lb)[:, None], db[:, j:j + 1], row)
+        row = torch.where(col == la[:, None], torch.full_like(row, 84), row)   # 'T'
+        ln = la + 1 + lb + 1
+        plain = torch.tensor([49, 53, 48, 0, 0, 0, 0, 0], dtype=torch.uint8, device=dev)   # "150\0"
+        row = torch.where(mm[:, None], row, plain[None, :].expand(m, 8))
+        ln = torch.where(mm, ln, torch.full_like(ln, 4))
+        byte_parts.append(row[col < ln[:, None]])
+        lens_parts.append(ln)
+    lens = torch.cat(lens_parts)
+    off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    off[1:] = torch.cumsum(lens, 0)
+    md = torch.cat(byte_parts)
+    return off.to(torch.int32), md, int(off[-1])
+
+
 def _cat_csr(parts, key_off="cig_off", key_arena="cigar"):
     offs, base = [torch.zeros(1, dtype=torch.int64, device=parts[0][key_off].device)], 0
     for p in parts:
