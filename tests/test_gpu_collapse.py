@@ -220,3 +220,64 @@ def test_collapse_device_resident_properties():
     exp = oracle.collapse(host, run_off)
     assert np.array_equal(rep, exp["rep_index"]) and np.array_equal(yc, exp["yc"]) and np.array_equal(yx, exp["yx"])
     assert np.array_equal(got["yd"].cpu().numpy(), exp["yd"])
+
+
+def _device_prefix_slice(cols, run_off, hi):
+    """Records of every file with pos < hi (a coordinate prefix of the window), gathered on the device, returned as host columns."""
+    import torch
+    dev = cols["pos"].device
+    parts, new_off = [], [0]
+    for f in range(len(run_off) - 1):
+        a, b = int(run_off[f]), int(run_off[f + 1])
+        c = a + int(torch.searchsorted(cols["pos"][a:b], torch.tensor([hi], device=dev, dtype=cols["pos"].dtype))[0])
+        parts.append(torch.arange(a, c, device=dev))
+        new_off.append(new_off[-1] + (c - a))
+    idx = torch.cat(parts)
+    sub = {k: cols[k][idx].cpu().numpy() for k in ("pos", "flag", "mapq", "strand", "nh")}
+    sub["flag"] = sub["flag"].view(np.uint16); sub["nh"] = sub["nh"].view(np.uint16)
+    c0 = cols["cig_off"][idx].long() & 0xffffffff
+    ln = (cols["cig_off"][idx + 1].long() & 0xffffffff) - c0
+    off = torch.zeros(len(idx) + 1, dtype=torch.long, device=dev); off[1:] = torch.cumsum(ln, 0)
+    rep = torch.repeat_interleave(torch.arange(len(idx), device=dev), ln)
+    src = c0[rep] + (torch.arange(int(off[-1]), device=dev) - off[:-1][rep])
+    sub["cigar"] = cols["cigar"][src].cpu().numpy().view(np.uint32)
+    sub["cig_off"] = off.cpu().numpy().astype(np.uint32)
+    return sub, np.asarray(new_off, np.int64), idx
+
+
+def test_collapse_baseline_size_properties_and_oracle_prefix():
+    """BASELINE C2 shape (100 samples on chr1, default mode) resident in HBM at the FULL configured size, 100 x 10M reads =
+    1e9 alignments (about 11 s on a B200; TB_TEST_FULL=0 shrinks it to 100 x 2M). Size-independent properties over the whole output (sum YC == records, YX bounds,
+    representatives in position order and inside their own position, YD >= 0) and bit-exact equality with the oracle
+    on a coordinate prefix of the same window (a prefix needs no state from the rest: groups and YD only look left)."""
+    import os
+    import torch
+    from oracle import oracle
+    from tiebrush_b200 import api, synth
+    k = 100
+    reads = 2_000_000 if os.environ.get("TB_TEST_FULL") == "0" else 10_000_000
+    cols, run_off, pr = synth.cohort_window(k, reads, seed=0, device="cuda")
+    n = k * reads
+    out = dict(rep_index=torch.empty(n, dtype=torch.int32, device="cuda"), yc=torch.empty(n, dtype=torch.float32, device="cuda"),
+               yx=torch.empty(n, dtype=torch.int32, device="cuda"), yd=torch.empty(n, dtype=torch.int32, device="cuda"))
+    with api.Context(device=0, n_samples=k) as ctx:
+        got = ctx.collapse_window(cols, run_off, pos_range=pr, out=out)
+        assert ctx.last_path() == 0 and ctx.last_yd_path() == 0
+    G = got["n_groups"]
+    rep = out["rep_index"][:G].long() & 0xffffffff
+    yc, yx, yd = out["yc"][:G], out["yx"][:G], out["yd"][:G]
+    assert got["n_kept"] == n
+    assert int(yc.to(torch.float64).sum().item()) == n
+    assert bool((yx >= 1).all()) and bool((yx.to(torch.float32) <= torch.clamp(yc, max=float(k))).all()) and bool((yd >= 0).all())
+    rpos = cols["pos"][rep]
+    assert bool((rpos[1:] >= rpos[:-1]).all())
+    # oracle on a prefix of ~2M records
+    first = cols["pos"][: reads]
+    hi = int(first[min(reads - 1, max(1, (2_000_000 // k)))].item())
+    sub, sub_off, idx = _device_prefix_slice(cols, run_off, hi)
+    exp = oracle.collapse(sub, sub_off)
+    Gs = len(exp["rep_index"])
+    assert Gs > 1000 and bool((rpos[:Gs] < hi).all()) and (G == Gs or int(rpos[Gs].item()) >= hi)
+    assert np.array_equal(idx[torch.as_tensor(exp["rep_index"].astype(np.int64), device="cuda")].cpu().numpy(), rep[:Gs].cpu().numpy())
+    assert np.array_equal(yc[:Gs].cpu().numpy(), exp["yc"]) and np.array_equal(yx[:Gs].cpu().numpy().view(np.uint32), exp["yx"])
+    assert np.array_equal(yd[:Gs].cpu().numpy(), exp["yd"])

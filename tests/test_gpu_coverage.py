@@ -82,3 +82,51 @@ def test_coverage_device_resident_large_random(ctx):
         assert np.array_equal(np.asarray(a), b)
     for a, b in zip(got["juncs"], exp["juncs"]):
         assert np.array_equal(np.asarray(a), b)
+
+
+def test_coverage_c4_scale_properties_and_oracle_prefix():
+    """BASELINE C4 shape: a whole-genome (24 chromosomes) collapsed stream resident in HBM, 2e8 records in one window
+    (TB_TEST_FULL=0: 2e7). Size-independent properties over the whole output — the covered weight sum(YC x M bases) is
+    conserved by the runs, runs are sorted / disjoint / non-zero, junction rows are sorted and positive — and bit-exact
+    equality with the oracle on a whole-bundle prefix of the same stream."""
+    import os
+    import torch
+    from oracle import oracle
+    from tiebrush_b200 import api, synth
+    n = 20_000_000 if os.environ.get("TB_TEST_FULL") == "0" else 200_000_000
+    cols = synth.coverage_stream(n, seed=3, chroms=24, device="cuda")
+    with api.Context(device=0, n_samples=1) as c4:
+        out = c4.coverage_window(cols)
+        t, s, e, v = out["runs"]
+        assert out["n_runs"] > 1000 and bool((v != 0).all()) and bool((e > s).all())
+        same = t[1:] == t[:-1]
+        assert bool((t[1:] >= t[:-1]).all()) and bool((s[1:][same] >= e[:-1][same]).all())
+        total = float(((e - s).to(torch.float64) * v).sum().item())
+        # covered weight on the device: per-record M bases (segment sum over the CIGAR arena) x YC
+        cig = cols["cigar"].to(torch.int64) & 0xFFFFFFFF
+        mlen = (cig >> 4) * ((cig & 0xF) == 0)
+        cs = torch.zeros(mlen.numel() + 1, dtype=torch.int64, device="cuda"); cs[1:] = torch.cumsum(mlen, 0)
+        off = cols["cig_off"].to(torch.int64) & 0xFFFFFFFF
+        per_rec = cs[off[1:]] - cs[off[:-1]]
+        assert total == float((per_rec.to(torch.float64) * cols["yc"].to(torch.float64)).sum().item())
+        jt, js, je, jstrand, jv = out["juncs"]
+        assert out["n_juncs"] > 100 and bool((jv > 0).all()) and bool((je >= js).all())
+        sj = jt[1:] == jt[:-1]
+        assert bool((jt[1:] >= jt[:-1]).all()) and bool((js[1:][sj] >= js[:-1][sj]).all())
+        # oracle on a whole-bundle prefix (first bundle boundary after 200k records)
+        H = 4_000_000
+        head = {k: cols[k][:H].cpu() for k in ("tid", "pos", "yc", "strand")}
+        head["cig_off"] = cols["cig_off"][:H + 1].cpu(); head["cigar"] = cols["cigar"][: int(off[H].item())].cpu()
+        host = synth.to_host(head)
+        cut = synth.bundle_cut(host, 200_000)
+        assert cut < H
+        sub = synth.take_prefix(host, cut)
+        exp = oracle.coverage(sub)
+        nr, nj = len(exp["runs"][0]), len(exp["juncs"][0])
+        for a, b in zip(out["runs"], exp["runs"]):
+            assert np.array_equal(a[:nr].cpu().numpy(), b)
+        # junction rows of the prefix: same (tid,start,end,strand,value) multiset restricted to the prefix's coordinates
+        got = c4.coverage_window(sub)
+        for a, b in zip(got["juncs"], exp["juncs"]):
+            assert np.array_equal(np.asarray(a), b)
+        assert nj > 0
