@@ -356,40 +356,53 @@ def main():
     if not args.no_e2e:
         host = {}
         h2d = 0
-        for name in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar") + (("md_off", "md") if args.mode == 1 else ()):
-            t = cols[name]
-            ht = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            ht.copy_(t)
-            host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32, "md_off": np.uint32, "flag": np.uint16, "nh": np.uint16}.get(name, ht.numpy().dtype))
-            h2d += ht.numel() * ht.element_size()
-        host["n_cig"] = n_cig
-        if args.mode == 1:
-            host["n_md"] = int(cols["n_md"])
-        # the device-resident copy is not needed any more: the host path stages its own (full size: 25 GB each)
-        del cols, out, res
-        torch.cuda.empty_cache()
-        cap = max(G + 1024, 1)
-        hout_t = dict(rep_index=torch.empty(cap, dtype=torch.int32, pin_memory=True), yc=torch.empty(cap, dtype=torch.float32, pin_memory=True),
-                      yx=torch.empty(cap, dtype=torch.int32, pin_memory=True), yd=torch.empty(cap, dtype=torch.int32, pin_memory=True))
-        hout = {kk: v.numpy().view(np.uint32) if kk in ("rep_index", "yx") else v.numpy() for kk, v in hout_t.items()}
-        es = max(1, min(args.steps, 3))
-        ctx.collapse_window(host, run_off, pos_range=pr, out=hout)  # warm the staging buffers
-        barrier()
-        t0 = time.perf_counter()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            g0.record(stream)
-            for _ in range(es):
-                r2 = ctx.collapse_window(host, run_off, pos_range=pr, out=hout)
-            g1.record(stream)
-        barrier()
-        e2e_ms = g0.elapsed_time(g1) / es
+        ok = 1
+        try:   # pinned host copies of every input column (25 GB per rank at full size): all ranks must succeed, or all skip
+            for name in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar") + (("md_off", "md") if args.mode == 1 else ()):
+                t = cols[name]
+                ht = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                ht.copy_(t)
+                host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32, "md_off": np.uint32, "flag": np.uint16, "nh": np.uint16}.get(name, ht.numpy().dtype))
+                h2d += ht.numel() * ht.element_size()
+            cap = max(G + 1024, 1)
+            hout_t = dict(rep_index=torch.empty(cap, dtype=torch.int32, pin_memory=True), yc=torch.empty(cap, dtype=torch.float32, pin_memory=True),
+                          yx=torch.empty(cap, dtype=torch.int32, pin_memory=True), yd=torch.empty(cap, dtype=torch.int32, pin_memory=True))
+        except (RuntimeError, MemoryError) as ex:
+            ok = 0
+            e2e_err = str(ex)[:200]
         if world > 1:
-            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
-        line["e2e"] = {"value": world * n / (e2e_ms / 1000.0), "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(16 * r2["n_groups"] + 128),
-                       "ms_per_step": e2e_ms, "steps": es, "wall_ms_per_step": 1000.0 * (time.perf_counter() - t0) / es}
+            t = torch.tensor([ok], device=dev, dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = int(t.item())
+        if not ok:
+            host = None
+            line["e2e"] = {"unavailable": "pinned host buffers for the end-to-end leg could not be allocated on every rank"}
+        else:
+            host["n_cig"] = n_cig
+            if args.mode == 1:
+                host["n_md"] = int(cols["n_md"])
+            # the device-resident copy is not needed any more: the host path stages its own (full size: 25 GB each)
+            del cols, out, res
+            torch.cuda.empty_cache()
+            hout = {kk: v.numpy().view(np.uint32) if kk in ("rep_index", "yx") else v.numpy() for kk, v in hout_t.items()}
+            es = max(1, min(args.steps, 3))
+            ctx.collapse_window(host, run_off, pos_range=pr, out=hout)  # warm the staging buffers
+            barrier()
+            t0 = time.perf_counter()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                g0.record(stream)
+                for _ in range(es):
+                    r2 = ctx.collapse_window(host, run_off, pos_range=pr, out=hout)
+                g1.record(stream)
+            barrier()
+            e2e_ms = g0.elapsed_time(g1) / es
+            if world > 1:
+                t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_ms = float(t.item())
+            line["e2e"] = {"value": world * n / (e2e_ms / 1000.0), "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(16 * r2["n_groups"] + 128),
+                           "ms_per_step": e2e_ms, "steps": es, "wall_ms_per_step": 1000.0 * (time.perf_counter() - t0) / es}
     sampler.stop_flag.set(); sampler.join(timeout=3)
     line["clocks"] = clocks.summary()
 
