@@ -219,10 +219,14 @@ __device__ __forceinline__ bool tile_same_key(const ColIn& in, uint32_t i, uint3
   return tb_mode_cmp(in, i, o) == 0;
 }
 
-template <int THREADS>
-__device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem<THREADS>& sm, uint32_t n_sub, uint32_t rankbase, bool single,
+// MODE >= 0 fixes the merge strategy at compile time (the default CIGAR mode gets its own instantiation: every mode branch
+// of the record parser / verifier / sort key folds away); MODE < 0 reads it from the window descriptor.
+template <int THREADS, int MODE>
+__device__ uint32_t tile_process(const ColIn& in_, const TileParams& tp, TileSmem<THREADS>& sm, uint32_t n_sub, uint32_t rankbase, bool single,
                                  uint64_t outbase, uint32_t* s_scan, volatile uint32_t* s_flags /*[0]=kept [1]=overflow [2]=ngroups*/) {
   constexpr int NW = THREADS / 32;
+  ColIn in = in_;
+  if (MODE >= 0) in.mode = MODE;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t E = tp.ecap, W = tp.W, k = (uint32_t)in.k;
   // ---- exclusive prefix of the slice lengths ----
@@ -357,15 +361,28 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
   __syncthreads();
   if (s_flags[1]) return 0xffffffffu;   // block-uniform: table overflow (single-position mode only)
 
-  // ---- epilogue A: compact the occupied entries in region (= position) order ----
+  // ---- epilogue A: compact the occupied entries in region (= position) order. Each warp owns a contiguous chunk of the
+  // table: ballot counts, one block-wide scan of the NW warp totals, ballot ranks (two barriers per sub-tile) ----
   uint32_t G = 0;
-  for (uint32_t base = 0; base < E_used; base += THREADS) {
-    const uint32_t e = base + tid;
-    const uint32_t occf = (e < E_used && sm.word[e] != EMPTY64) ? 1u : 0u;
+  {
+    const uint32_t chunk = (((E_used + NW - 1) / NW) + 31u) & ~31u;
+    const uint32_t e0 = warp * chunk, e1 = min(E_used, e0 + chunk);
+    uint32_t mine = 0;
+    for (uint32_t eb = e0; eb < e1; eb += 32) {
+      const uint32_t e = eb + lane;
+      mine += __popc(__ballot_sync(0xffffffffu, e < e1 && sm.word[e] != EMPTY64));
+    }
     uint32_t tot;
-    const uint32_t exc = tb_block_exscan<OpSumU32>(occf, s_scan, &tot);
-    if (occf) sm.occ[G + exc] = (uint16_t)e;
-    G += tot;
+    uint32_t base = tb_block_exscan<OpSumU32>(lane == 0 ? mine : 0u, s_scan, &tot);   // lane 0 of warp w: entries before the warp's chunk
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t eb = e0; eb < e1; eb += 32) {
+      const uint32_t e = eb + lane;
+      const bool occf = e < e1 && sm.word[e] != EMPTY64;
+      const unsigned bal = __ballot_sync(0xffffffffu, occf);
+      if (occf) sm.occ[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
+      base += __popc(bal);
+    }
+    G = tot;
   }
   __syncthreads();
   // ---- epilogue B: sort keys ----
@@ -449,7 +466,7 @@ __device__ uint32_t tile_process(const ColIn& in, const TileParams& tp, TileSmem
 // slot descriptor handed from the prefetching thread to the block
 struct SlotMeta { uint32_t m, rank0, rank1, p0, p1; };
 
-template <int THREADS>
+template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) col_tile_kernel(ColIn in, TileParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_scan[33];
@@ -495,7 +512,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) col_tile_kernel(ColIn
     uint32_t G = 0, kept_slot = 0;   // kept_slot: thread 0 only
     bool overflow = false;
     if (n_t <= tp.cap_records) {
-      G = tile_process<THREADS>(in, tp, sm, n_t, rank0, false, rank0, s_scan, s_flags);
+      G = tile_process<THREADS, MODE>(in, tp, sm, n_t, rank0, false, rank0, s_scan, s_flags);
       overflow = G == 0xffffffffu;
       if (tid == 0) kept_slot = s_flags[0];
     } else {
@@ -517,7 +534,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) col_tile_kernel(ColIn
       __syncthreads();
       uint32_t G1 = 0;
       if (rb > rank0) {
-        G1 = tile_process<THREADS>(in, tp, sm, rb - rank0, rank0, false, rank0, s_scan, s_flags);
+        G1 = tile_process<THREADS, MODE>(in, tp, sm, rb - rank0, rank0, false, rank0, s_scan, s_flags);
         overflow = G1 == 0xffffffffu;
         if (tid == 0) kept_slot = s_flags[0];
       }
@@ -525,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) col_tile_kernel(ColIn
         __syncthreads();
         for (uint32_t f = tid; f < k; f += THREADS) { sm.a[f] = sm.b[f]; sm.b[f] = sm.c[f]; }
         __syncthreads();
-        const uint32_t G2 = tile_process<THREADS>(in, tp, sm, rank1 - rb, rb, true, (uint64_t)rank0 + G1, s_scan, s_flags);
+        const uint32_t G2 = tile_process<THREADS, MODE>(in, tp, sm, rank1 - rb, rb, true, (uint64_t)rank0 + G1, s_scan, s_flags);
         overflow = G2 == 0xffffffffu;
         if (tid == 0) kept_slot += s_flags[0];
         G = G1 + G2;
@@ -639,16 +656,16 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
     const unsigned grid = nslots < want ? nslots : want;
     cudaError_t e = cudaMemsetAsync(t.slot_counter, 0, 64, st);
     if (e != cudaSuccess) return e;
-    if (thr == 1024) {
-      if ((e = cudaFuncSetAttribute(col_tile_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-      col_tile_kernel<1024><<<grid, 1024, smem, st>>>(in, t);
-    } else if (thr == 512) {
-      if ((e = cudaFuncSetAttribute(col_tile_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-      col_tile_kernel<512><<<grid, 512, smem, st>>>(in, t);
-    } else {
-      if ((e = cudaFuncSetAttribute(col_tile_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-      col_tile_kernel<256><<<grid, 256, smem, st>>>(in, t);
-    }
+#define TB_TILE_LAUNCH(T, M)                                                                                                     \
+  do {                                                                                                                           \
+    if ((e = cudaFuncSetAttribute(col_tile_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e; \
+    col_tile_kernel<T, M><<<grid, T, smem, st>>>(in, t);                                                                        \
+  } while (0)
+    const bool dflt = in.mode == TB_MODE_CIGAR;
+    if (thr == 1024) { if (dflt) TB_TILE_LAUNCH(1024, TB_MODE_CIGAR); else TB_TILE_LAUNCH(1024, -1); }
+    else if (thr == 512) { if (dflt) TB_TILE_LAUNCH(512, TB_MODE_CIGAR); else TB_TILE_LAUNCH(512, -1); }
+    else { if (dflt) TB_TILE_LAUNCH(256, TB_MODE_CIGAR); else TB_TILE_LAUNCH(256, -1); }
+#undef TB_TILE_LAUNCH
     ctx->launches++;
     return cudaGetLastError();
   };
