@@ -43,9 +43,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("TB_BENCH_CPU_SAMPLE", 20_000_000)),
                     help="records of the cohort fed to the CPU baseline (bounded sample)")
-    ap.add_argument("--cli-reads", type=int, default=int(os.environ.get("TB_BENCH_CLI_READS", 20_000)),
+    ap.add_argument("--cli-reads", type=int, default=int(os.environ.get("TB_BENCH_CLI_READS", 50_000)),
                     help="reads per sample file of the host command-line leg (0 = skip)")
-    ap.add_argument("--ref-reads", type=int, default=int(os.environ.get("TB_BENCH_REF_READS", 20_000)),
+    ap.add_argument("--ref-reads", type=int, default=int(os.environ.get("TB_BENCH_REF_READS", 50_000)),
                     help="--impl reference: reads per sample file written as SAM for the reference binary")
     return ap.parse_args()
 

@@ -41,7 +41,7 @@ def yd_path(request, monkeypatch):
 
 
 @pytest.mark.parametrize("mode", [0, 2, 3])
-@pytest.mark.parametrize("n_tx,k,reads", [(40, 12, 20000), (2000, 40, 5000), (3, 5, 30000)])
+@pytest.mark.parametrize("n_tx,k,reads", [(40, 12, 20000), (2000, 40, 5000), (3, 5, 30000), (150, 1000, 300)])
 def test_collapse_synthetic_vs_oracle(mode, n_tx, k, reads, yd_path):
     """Seeded synthetic cohorts (deep pile-ups when n_tx is tiny) against the oracle, bit for bit."""
     from oracle import oracle

@@ -602,7 +602,7 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
   // ---- geometry: CTAs of `threads` threads, 1024/threads of them per SM, each with an equal share of the opt-in
   // shared memory for its table (TB_TILE_THREADS=256|512|1024 overrides the default for experiments) ----
   int threads = TILE_THREADS_DEFAULT;
-  if (const char* e = getenv("TB_TILE_THREADS")) { const int t = atoi(e); if (t == 256 || t == 512 || t == 1024) threads = t; }
+  if (const char* e = getenv("TB_TILE_THREADS")) { const int t = atoi(e); if (t == 128 || t == 256 || t == 512 || t == 1024) threads = t; }
   const int ctas_per_sm = 1024 / threads;
   const size_t smem_sm = ctx->smem_optin ? ctx->smem_optin + 1024 : 233472;   // shared memory per SM (opt-in per block + 1 KB reserved)
   const size_t smem_limit = smem_sm / ctas_per_sm - 1024 - 512;               // per CTA: minus the reserved KB and the static part
@@ -664,6 +664,7 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
     const bool dflt = in.mode == TB_MODE_CIGAR;
     if (thr == 1024) { if (dflt) TB_TILE_LAUNCH(1024, TB_MODE_CIGAR); else TB_TILE_LAUNCH(1024, -1); }
     else if (thr == 512) { if (dflt) TB_TILE_LAUNCH(512, TB_MODE_CIGAR); else TB_TILE_LAUNCH(512, -1); }
+    else if (thr == 128) { if (dflt) TB_TILE_LAUNCH(128, TB_MODE_CIGAR); else TB_TILE_LAUNCH(128, -1); }
     else { if (dflt) TB_TILE_LAUNCH(256, TB_MODE_CIGAR); else TB_TILE_LAUNCH(256, -1); }
 #undef TB_TILE_LAUNCH
     ctx->launches++;

@@ -15,6 +15,11 @@
 // merge itself); the raw GSamRecords of a window stay alive until rep_index[] comes back, then the representatives
 // get their tags and are written, the rest are freed.
 //
+// Host pipeline (first step): the main thread decodes + merges (the reference's TInputFiles) and cuts
+// windows; a second thread owns the CUDA context and does pack -> tb_collapse_window -> tag patching -> BAM write (BGZF
+// compression on TB_IO_THREADS htslib worker threads) -> free, so decode of window w+1 overlaps device + write of window w,
+// and CUDA start-up overlaps the first window's decode.
+//
 // No CPU fallback: without a CUDA device tb_create() fails and the tool exits 1 like any other GError.
 #define main tb_reference_main_unused
 #include "src/tiebrush.cpp"
@@ -22,15 +27,32 @@
 
 #include <vector>
 #include <chrono>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <deque>
+#include <memory>
 #include "tiebrush_b200.h"
 
 namespace {
 
+struct TbWindow {   // what the reader thread hands to the device thread
+  int tid = -1;
+  size_t n = 0;
+  std::vector<std::vector<GSamRecord*>> per_file;   // records of the window, per input file, in file order
+  std::vector<uint8_t> file_merged;
+  explicit TbWindow(int k) : per_file(k), file_merged(k, 0) {}
+  void add(TInputRecord* irec) {
+    per_file[irec->fidx].push_back(irec->brec);
+    file_merged[irec->fidx] = irec->tbMerged ? 1 : 0;
+    irec->disown();   // the window owns the record now (TInputFiles::next deletes its current record otherwise)
+    ++n;
+  }
+};
+
 struct TbWindowPacker {
   int k = 0;
-  std::vector<std::vector<GSamRecord*>> per_file;   // records of the open window, per input file, in file order
-  std::vector<uint8_t> file_merged;
-  size_t n = 0;
+  htsFile* out_fp = NULL; sam_hdr_t* out_hdr = NULL;
   // SoA staging (reused between windows)
   std::vector<int64_t> run_off;
   std::vector<int32_t> pos, yx_in, yd_in;
@@ -44,7 +66,7 @@ struct TbWindowPacker {
   double t_pack = 0, t_device = 0, t_write = 0;
   int64_t n_windows = 0;
 
-  void init(int nfiles) { k = nfiles; per_file.assign(k, {}); file_merged.assign(k, 0); }
+  void init(int nfiles) { k = nfiles; }
 
   static uint64_t fnv1a(const char* s) {
     uint64_t h = 1469598103934665603ULL;
@@ -52,14 +74,10 @@ struct TbWindowPacker {
     return h;
   }
 
-  void add(TInputRecord* irec) {
-    per_file[irec->fidx].push_back(irec->brec);
-    file_merged[irec->fidx] = irec->tbMerged ? 1 : 0;
-    irec->disown();   // the window owns the record now (TInputFiles::next deletes its current record otherwise)
-    ++n;
-  }
-
-  void flush(tb_ctx* ctx, int tid) {
+  void flush(tb_ctx* ctx, TbWindow& w) {
+    const size_t n = w.n; const int tid = w.tid;
+    std::vector<std::vector<GSamRecord*>>& per_file = w.per_file;
+    std::vector<uint8_t>& file_merged = w.file_merged;
     if (n == 0) return;
     using clk = std::chrono::steady_clock;
     auto t0 = clk::now();
@@ -131,12 +149,11 @@ struct TbWindowPacker {
       r->add_double_tag("YC", (double)o_yc[g]);
       r->add_int_tag("YX", (int64_t)o_yx[g]);
       if (o_yd[g] > 0) r->add_int_tag("YD", o_yd[g]); else r->remove_tag("YD");
-      outfile->write(r);
+      if (sam_write1(out_fp, out_hdr, r->get_b()) < 0) GError("Error writing SAM record!\n");   // GSamWriter::write, GSam.h:648-653
       outCounter++;
     }
     for (GSamRecord* r : held) delete r;
-    for (int f = 0; f < k; ++f) per_file[f].clear();
-    n = 0; ++n_windows;
+    ++n_windows;
     auto t3 = clk::now();
     t_pack += std::chrono::duration<double>(t1 - t0).count();
     t_device += std::chrono::duration<double>(t2 - t1).count();
@@ -146,55 +163,90 @@ struct TbWindowPacker {
 
 }  // namespace
 
+// bounded hand-off queue between the reader thread and the device thread
+struct TbQueue {
+  std::mutex m; std::condition_variable cv;
+  std::deque<std::unique_ptr<TbWindow>> q; bool done = false;
+  void push(std::unique_ptr<TbWindow> w) {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return q.size() < 2; });
+    q.push_back(std::move(w)); cv.notify_all();
+  }
+  std::unique_ptr<TbWindow> pop() {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return !q.empty() || done; });
+    if (q.empty()) return nullptr;
+    std::unique_ptr<TbWindow> w = std::move(q.front()); q.pop_front(); cv.notify_all();
+    return w;
+  }
+  void finish() { std::lock_guard<std::mutex> lk(m); done = true; cv.notify_all(); }
+};
+
 int main(int argc, char* argv[]) {
   using clk = std::chrono::steady_clock;
   auto t_begin = clk::now();
   inRecords.setup(VERSION, argc, argv);
   processOptions(argc, argv);
   int numSamples = inRecords.start();
-  outfile = new GSamWriter(outfname, inRecords.header(), GSamFile_BAM);
+  // output: same header and record bytes as GSamWriter (GSam.h:537-573), BGZF compression on worker threads
+  int io_threads = 4;
+  if (const char* e = getenv("TB_IO_THREADS")) io_threads = atoi(e);
+  htsFile* out_fp = hts_open(outfname.chars(), "wb");
+  if (out_fp == NULL) GError("Error: could not create output file %s\n", outfname.chars());
+  if (io_threads > 1) hts_set_threads(out_fp, io_threads);
+  sam_hdr_t* out_hdr = sam_hdr_dup(inRecords.header());
+  if (sam_hdr_write(out_fp, out_hdr) < 0) GError("Error writing header data to file %s\n", outfname.chars());
 
   const int keep = (options.keep_supplementary ? TB_KEEP_SUPP : 0) | (options.keep_secondary ? TB_KEEP_SECONDARY : 0) |
                    (options.keep_unmapped ? TB_KEEP_UNMAP : 0) | (options.store_frac ? TB_STORE_FRAC : 0);
   const int mode = mrgStrategy == tMrgStratFull ? TB_MODE_FULL : mrgStrategy == tMrgStratClip ? TB_MODE_CLIP :
                    mrgStrategy == tMrgStratExon ? TB_MODE_EXON : TB_MODE_CIGAR;
-  const char* dev_env = getenv("TB_DEVICE");
-  tb_ctx* ctx = tb_create(dev_env ? atoi(dev_env) : 0, numSamples, mode, options.flags, options.max_nh, options.min_qual, keep,
-                          options.collapse_same ? 1 : 0);
-  if (!ctx) GError("%s\n", tb_last_error(NULL));
   // records buffered before a coverage gap closes the window (TB_WINDOW_RECORDS; host memory ~ 400 B per record)
-  size_t window_min = 4u << 20;
+  size_t window_min = 1u << 20;
   if (const char* e = getenv("TB_WINDOW_RECORDS")) { long v = atol(e); if (v > 0) window_min = (size_t)v; }
 
-  TbWindowPacker packer; packer.init(numSamples);
+  TbWindowPacker packer; packer.init(numSamples); packer.out_fp = out_fp; packer.out_hdr = out_hdr;
+  TbQueue queue;
+  double t_create = 0;
+  std::thread device_thread([&] {   // owns the CUDA context: one submitting host thread per context
+    auto c0 = clk::now();
+    const char* dev_env = getenv("TB_DEVICE");
+    tb_ctx* ctx = tb_create(dev_env ? atoi(dev_env) : 0, numSamples, mode, options.flags, options.max_nh, options.min_qual, keep,
+                            options.collapse_same ? 1 : 0);
+    if (!ctx) GError("%s\n", tb_last_error(NULL));
+    t_create = std::chrono::duration<double>(clk::now() - c0).count();
+    while (std::unique_ptr<TbWindow> w = queue.pop()) packer.flush(ctx, *w);
+    tb_destroy(ctx);
+  });
+
   TInputRecord* irec = NULL;
   int cur_tid = -2; uint max_end = 0;
-  double t_read = 0;
+  std::unique_ptr<TbWindow> win(new TbWindow(numSamples));
   auto tr0 = clk::now();
   while ((irec = inRecords.next()) != NULL) {
     GSamRecord* brec = irec->brec;
     const int tid = brec->refId();
     if (brec->isUnmapped() || tid < 0)   // the reference's own loop does not survive these either
       GError("Error: unmapped read %s in the input (not supported by tiebrush)\n", brec->name());
-    if (tid != cur_tid || (packer.n >= window_min && brec->start > max_end)) {
-      t_read += std::chrono::duration<double>(clk::now() - tr0).count();
-      packer.flush(ctx, cur_tid);
-      tr0 = clk::now();
+    if (tid != cur_tid || (win->n >= window_min && brec->start > max_end)) {
+      if (win->n) { win->tid = cur_tid; queue.push(std::move(win)); win.reset(new TbWindow(numSamples)); }
       if (tid != cur_tid) { cur_tid = tid; max_end = 0; }
     }
     if (brec->end > max_end) max_end = brec->end;
-    packer.add(irec);
+    win->add(irec);
   }
-  t_read += std::chrono::duration<double>(clk::now() - tr0).count();
-  packer.flush(ctx, cur_tid);
+  if (win->n) { win->tid = cur_tid; queue.push(std::move(win)); }
+  const double t_read = std::chrono::duration<double>(clk::now() - tr0).count();
+  queue.finish();
+  device_thread.join();
   inRecords.stop();
-  delete outfile;
-  tb_destroy(ctx);
+  if (hts_close(out_fp) < 0) GError("Error closing output file %s\n", outfname.chars());
+  sam_hdr_destroy(out_hdr);
 
   double p = 100.00 - (double)(outCounter * 100.00) / (double)inCounter;
   GMessage("%ld input records written as %ld (%.2f%% reduction)\n", inCounter, outCounter, p);
   if (getenv("TB_TIMING"))
-    fprintf(stderr, "tb_b200 timing: total %.3f s | decode+merge %.3f | pack %.3f | device (H2D+kernels+D2H) %.3f | tag+write %.3f | windows %ld\n",
-            std::chrono::duration<double>(clk::now() - t_begin).count(), t_read, packer.t_pack, packer.t_device, packer.t_write, (long)packer.n_windows);
+    fprintf(stderr, "tb_b200 timing: total %.3f s | decode+merge %.3f | pack %.3f | device (H2D+kernels+D2H) %.3f | tag+write %.3f | windows %ld | cuda init %.3f (overlapped) | reader thread includes waiting for the device thread\n",
+            std::chrono::duration<double>(clk::now() - t_begin).count(), t_read, packer.t_pack, packer.t_device, packer.t_write, (long)packer.n_windows, t_create);
   return 0;
 }
