@@ -130,3 +130,14 @@ def test_coverage_c4_scale_properties_and_oracle_prefix():
         for a, b in zip(got["juncs"], exp["juncs"]):
             assert np.array_equal(np.asarray(a), b)
         assert nj > 0
+
+
+def test_coverage_unaligned_columns_take_the_scalar_path(ctx, monkeypatch):
+    """The bundle kernel's 128-bit loads need 16-byte aligned columns; other inputs must take the scalar path and agree."""
+    from oracle import oracle
+    from tiebrush_b200 import synth
+    monkeypatch.setenv("TB_COV_NOVEC", "1")
+    cols = synth.to_host(synth.coverage_stream(60_001, seed=21, n_tx=40, chroms=3))
+    got, exp = ctx.coverage_window(cols), oracle.coverage(cols)
+    for a, b in zip(got["runs"] + got["juncs"], exp["runs"] + exp["juncs"]):
+        assert np.array_equal(np.asarray(a), b)

@@ -14,6 +14,7 @@
 // Weights: YC is float32 on disk; the reference accumulates doubles. Here every weight is
 // converted once to 2^-20 fixed point (exact for all integer-valued YC and for dyadic fractions) and
 // summed in int64, which equals the reference's double sum whenever that sum is exact.
+#include <stdlib.h>
 #include "tb_common.cuh"
 
 namespace {
@@ -21,8 +22,8 @@ namespace {
 constexpr double COV_FX_SCALE = 1048576.0;
 
 enum {  // workspace slots in ctx->buf
-  CB_KEY = 0,     // u64 [n]   (tid<<32 | end1)
-  CB_PM,          // u64 [n]   exclusive prefix max of CB_KEY
+  CB_KEY = 0,     // u64 [2*tiles+8] look-back tile states of K6 (max chain, count chain) + ticket
+  CB_PM,          // unused
   CB_BID,         // u32 [n]   bundle id per record
   CB_BSTART,      // i32 [n]   bundle start (1-based)   (indexed by bundle)
   CB_BEND,        // i32 [n]
@@ -50,7 +51,7 @@ enum {  // workspace slots in ctx->buf
 };
 
 // status block layout (int64 each)
-enum { ST_ERRIDX = 0, ST_NBUNDLES, ST_DENSE_LEN, ST_NCHANGE, ST_NRUNS, ST_NJUNC, ST_JOVERFLOW, ST_JCOLLISION, ST_RUNOVERFLOW, ST_INEXACT, ST_N_ };
+enum { ST_ERRIDX = 0, ST_NBUNDLES, ST_DENSE_LEN, ST_NCHANGE, ST_NRUNS, ST_NJUNC, ST_JOVERFLOW, ST_JCOLLISION, ST_RUNOVERFLOW, ST_INEXACT, ST_LBFAIL, ST_N_ };
 
 struct CovIn {
   int64_t n;
@@ -58,58 +59,164 @@ struct CovIn {
   const uint32_t* cig_off; const uint32_t* cigar;
 };
 
-// ---- K6a: per-record end coordinate + op validation ---------------------------------------------
-__global__ void __launch_bounds__(256) cov_key_kernel(CovIn in, int check_ops, unsigned long long* __restrict__ key,
-                                                      long long* __restrict__ status) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= in.n) return;
-  uint32_t c0 = in.cig_off[i], c1 = in.cig_off[i + 1];
-  int l = 0;
-  bool bad = check_ops && (c1 - c0 >= 256u);  // tiecov.cpp:198 uint8_t loop counter never terminates
-  for (uint32_t c = c0; c < c1; ++c) {
-    uint32_t w = in.cigar[c];
-    uint32_t op = w & 0xf, len = w >> 4;
-    if (op == TB_OP_M || op == TB_OP_D || op == TB_OP_N || op == TB_OP_EQ || op == TB_OP_X) l += (int)len;
-    if (check_ops && !(op == TB_OP_M || op == TB_OP_I || op == TB_OP_D || op == TB_OP_N || op == TB_OP_S)) bad = true;
+// ---- K6: bundles in ONE pass over the records (decoupled look-back) -----------------------------------------------
+// A record opens a bundle iff its tid differs from, or its start exceeds, the running maximum end of everything before
+// it (tiecov.cpp:443): with key = tid << 32 | end that is a test against the exclusive prefix maximum of the keys, and the
+// bundle id is the inclusive prefix count of such heads. Both prefixes are carried across tiles of 2048 records by
+// single-word tile states (2 flag bits | 62-bit payload; aggregate first, inclusive prefix once the tile's own look-back
+// is done): the max chain resolves first, the head count of a tile follows from it, then the count chain. Tiles take
+// tickets in launch order, so every predecessor of a running tile is itself running or finished (forward progress);
+// the spin is bounded and reports through ST_LBFAIL instead of hanging. The head of bundle b also closes bundle b-1:
+// its exclusive prefix maximum IS that bundle's end (a bundle starts beyond every earlier end of its tid).
+// Reads every input field once (27 B per record) and writes the bundle id (4 B); no key / prefix arrays.
+#ifndef TB_CBK_ITEMS
+#define TB_CBK_ITEMS 8
+#endif
+#ifndef TB_CBK_MINB
+#define TB_CBK_MINB 4
+#endif
+constexpr int CBK_THREADS = 256, CBK_ITEMS = TB_CBK_ITEMS, CBK_TILE = CBK_THREADS * CBK_ITEMS;
+constexpr unsigned long long LB_AGG = 1ULL << 62, LB_INC = 2ULL << 62, LB_MASK = (1ULL << 62) - 1ULL;
+
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+__device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+
+// exclusive prefix (max or sum of the 62-bit payloads) of the tiles before `tile`; called by one whole warp
+template <bool IS_MAX>
+__device__ unsigned long long lb_lookback(const unsigned long long* st, long long tile, long long* status) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long acc = 0;   // identity of both operators (payloads are non-negative)
+  int spins = 0;
+  for (long long idx = tile - 1; idx >= 0; idx -= 32) {
+    const long long j = idx - lane;
+    unsigned long long w = j >= 0 ? lb_load(&st[j]) : LB_INC;   // before the first tile: an inclusive identity
+    while (__any_sync(0xffffffffu, (w >> 62) == 0)) {
+      if (++spins > (1 << 22)) { status[ST_LBFAIL] = 1; break; }
+      if ((w >> 62) == 0) w = lb_load(&st[j]);
+    }
+    const unsigned inc = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+    const int first = inc ? __ffs(inc) - 1 : 32;
+    unsigned long long v = lane <= first ? (w & LB_MASK) : 0ULL;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
+      v = IS_MAX ? (v > o ? v : o) : v + o;
+    }
+    acc = IS_MAX ? (acc > v ? acc : v) : acc + v;
+    if (inc) break;
   }
-  if (bad) atomicMin((unsigned long long*)&status[ST_ERRIDX], (unsigned long long)i);
-  uint32_t end1 = (uint32_t)(in.pos[i] + l);
-  key[i] = ((unsigned long long)(uint32_t)in.tid[i] << 32) | end1;
-  float w = in.yc[i];
-  float sc = w * (float)COV_FX_SCALE;
-  if (sc != truncf(sc)) status[ST_INEXACT] = 1;  // benign race: any writer stores 1
+  return acc;
 }
 
-struct KeyIn { const unsigned long long* k; __device__ unsigned long long operator()(int64_t i) const { return k[i]; } };
-struct PmOut { unsigned long long* pm; __device__ void operator()(int64_t i, unsigned long long exc, unsigned long long) const { pm[i] = exc; } };
-
-__device__ __forceinline__ bool cov_is_head(const CovIn& in, const unsigned long long* pm, int64_t i) {
-  if (i == 0) return true;
-  unsigned long long p = pm[i];
-  int ptid = (int)(p >> 32);
-  int pend = (int)(uint32_t)p;
-  return in.tid[i] != ptid || (in.pos[i] + 1) > pend;  // tiecov.cpp:443
-}
-
-struct HeadIn {
-  CovIn in; const unsigned long long* pm;
-  __device__ uint32_t operator()(int64_t i) const { return cov_is_head(in, pm, i) ? 1u : 0u; }
-};
-struct BundleOut {
-  CovIn in; const unsigned long long* pm; const unsigned long long* key;
-  uint32_t* bid; int32_t* bstart; int32_t* bend; int32_t* btid;
-  __device__ void operator()(int64_t i, uint32_t, uint32_t inc) const {
-    uint32_t b = inc - 1;
-    bid[i] = b;
-    if (cov_is_head(in, pm, i)) { bstart[b] = in.pos[i] + 1; btid[b] = in.tid[i]; }
-    if (i == in.n - 1 || cov_is_head(in, pm, i + 1)) {
-      int e = (int)(uint32_t)key[i];
-      unsigned long long p = pm[i];
-      if (i > 0 && (int)(p >> 32) == in.tid[i] && (int)(uint32_t)p > e) e = (int)(uint32_t)p;
-      bend[b] = e;
+// VEC: the per-record columns are 16-byte aligned, so a thread fetches its 8 consecutive records with 128-bit loads
+// (a warp request then covers 512 contiguous bytes instead of 32 scattered sectors)
+template <bool VEC>
+__global__ void __launch_bounds__(CBK_THREADS, TB_CBK_MINB) cov_bundle_kernel(CovIn in, int check_ops, unsigned long long* __restrict__ st_max,
+                                                                 unsigned long long* __restrict__ st_cnt, unsigned long long* __restrict__ ticket,
+                                                                 uint32_t* __restrict__ bid, int32_t* __restrict__ bstart, int32_t* __restrict__ bend,
+                                                                 int32_t* __restrict__ btid, long long* __restrict__ status) {
+  __shared__ unsigned long long s_scan64[33];
+  __shared__ uint32_t s_scan32[33];
+  __shared__ unsigned long long s_tile, s_pa, s_pb;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1ULL);
+  __syncthreads();
+  const long long tile = (long long)s_tile;
+  const int64_t base = tile * CBK_TILE + (int64_t)threadIdx.x * CBK_ITEMS;
+  unsigned long long key[CBK_ITEMS]; int pos[CBK_ITEMS], tidv[CBK_ITEMS];
+  uint32_t coff[CBK_ITEMS + 1]; float ycv[CBK_ITEMS];
+  const bool full = base + CBK_ITEMS <= in.n;
+  if (VEC && full) {
+    static_assert(CBK_ITEMS % 4 == 0, "128-bit loads");
+#pragma unroll
+    for (int q = 0; q < CBK_ITEMS / 4; ++q) {
+      const int4 p = *reinterpret_cast<const int4*>(in.pos + base + 4 * q), t = *reinterpret_cast<const int4*>(in.tid + base + 4 * q);
+      const uint4 c = *reinterpret_cast<const uint4*>(in.cig_off + base + 4 * q);
+      const float4 y = *reinterpret_cast<const float4*>(in.yc + base + 4 * q);
+      pos[4 * q] = p.x; pos[4 * q + 1] = p.y; pos[4 * q + 2] = p.z; pos[4 * q + 3] = p.w;
+      tidv[4 * q] = t.x; tidv[4 * q + 1] = t.y; tidv[4 * q + 2] = t.z; tidv[4 * q + 3] = t.w;
+      coff[4 * q] = c.x; coff[4 * q + 1] = c.y; coff[4 * q + 2] = c.z; coff[4 * q + 3] = c.w;
+      ycv[4 * q] = y.x; ycv[4 * q + 1] = y.y; ycv[4 * q + 2] = y.z; ycv[4 * q + 3] = y.w;
+    }
+    coff[CBK_ITEMS] = in.cig_off[base + CBK_ITEMS];
+  } else {
+#pragma unroll
+    for (int k = 0; k < CBK_ITEMS; ++k) {
+      const int64_t i = base + k;
+      pos[k] = 0; tidv[k] = 0; coff[k] = 0; ycv[k] = 0.f;
+      if (i < in.n) { pos[k] = in.pos[i]; tidv[k] = in.tid[i]; coff[k] = in.cig_off[i]; ycv[k] = in.yc[i]; }
+    }
+    coff[CBK_ITEMS] = 0;
+#pragma unroll
+    for (int k = 0; k < CBK_ITEMS; ++k) if (base + k < in.n) coff[k + 1] = in.cig_off[base + k + 1];
+  }
+  unsigned long long tm = 0;
+#pragma unroll
+  for (int k = 0; k < CBK_ITEMS; ++k) {
+    const int64_t i = base + k;
+    key[k] = 0;
+    if (i < in.n) {
+      const uint32_t c0 = coff[k], c1 = coff[k + 1];
+      int l = 0;
+      bool bad = check_ops && (c1 - c0 >= 256u);  // tiecov.cpp:198 uint8_t loop counter never terminates
+      for (uint32_t c = c0; c < c1; ++c) {
+        const uint32_t w = in.cigar[c];
+        const uint32_t op = w & 0xf, len = w >> 4;
+        if (op == TB_OP_M || op == TB_OP_D || op == TB_OP_N || op == TB_OP_EQ || op == TB_OP_X) l += (int)len;
+        if (check_ops && !(op == TB_OP_M || op == TB_OP_I || op == TB_OP_D || op == TB_OP_N || op == TB_OP_S)) bad = true;
+      }
+      if (bad) atomicMin((unsigned long long*)&status[ST_ERRIDX], (unsigned long long)i);
+      key[k] = ((unsigned long long)(uint32_t)tidv[k] << 32) | (uint32_t)(pos[k] + l);
+      const float sc = ycv[k] * (float)COV_FX_SCALE;
+      if (sc != truncf(sc)) status[ST_INEXACT] = 1;  // benign race: any writer stores 1
+      tm = key[k] > tm ? key[k] : tm;
     }
   }
-};
+  // ---- max chain ----
+  unsigned long long tot;
+  const unsigned long long texc = tb_block_exscan<OpMaxU64>(tm, s_scan64, &tot);
+  if (threadIdx.x == 0) lb_store(&st_max[tile], LB_AGG | tot);
+  if (threadIdx.x < 32) {
+    const unsigned long long pa = lb_lookback<true>(st_max, tile, status);
+    if (threadIdx.x == 0) { s_pa = pa; lb_store(&st_max[tile], LB_INC | (pa > tot ? pa : tot)); }
+  }
+  __syncthreads();
+  unsigned long long run = s_pa > texc ? s_pa : texc;   // exclusive prefix maximum at this thread's first record
+  // ---- heads ----
+  const unsigned long long run0 = run; uint32_t headm = 0, hc = 0;
+#pragma unroll
+  for (int k = 0; k < CBK_ITEMS; ++k) {
+    const int64_t i = base + k;
+    if (i < in.n) {
+      const bool h = i == 0 || tidv[k] != (int)(run >> 32) || (pos[k] + 1) > (int)(uint32_t)run;   // tiecov.cpp:443
+      if (h) { headm |= 1u << k; ++hc; }
+      run = key[k] > run ? key[k] : run;
+    }
+  }
+  // ---- count chain ----
+  uint32_t htot;
+  const uint32_t hexc = tb_block_exscan<OpSumU32>(hc, s_scan32, &htot);
+  if (threadIdx.x == 0) lb_store(&st_cnt[tile], LB_AGG | (unsigned long long)htot);
+  if (threadIdx.x < 32) {
+    const unsigned long long pb = lb_lookback<false>(st_cnt, tile, status);
+    if (threadIdx.x == 0) { s_pb = pb; lb_store(&st_cnt[tile], LB_INC | (pb + htot)); }
+  }
+  __syncthreads();
+  uint32_t cnt = (uint32_t)s_pb + hexc;   // heads before this thread's first record
+  run = run0;
+#pragma unroll
+  for (int k = 0; k < CBK_ITEMS; ++k) {
+    const int64_t i = base + k;
+    if (i >= in.n) break;
+    if (headm & (1u << k)) {
+      const uint32_t b = cnt++;
+      bstart[b] = pos[k] + 1; btid[b] = tidv[k];
+      if (b > 0) bend[b - 1] = (int)(uint32_t)run;   // this head closes the previous bundle
+    }
+    bid[i] = cnt - 1;
+    run = key[k] > run ? key[k] : run;
+    if (i == in.n - 1) { bend[cnt - 1] = (int)(uint32_t)run; status[ST_NBUNDLES] = cnt; }
+  }
+}
 
 struct BLenIn {
   const int32_t* bstart; const int32_t* bend; const long long* status;
@@ -433,8 +540,7 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
   if (stage_in(ctx, ctx->in_stage[5], hin->cigar, (size_t)ncig, hin->on_device, &in.cigar)) return 1;
 
   DevBuf* B = ctx->buf;
-  TB_CUDA(B[CB_KEY].ensure(sizeof(uint64_t) * n));
-  TB_CUDA(B[CB_PM].ensure(sizeof(uint64_t) * n));
+  TB_CUDA(B[CB_KEY].ensure(sizeof(uint64_t) * (2 * (size_t)((n + CBK_TILE - 1) / CBK_TILE) + 16)));
   TB_CUDA(B[CB_BID].ensure(sizeof(uint32_t) * n));
   TB_CUDA(B[CB_BSTART].ensure(sizeof(int32_t) * n));
   TB_CUDA(B[CB_BEND].ensure(sizeof(int32_t) * n));
@@ -450,23 +556,33 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     TB_CUDA(cudaMemcpyAsync(d_status, h_status, sizeof(init), cudaMemcpyHostToDevice, st));
     TB_CUDA(cudaStreamSynchronize(st));  // h_status is reused for readback below
   }
-  unsigned long long* d_key = B[CB_KEY].as<unsigned long long>();
-  unsigned long long* d_pm = B[CB_PM].as<unsigned long long>();
-
   // ---- K6 ----
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[8], st));
-  cov_key_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, do_cov, d_key, d_status);
-  ctx->launches++;
+  {
+    const int64_t ntiles = (n + CBK_TILE - 1) / CBK_TILE;
+    unsigned long long* st_max = B[CB_KEY].as<unsigned long long>();
+    unsigned long long* st_cnt = st_max + ntiles;
+    unsigned long long* ticket = st_cnt + ntiles;
+    TB_CUDA(cudaMemsetAsync(st_max, 0, sizeof(uint64_t) * (2 * (size_t)ntiles + 8), st));
+    const bool vec = (((uintptr_t)in.pos | (uintptr_t)in.tid | (uintptr_t)in.cig_off | (uintptr_t)in.yc) & 15u) == 0 && !getenv("TB_COV_NOVEC");
+    if (vec)
+      cov_bundle_kernel<true><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, do_cov, st_max, st_cnt, ticket, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(),
+                                                                       B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_status);
+    else
+      cov_bundle_kernel<false><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, do_cov, st_max, st_cnt, ticket, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(),
+                                                                        B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_status);
+    ctx->launches++;
+  }
+  // the bundle count decides the size of the next scan
+  TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  if (h_status[ST_LBFAIL]) { ctx->set_error("tc_coverage_window: bundle scan did not make progress (internal error)"); return 1; }
+  const int64_t NB = h_status[ST_NBUNDLES];
   size_t agg_bytes = (size_t)(tb_scan_blocks(n > 2 * ncig + 16 ? n : 2 * ncig + 16) + 8) * sizeof(SumNz);
   TB_CUDA(B[CB_AGG].ensure(agg_bytes));
-  TB_CUDA((tb_device_scan<OpMaxU64>(ctx, KeyIn{d_key}, n, B[CB_AGG].as<unsigned long long>(), PmOut{d_pm})));
-  BundleOut bo{in, d_pm, d_key, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>()};
-  TB_CUDA((tb_device_scan<OpSumU32>(ctx, HeadIn{in, d_pm}, n, B[CB_AGG].as<uint32_t>(), bo)));
-  cov_publish_kernel<<<1, 1, 0, st>>>(B[CB_AGG].as<uint32_t>() + tb_scan_blocks(n), nullptr, d_status);
-  ctx->launches++;
-  TB_CUDA((tb_device_scan<OpSumI64>(ctx, BLenIn{B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(), d_status}, n,
+  TB_CUDA((tb_device_scan<OpSumI64>(ctx, BLenIn{B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(), d_status}, NB,
                                     B[CB_AGG].as<long long>(), BBaseOut{B[CB_BBASE].as<long long>()})));
-  cov_publish_kernel<<<1, 1, 0, st>>>(nullptr, B[CB_AGG].as<long long>() + tb_scan_blocks(n), d_status);
+  cov_publish_kernel<<<1, 1, 0, st>>>(nullptr, B[CB_AGG].as<long long>() + tb_scan_blocks(NB), d_status);
   ctx->launches++;
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[9], st));
   TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
