@@ -290,9 +290,15 @@ __device__ __forceinline__ long long cov_seg_prefix(bool head_in, long long val)
 // shared atomicAdd is a CAS loop on sm_100). Junction weights are pre-aggregated the same way in a small shared hash
 // table. The flush issues one global RED per NON-ZERO cell / occupied junction slot: an order of magnitude fewer global
 // atomics than one per update, and none of them contended inside the CTA.
+#ifndef TB_COV_TILE
+#define TB_COV_TILE 4096
+#endif
+#ifndef TB_COV_RPT
+#define TB_COV_RPT 16
+#endif
 constexpr int COV_THREADS = 256;
-constexpr int COV_RPT = 4;
-constexpr int COV_TILE = 4096;
+constexpr int COV_RPT = TB_COV_RPT;
+constexpr int COV_TILE = TB_COV_TILE;
 constexpr int COV_JSLOTS = 256;
 
 __device__ __forceinline__ void cov_cell_add(uint32_t* lo, uint32_t* hi, uint32_t c, long long w) {   // cell c += w
@@ -377,31 +383,32 @@ __global__ void __launch_bounds__(COV_THREADS) cov_accumulate_kernel(CovIn in, c
     for (uint32_t q = 0; q < nc; ++q) {
       const uint32_t cw = in.cigar[c0 + q];
       const uint32_t op = cw & 0xf; const int len = (int)(cw >> 4);
-      switch (op) {
-        case TB_OP_M:
-          if (do_cov && len > 0 && w != 0) {
-            const long long a = (long long)(pos + l + 1) + shift;
-            if (pend != a) {
-              if (pend >= 0) cell_update(pend, -w);
-              cell_update(a, w);
-            }
-            pend = a + len;
+      // the switch of setupCoordinates / addCov as predicated arithmetic (lanes of a warp sit on different ops):
+      //   M,=,X,D : l += len, intron = ins = false      N : close the exon (unless ins && intron), l += len, intron = true
+      //   S,H     : intron = ins = false                I : ins = true                  M alone adds coverage
+      if (op == TB_OP_M) {
+        if (do_cov && len > 0 && w != 0) {
+          const long long a = (long long)(pos + l + 1) + shift;
+          if (pend != a) {
+            if (pend >= 0) cell_update(pend, -w);
+            cell_update(a, w);
           }
-          l += len; intron = false; ins = false; break;
-        case TB_OP_EQ: case TB_OP_X: case TB_OP_D:
-          l += len; intron = false; ins = false; break;
-        case TB_OP_N:
-          if (!ins || !intron) {
-            if (do_junc && nclosed > 0)
-              junc_update(tid, ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc, w);
-            last_end = pos + l; nclosed++;
-          }
-          l += len; exstart = pos + l; intron = true; break;
-        case TB_OP_S: case TB_OP_H:
-          intron = false; ins = false; break;
-        case TB_OP_I:
-          ins = true; break;
-        default: break;
+          pend = a + len;
+        }
+      } else if (op == TB_OP_N) {
+        if (!ins || !intron) {
+          if (do_junc && nclosed > 0)
+            junc_update(tid, ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc, w);
+          last_end = pos + l; nclosed++;
+        }
+        exstart = pos + l + len;
+      }
+      const bool refc = (0x18Du >> op) & 1u;            // M(0) D(2) N(3) =(7) X(8) consume the reference
+      const bool known = (0x1BFu >> op) & 1u;           // M I D N S H = X: the ops the reference's switch names
+      l += refc ? len : 0;
+      if (known) {
+        ins = (op == TB_OP_I) || (op == TB_OP_N && ins);
+        intron = (op == TB_OP_N) || (op == TB_OP_I && intron);
       }
     }
     if (pend >= 0) cell_update(pend, -w);
