@@ -101,7 +101,7 @@ def test_tiebrush_cli_small_windows_and_collapse_same(sams):
     for name, files, opts in (("w", paths, []), ("a", paired, ["-A"]), ("af", paired, ["-A", "-F", "192"])):
         ref_out, our_out = os.path.join(tmp, f"ref_{name}.bam"), os.path.join(tmp, f"gpu_{name}.bam")
         _run([os.path.join(REF, "tiebrush")] + opts + ["-o", ref_out] + files)
-        msg = _run([os.path.join(HOST, "tiebrush_gpu")] + opts + ["-o", our_out] + files, env={"TB_WINDOW_RECORDS": "300", "TB_TIMING": "1"})
+        msg = _run([os.path.join(HOST, "tiebrush_gpu")] + opts + ["-o", our_out] + files, env={"TB_WINDOW_RECORDS": "300", "TB_WINDOW_SPAN": "2000", "TB_DECODE_THREADS": "3", "TB_TIMING": "1"})
         assert _records(our_out) == _records(ref_out)
         assert "windows" in msg
 

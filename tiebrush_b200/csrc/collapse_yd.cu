@@ -175,11 +175,24 @@ __global__ void __launch_bounds__(128) yd_scatter_kernel(const uint32_t* __restr
   }
 }
 
-// chain id of every member: chain c owns members [colbase[c], colbase[c+1]) (coalesced fill, blockIdx.y = chain)
+// chain id of every member: chain c owns members [colbase[c], colbase[c+1]). One binary search per block of YD_FILL members,
+// then every thread walks forward over the (few) chain boundaries inside the block; coalesced 2-byte stores.
 constexpr int YD_FILL = 16384;
-__global__ void __launch_bounds__(256) yd_fill_mchain_kernel(const unsigned long long* __restrict__ colbase, uint16_t* __restrict__ mchain) {
-  const unsigned long long a = colbase[blockIdx.y] + (unsigned long long)blockIdx.x * YD_FILL, e = colbase[blockIdx.y + 1];
-  for (unsigned long long i = a + threadIdx.x; i < e && i < a + YD_FILL; i += 256) mchain[i] = (uint16_t)blockIdx.y;
+__global__ void __launch_bounds__(256) yd_fill_mchain_kernel(const unsigned long long* __restrict__ colbase, int nchains, unsigned long long n_members,
+                                                             uint16_t* __restrict__ mchain) {
+  __shared__ int s_c0;
+  const unsigned long long a = (unsigned long long)blockIdx.x * YD_FILL;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = nchains;   // last c with colbase[c] <= a
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (colbase[mid] <= a) lo = mid; else hi = mid; }
+    s_c0 = lo;
+  }
+  __syncthreads();
+  int c = s_c0;
+  for (unsigned long long i = a + threadIdx.x; i < a + YD_FILL && i < n_members; i += 256) {
+    while (c + 1 < nchains && colbase[c + 1] <= i) ++c;
+    mchain[i] = (uint16_t)c;
+  }
 }
 
 // sub-chain heads: prefix max of (chain<<32 | end) over the member array is a segmented prefix max (chain ids ascend).
@@ -689,7 +702,7 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
     uint32_t* chain = B[XB_YDCHAIN].as<uint32_t>(); uint32_t* heads = B[XB_BHEAD].as<uint32_t>(); uint32_t* flag = B[XB_YDFLAG].as<uint32_t>();
     uint16_t* mchain = (uint16_t*)(flag + n_members + 32);
     yd_scatter_kernel<<<tb_grid_for(nwarps * 32, 128), 128, 0, st>>>(grp.bits, W, k, G, gstrand, blkoff, nblk, chain);
-    yd_fill_mchain_kernel<<<dim3((unsigned)((n_members + YD_FILL - 1) / YD_FILL), (unsigned)nchains), 256, 0, st>>>(colbase, mchain);
+    yd_fill_mchain_kernel<<<(unsigned)((n_members + YD_FILL - 1) / YD_FILL), 256, 0, st>>>(colbase, nchains, (unsigned long long)n_members, mchain);
     ctx->launches += 2;
     const uint32_t* hs = gstart; const uint32_t* he = gend;
     if (parallel) {

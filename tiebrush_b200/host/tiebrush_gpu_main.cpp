@@ -205,10 +205,30 @@ int main(int argc, char* argv[]) {
   size_t window_min = 1u << 20;
   if (const char* e = getenv("TB_WINDOW_RECORDS")) { long v = atol(e); if (v > 0) window_min = (size_t)v; }
 
+  const bool dry_run = getenv("TB_DRYRUN") != NULL;   // reader self-check: no device, no output records, window statistics only
   TbWindowPacker packer; packer.init(numSamples); packer.out_fp = out_fp; packer.out_hdr = out_hdr;
   TbQueue queue;
   double t_create = 0;
   std::thread device_thread([&] {   // owns the CUDA context: one submitting host thread per context
+    if (dry_run) {   // checks the reader's contract: file order kept, windows separated by coverage gaps, nothing lost
+      long nwin = 0, nrec = 0, bad_order = 0, bad_gap = 0; int last_tid = -1; uint64_t last_end = 0;
+      while (std::unique_ptr<TbWindow> w = queue.pop()) {
+        uint64_t lo = ~0ULL, hi = 0;
+        for (auto& v : w->per_file)
+          for (size_t i = 0; i < v.size(); ++i) {
+            if (i && v[i]->start < v[i - 1]->start) ++bad_order;
+            if (v[i]->refId() != w->tid) ++bad_order;
+            if (v[i]->start < lo) lo = v[i]->start;
+            if (v[i]->end > hi) hi = v[i]->end;
+          }
+        for (auto& v : w->per_file) for (GSamRecord* r : v) delete r;
+        if (w->tid == last_tid && lo <= last_end) ++bad_gap;
+        if (w->tid < last_tid) ++bad_order;
+        last_tid = w->tid; last_end = hi; ++nwin; nrec += (long)w->n;
+      }
+      fprintf(stderr, "tb_b200 dry run: %ld windows, %ld records, %ld order violations, %ld gap violations\n", nwin, nrec, bad_order, bad_gap);
+      return;
+    }
     auto c0 = clk::now();
     const char* dev_env = getenv("TB_DEVICE");
     tb_ctx* ctx = tb_create(dev_env ? atoi(dev_env) : 0, numSamples, mode, options.flags, options.max_nh, options.min_qual, keep,
@@ -219,23 +239,107 @@ int main(int argc, char* argv[]) {
     tb_destroy(ctx);
   });
 
-  TInputRecord* irec = NULL;
-  int cur_tid = -2; uint max_end = 0;
-  std::unique_ptr<TbWindow> win(new TbWindow(numSamples));
-  auto tr0 = clk::now();
-  while ((irec = inRecords.next()) != NULL) {
-    GSamRecord* brec = irec->brec;
-    const int tid = brec->refId();
-    if (brec->isUnmapped() || tid < 0)   // the reference's own loop does not survive these either
-      GError("Error: unmapped read %s in the input (not supported by tiebrush)\n", brec->name());
-    if (tid != cur_tid || (win->n >= window_min && brec->start > max_end)) {
-      if (win->n) { win->tid = cur_tid; queue.push(std::move(win)); win.reset(new TbWindow(numSamples)); }
-      if (tid != cur_tid) { cur_tid = tid; max_end = 0; }
-    }
-    if (brec->end > max_end) max_end = brec->end;
-    win->add(irec);
+  // ---- parallel decode: the files are read independently (the device does the k-way merge), TB_DECODE_THREADS readers
+  // each own a share of the files. A chunk = every record of the current tid that starts at or before `bound`; the window
+  // is cut at the LAST coordinate of the chunk that no read covers (depth array over the chunk), the records behind the
+  // cut stay queued for the next window; without such a coordinate the chunk is extended.
+  struct Cursor { GSamRecord* carry = NULL; bool merged = false; };
+  std::vector<Cursor> cur(numSamples);
+  while (inRecords.recs.Count() > 0) {   // TInputFiles::start() read the first record of every file (tmerge.cpp:319-327)
+    TInputRecord* r0 = inRecords.recs.Pop();
+    cur[r0->fidx].carry = r0->brec; cur[r0->fidx].merged = r0->tbMerged;
+    r0->disown(); delete r0;
   }
-  if (win->n) { win->tid = cur_tid; queue.push(std::move(win)); }
+  int n_threads = (int)std::thread::hardware_concurrency();
+  if (n_threads > 16) n_threads = 16;
+  if (const char* e = getenv("TB_DECODE_THREADS")) n_threads = atoi(e);
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > numSamples) n_threads = numSamples;
+  std::vector<std::vector<GSamRecord*>> pend(numSamples);   // records read but not yet handed over (current tid), per file
+  std::vector<int32_t> depth;                               // difference array over [chunk_lo, bound + 1]
+  auto tr0 = clk::now();
+  uint64_t span = 1u << 21;   // first chunk length in bases (TB_WINDOW_SPAN); later chunks follow the read density
+  if (const char* e = getenv("TB_WINDOW_SPAN")) { long v = atol(e); if (v > 0) span = (uint64_t)v; }
+  for (;;) {
+    int cur_tid = 0x7fffffff;
+    for (int f = 0; f < numSamples; ++f)
+      if (cur[f].carry) {
+        GSamRecord* c = cur[f].carry;
+        if (c->isUnmapped() || c->refId() < 0)   // the reference's own loop does not survive these either
+          GError("Error: unmapped read %s in the input (not supported by tiebrush)\n", c->name());
+        if (c->refId() < cur_tid) cur_tid = c->refId();
+      }
+    if (cur_tid == 0x7fffffff) break;   // every file is exhausted
+    uint64_t chunk_lo = ~0ULL;
+    for (int f = 0; f < numSamples; ++f)
+      if (cur[f].carry && cur[f].carry->refId() == cur_tid && cur[f].carry->start < chunk_lo) chunk_lo = cur[f].carry->start;
+    uint64_t bound = chunk_lo + span;
+    bool tid_done = false;
+    while (!tid_done) {
+      // ---- read every file up to `bound` ----
+      std::vector<std::thread> readers;
+      for (int t = 0; t < n_threads; ++t)
+        readers.emplace_back([&, t] {
+          for (int f = t; f < numSamples; f += n_threads) {
+            GSamRecord* c = cur[f].carry;
+            GSamReader* rd = inRecords.freaders[f]->samreader;
+            while (c && c->refId() == cur_tid && (uint64_t)c->start <= bound) { pend[f].push_back(c); c = rd->next(); }
+            cur[f].carry = c;
+          }
+        });
+      for (auto& th : readers) th.join();
+      tid_done = true;
+      for (int f = 0; f < numSamples; ++f) if (cur[f].carry && cur[f].carry->refId() == cur_tid) tid_done = false;
+      size_t n_pend = 0;
+      for (int f = 0; f < numSamples; ++f) n_pend += pend[f].size();
+      uint64_t cut = 0;   // window = records with start < cut; 0 = no cut yet
+      if (tid_done) cut = ~0ULL;
+      else if (n_pend >= window_min) {
+        // ---- depth over [chunk_lo, bound]: +1 at start, -1 one past end (clipped to the chunk); a coordinate of depth zero
+        // is covered by no read that starts before it, and every such read has been decoded (start <= bound) ----
+        const size_t m = (size_t)(bound - chunk_lo) + 1;
+        depth.assign(m + 2, 0);
+        for (int f = 0; f < numSamples; ++f)
+          for (GSamRecord* r : pend[f]) {
+            uint64_t e = r->end; if (e > bound) e = bound;
+            depth[(size_t)(r->start - chunk_lo)] += 1;
+            depth[(size_t)(e - chunk_lo) + 1] -= 1;
+          }
+        int64_t run = 0;
+        for (size_t x = 0; x < m; ++x) { run += depth[x]; if (run == 0 && x > 0) cut = chunk_lo + x; }   // keeps the last one
+      }
+      if (cut == 0) {   // too few records or no gap inside the chunk: extend it (span follows the read density)
+        if (n_pend > 0) {
+          const double dens = (double)n_pend / (double)(bound - chunk_lo + 1);
+          const double want = (double)window_min / (dens > 1e-9 ? dens : 1e-9);
+          span = want < 65536.0 ? 65536u : (want > 67108864.0 ? 67108864u : (uint64_t)want);
+        }
+        bound += span;
+        continue;
+      }
+      // ---- hand over the records in front of the cut; the rest stays queued ----
+      std::unique_ptr<TbWindow> win(new TbWindow(numSamples));
+      win->tid = cur_tid;
+      for (int f = 0; f < numSamples; ++f) {
+        std::vector<GSamRecord*>& v = pend[f];
+        size_t idx = v.size();
+        if (cut != ~0ULL) {
+          size_t lo = 0, hi = v.size();   // first record with start >= cut (file order = coordinate order)
+          while (lo < hi) { const size_t mid = (lo + hi) >> 1; if ((uint64_t)v[mid]->start >= cut) hi = mid; else lo = mid + 1; }
+          idx = lo;
+        }
+        win->per_file[f].assign(v.begin(), v.begin() + idx);
+        win->file_merged[f] = cur[f].merged ? 1 : 0;
+        win->n += idx;
+        v.erase(v.begin(), v.begin() + idx);
+      }
+      if (win->n) queue.push(std::move(win));
+      if (tid_done) break;
+      chunk_lo = cut;
+      if (bound < chunk_lo) bound = chunk_lo;
+      bound += span;
+    }
+  }
   const double t_read = std::chrono::duration<double>(clk::now() - tr0).count();
   queue.finish();
   device_thread.join();
