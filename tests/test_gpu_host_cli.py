@@ -84,7 +84,8 @@ def sams(tmp_path_factory):
 
 
 @pytest.mark.parametrize("opts", [[], ["-E"], ["-P"], ["-L"], ["-N", "1", "-Q", "30"], ["-F", "16"], ["-S", "--keep-secondary", "-E"],
-                                  ["--keep-secondary", "--store-frac"]])
+                                  ["--keep-secondary", "--store-frac"], ["-L", "-F", "272", "--keep-secondary"], ["-P", "-N", "2"],
+                                  ["-E", "-Q", "1", "--keep-secondary"], ["-L", "-N", "5", "-Q", "1"], ["-P", "-F", "16", "-S"]])
 def test_tiebrush_cli_matches_reference(sams, opts):
     tmp, paths, _ = sams
     tag = "_".join(o.strip("-") for o in opts) or "default"
