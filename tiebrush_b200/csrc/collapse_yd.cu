@@ -216,6 +216,77 @@ __global__ void yd_subchain_total_kernel(const uint32_t* tot, uint32_t* heads, u
   heads[*tot] = n_members; work[0] = 0; work[1] = *tot;
 }
 
+// Y5 in ONE pass over the members (decoupled look-back, see tb_common.cuh): the segmented prefix maximum of the group ends
+// (key = chain << 32 | end: chain ids ascend, so the plain prefix maximum is the segmented one), the head test against it,
+// flag[i] = head | chain << 1, and the list of sub-chain heads (a head's list slot is the prefix count of heads before it).
+// Replaces two three-phase scans (the member keys were gathered three times).
+constexpr int YDH_THREADS = 256, YDH_ITEMS = 8, YDH_TILE = YDH_THREADS * YDH_ITEMS;
+enum { YS_LBFAIL = 10 };
+__global__ void __launch_bounds__(YDH_THREADS, 4) yd_heads_kernel(const uint32_t* __restrict__ chain, const uint16_t* __restrict__ mchain,
+                                                                 const uint32_t* __restrict__ gend, const uint32_t* __restrict__ gstart, uint32_t n_members,
+                                                                 unsigned long long* __restrict__ st_max, unsigned long long* __restrict__ st_cnt,
+                                                                 unsigned long long* __restrict__ ticket, uint32_t* __restrict__ flag,
+                                                                 uint32_t* __restrict__ heads, uint32_t* __restrict__ nsub_out, unsigned long long* work,
+                                                                 long long* __restrict__ status) {
+  __shared__ unsigned long long s_scan64[33];
+  __shared__ uint32_t s_scan32[33];
+  __shared__ unsigned long long s_tile, s_pa, s_pb;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1ULL);
+  __syncthreads();
+  const long long tile = (long long)s_tile;
+  const uint32_t base = (uint32_t)tile * YDH_TILE + threadIdx.x * YDH_ITEMS;
+  unsigned long long key[YDH_ITEMS]; uint32_t gs[YDH_ITEMS];
+  unsigned long long tm = 0;
+#pragma unroll
+  for (int k = 0; k < YDH_ITEMS; ++k) {
+    const uint32_t i = base + k;
+    key[k] = 0; gs[k] = 0;
+    if (i < n_members) {
+      const uint32_t g = chain[i];
+      key[k] = ((unsigned long long)mchain[i] << 32) | gend[g];
+      gs[k] = gstart[g];
+      tm = key[k] > tm ? key[k] : tm;
+    }
+  }
+  unsigned long long tot;
+  const unsigned long long texc = tb_block_exscan<OpMaxU64>(tm, s_scan64, &tot);
+  if (threadIdx.x == 0) lb_store(&st_max[tile], LB_AGG | tot);
+  if (threadIdx.x < 32) {
+    const unsigned long long pa = lb_lookback<true>(st_max, tile, &status[YS_LBFAIL]);
+    if (threadIdx.x == 0) { s_pa = pa; lb_store(&st_max[tile], LB_INC | (pa > tot ? pa : tot)); }
+  }
+  __syncthreads();
+  unsigned long long run = s_pa > texc ? s_pa : texc;   // exclusive prefix maximum at this thread's first member
+  uint32_t headm = 0, hc = 0;
+#pragma unroll
+  for (int k = 0; k < YDH_ITEMS; ++k) {
+    const uint32_t i = base + k;
+    if (i < n_members) {
+      const uint32_t c = (uint32_t)(key[k] >> 32);
+      const bool h = i == 0 || (uint32_t)(run >> 32) != c || gs[k] > (uint32_t)run;
+      if (h) { headm |= 1u << k; ++hc; }
+      flag[i] = (h ? 1u : 0u) | (c << 1);
+      run = key[k] > run ? key[k] : run;
+    }
+  }
+  uint32_t htot;
+  const uint32_t hexc = tb_block_exscan<OpSumU32>(hc, s_scan32, &htot);
+  if (threadIdx.x == 0) lb_store(&st_cnt[tile], LB_AGG | (unsigned long long)htot);
+  if (threadIdx.x < 32) {
+    const unsigned long long pb = lb_lookback<false>(st_cnt, tile, &status[YS_LBFAIL]);
+    if (threadIdx.x == 0) { s_pb = pb; lb_store(&st_cnt[tile], LB_INC | (pb + htot)); }
+  }
+  __syncthreads();
+  uint32_t cnt = (uint32_t)s_pb + hexc;   // heads before this thread's first member
+#pragma unroll
+  for (int k = 0; k < YDH_ITEMS; ++k) {
+    const uint32_t i = base + k;
+    if (i >= n_members) break;
+    if (headm & (1u << k)) heads[cnt++] = i;
+    if (i == n_members - 1) { heads[cnt] = n_members; *nsub_out = cnt; work[0] = 0; work[1] = cnt; }
+  }
+}
+
 constexpr int YD_WARPS = 8;
 constexpr uint32_t YD_LONG = 16;     // sub-chains longer than this are walked by the whole warp
 
@@ -711,11 +782,18 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
       hs = cstart; he = cend;
     }
     // ---- Y5: sub-chain heads ----
-    MemberKeyIn mk{chain, he, mchain};
-    TB_CUDA((tb_device_scan<OpMaxU64>(ctx, mk, n_members, B[XB_AGG].as<unsigned long long>(), MemberHeadOut{mk, hs, flag})));
-    TB_CUDA((tb_device_scan<OpSumU32>(ctx, FlagIn{flag}, n_members, B[XB_AGG].as<uint32_t>(), HeadListOut{heads})));
-    yd_subchain_total_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(n_members), heads, (uint32_t)n_members, work);
-    ctx->launches++;
+    uint32_t* nsub_dev = B[XB_AGG].as<uint32_t>();   // number of sub-chains, written by the heads kernel
+    {
+      const int64_t ntiles = (n_members + YDH_TILE - 1) / YDH_TILE;
+      TB_CUDA(B[XB_YDLB].ensure(sizeof(uint64_t) * (2 * (size_t)ntiles + 8)));
+      unsigned long long* st_max = B[XB_YDLB].as<unsigned long long>();
+      unsigned long long* st_cnt = st_max + ntiles;
+      unsigned long long* ticket = st_cnt + ntiles;
+      TB_CUDA(cudaMemsetAsync(st_max, 0, sizeof(uint64_t) * (2 * (size_t)ntiles + 8), st));
+      yd_heads_kernel<<<(unsigned)ntiles, YDH_THREADS, 0, st>>>(chain, mchain, he, hs, (uint32_t)n_members, st_max, st_cnt, ticket, flag, heads, nsub_dev, work,
+                                                               g.d_status);
+      ctx->launches++;
+    }
     if (parallel) {
       // ---- Y6-Y9 ----
       TB_CUDA(B[XB_YDKEPT].ensure(sizeof(int32_t) * (size_t)n_members + 128));
@@ -728,7 +806,7 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
       const uint32_t nunits = (uint32_t)((n_members + YD_UNIT - 1) / YD_UNIT);
       TB_CUDA(B[XB_YDUNIT].ensure(sizeof(uint32_t) * ((size_t)nunits + 2)));
       uint32_t* ustart = B[XB_YDUNIT].as<uint32_t>();
-      yd_unit_kernel<<<tb_grid_for((int64_t)nunits + 1, 256), 256, 0, st>>>(heads, B[XB_AGG].as<uint32_t>() + tb_scan_blocks(n_members), (uint32_t)n_members, nunits, ustart);
+      yd_unit_kernel<<<tb_grid_for((int64_t)nunits + 1, 256), 256, 0, st>>>(heads, nsub_dev, (uint32_t)n_members, nunits, ustart);
       yd_frontier_kernel<<<(unsigned)ctx->sm_count * 16, YD_FWARPS * 32, 0, st>>>(in, cdesc, grp.rep, chain, flag, ustart, nunits, work, U, rankpre, bm, lpad, mstart);
       ctx->launches++;
       ctx->launches += 2;
@@ -759,5 +837,8 @@ int col_yd(tb_ctx* ctx, const ColIn& in, const ColGeom& g, const ColGroups& grp,
   }
   yd_combine_kernel<<<tb_grid_for(G, 256), 256, 0, st>>>(grp.yd, ydc, G);
   ctx->launches++;
+  TB_CUDA(cudaMemcpyAsync(h_status + YS_LBFAIL, g.d_status + YS_LBFAIL, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  if (h_status[YS_LBFAIL]) { ctx->set_error("tb_collapse_window: sub-chain head scan did not make progress (internal error)"); return 1; }
   return 0;
 }

@@ -76,38 +76,6 @@ struct CovIn {
 #define TB_CBK_MINB 4
 #endif
 constexpr int CBK_THREADS = 256, CBK_ITEMS = TB_CBK_ITEMS, CBK_TILE = CBK_THREADS * CBK_ITEMS;
-constexpr unsigned long long LB_AGG = 1ULL << 62, LB_INC = 2ULL << 62, LB_MASK = (1ULL << 62) - 1ULL;
-
-__device__ __forceinline__ unsigned long long lb_load(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
-__device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
-
-// exclusive prefix (max or sum of the 62-bit payloads) of the tiles before `tile`; called by one whole warp
-template <bool IS_MAX>
-__device__ unsigned long long lb_lookback(const unsigned long long* st, long long tile, long long* status) {
-  const int lane = threadIdx.x & 31;
-  unsigned long long acc = 0;   // identity of both operators (payloads are non-negative)
-  int spins = 0;
-  for (long long idx = tile - 1; idx >= 0; idx -= 32) {
-    const long long j = idx - lane;
-    unsigned long long w = j >= 0 ? lb_load(&st[j]) : LB_INC;   // before the first tile: an inclusive identity
-    while (__any_sync(0xffffffffu, (w >> 62) == 0)) {
-      if (++spins > (1 << 22)) { status[ST_LBFAIL] = 1; break; }
-      if ((w >> 62) == 0) w = lb_load(&st[j]);
-    }
-    const unsigned inc = __ballot_sync(0xffffffffu, (w >> 62) == 2);
-    const int first = inc ? __ffs(inc) - 1 : 32;
-    unsigned long long v = lane <= first ? (w & LB_MASK) : 0ULL;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
-      v = IS_MAX ? (v > o ? v : o) : v + o;
-    }
-    acc = IS_MAX ? (acc > v ? acc : v) : acc + v;
-    if (inc) break;
-  }
-  return acc;
-}
-
 // VEC: the per-record columns are 16-byte aligned, so a thread fetches its 8 consecutive records with 128-bit loads
 // (a warp request then covers 512 contiguous bytes instead of 32 scattered sectors)
 template <bool VEC>
@@ -176,7 +144,7 @@ __global__ void __launch_bounds__(CBK_THREADS, TB_CBK_MINB) cov_bundle_kernel(Co
   const unsigned long long texc = tb_block_exscan<OpMaxU64>(tm, s_scan64, &tot);
   if (threadIdx.x == 0) lb_store(&st_max[tile], LB_AGG | tot);
   if (threadIdx.x < 32) {
-    const unsigned long long pa = lb_lookback<true>(st_max, tile, status);
+    const unsigned long long pa = lb_lookback<true>(st_max, tile, &status[ST_LBFAIL]);
     if (threadIdx.x == 0) { s_pa = pa; lb_store(&st_max[tile], LB_INC | (pa > tot ? pa : tot)); }
   }
   __syncthreads();
@@ -197,7 +165,7 @@ __global__ void __launch_bounds__(CBK_THREADS, TB_CBK_MINB) cov_bundle_kernel(Co
   const uint32_t hexc = tb_block_exscan<OpSumU32>(hc, s_scan32, &htot);
   if (threadIdx.x == 0) lb_store(&st_cnt[tile], LB_AGG | (unsigned long long)htot);
   if (threadIdx.x < 32) {
-    const unsigned long long pb = lb_lookback<false>(st_cnt, tile, status);
+    const unsigned long long pb = lb_lookback<false>(st_cnt, tile, &status[ST_LBFAIL]);
     if (threadIdx.x == 0) { s_pb = pb; lb_store(&st_cnt[tile], LB_INC | (pb + htot)); }
   }
   __syncthreads();

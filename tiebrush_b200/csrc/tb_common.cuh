@@ -242,6 +242,46 @@ __global__ void __launch_bounds__(SCAN_THREADS) tb_scan_down_kernel(InF in, int6
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Decoupled look-back (single-pass device-wide prefixes): a tile publishes one 64-bit state word,
+// 2 flag bits | 62-bit payload: first its own aggregate (LB_AGG), then its inclusive prefix (LB_INC)
+// once its look-back over the predecessors is done. Tiles must take their ids from a ticket counter
+// so that every predecessor of a running tile is itself running or finished. The spin is bounded
+// and reports through *fail instead of hanging the device.
+// -------------------------------------------------------------------------------------------------
+constexpr unsigned long long LB_AGG = 1ULL << 62, LB_INC = 2ULL << 62, LB_MASK = (1ULL << 62) - 1ULL;
+
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+__device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+
+// exclusive prefix (max or sum of the 62-bit payloads) of the tiles before `tile`; called by one whole warp
+template <bool IS_MAX>
+__device__ unsigned long long lb_lookback(const unsigned long long* st, long long tile, long long* fail) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long acc = 0;   // identity of both operators (payloads are non-negative)
+  int spins = 0;
+  for (long long idx = tile - 1; idx >= 0; idx -= 32) {
+    const long long j = idx - lane;
+    unsigned long long w = j >= 0 ? lb_load(&st[j]) : LB_INC;   // before the first tile: an inclusive identity
+    while (__any_sync(0xffffffffu, (w >> 62) == 0)) {
+      if (++spins > (1 << 22)) { *fail = 1; break; }
+      if ((w >> 62) == 0) w = lb_load(&st[j]);
+    }
+    const unsigned inc = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+    const int first = inc ? __ffs(inc) - 1 : 32;
+    unsigned long long v = lane <= first ? (w & LB_MASK) : 0ULL;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
+      v = IS_MAX ? (v > o ? v : o) : v + o;
+    }
+    acc = IS_MAX ? (acc > v ? acc : v) : acc + v;
+    if (inc) break;
+  }
+  return acc;
+}
+
+
 struct OpSumU32 { typedef uint32_t T; __host__ __device__ static T identity() { return 0; } __host__ __device__ static T combine(T a, T b) { return a + b; } };
 struct OpSumI64 { typedef long long T; __host__ __device__ static T identity() { return 0; } __host__ __device__ static T combine(T a, T b) { return a + b; } };
 struct OpMaxU64 { typedef unsigned long long T; __host__ __device__ static T identity() { return 0; } __host__ __device__ static T combine(T a, T b) { return a > b ? a : b; } };
