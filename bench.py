@@ -41,6 +41,8 @@ def parse_args():
                     help="records of the secondary tiecov leg (0 = skip)")
     ap.add_argument("--cov-chroms", type=int, default=1, help="chromosomes of the tiecov leg's stream (C4 whole genome: 24)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--wire", default="compact", choices=["compact", "wide"],
+                    help="host column format of the e2e leg: compact = n_cigar8 + cigar16 (+cigar_ext), wide = cig_off + cigar (u32)")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("TB_BENCH_CPU_SAMPLE", 20_000_000)),
                     help="records of the cohort fed to the CPU baseline (bounded sample)")
     ap.add_argument("--cli-reads", type=int, default=int(os.environ.get("TB_BENCH_CLI_READS", 50_000)),
@@ -224,6 +226,16 @@ def main():
     from tiebrush_b200 import api, synth
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # keep this rank's host threads (and so its first-touch / pinned allocations) on the CPUs next to its GPU: with one
+    # process per GPU the host->device copies of the e2e leg otherwise cross the socket interconnect
+    numa = "unset"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        numa = f"nvml cpu affinity, {len(os.sched_getaffinity(0))} cpus"
+    except Exception as ex:   # not fatal: only the e2e leg's copy rate depends on it
+        numa = f"unset ({type(ex).__name__})"
     if world > 1:
         # keep stdout to the ONE JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -345,12 +357,16 @@ def main():
                                    + (f", -F {args.flag_mask}" if args.flag_mask else "") + ", one window per GPU",
                        "front_end_path": int(ctx.last_path()) if hasattr(ctx, "last_path") else None,
                        "records_per_step_per_gpu": n, "groups_out": G, "mean_cigar_ops": cbar, "l2": "inputs (>=20 GB at full size) exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"coordinate shards x{world}, no data-path collective", "gen_seconds": t_gen},
+                       "parallelism": f"coordinate shards x{world}, no data-path collective", "gen_seconds": t_gen, "host_affinity": numa},
             "roofline": roofline, "gpu_launches": int(launches),
             "stage_ms": dict(zip(("hist_scan", "slots_offsets", "tile", "compaction", "yd"), [float(x) for x in np.mean(np.asarray(stages), 0)]))}
     if tiecov_line is not None:
         line["tiecov"] = tiecov_line
 
+    # the CPU baseline's bounded sample is cut from the device-resident window before the e2e leg frees it
+    cpu_sub = None
+    if rank == 0 and world == 1 and args.cpu_sample > 0:
+        cpu_sub = synth.prefix_slice(cols, run_off, args.cpu_sample)
     # ---- end to end through the C ABI with host buffers ----
     host = None
     if not args.no_e2e:
@@ -358,11 +374,19 @@ def main():
         h2d = 0
         ok = 1
         try:   # pinned host copies of every input column (25 GB per rank at full size): all ranks must succeed, or all skip
-            for name in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar") + (("md_off", "md") if args.mode == 1 else ()):
-                t = cols[name]
+            del out, res   # 16 GB of device output columns at full size: not needed by the host-buffer leg
+            out = res = None
+            torch.cuda.empty_cache()
+            wire_cols = dict(cols)
+            names = ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar")
+            if args.wire == "compact":   # what a host packer would fill directly; built here from the wide columns
+                wire_cols["n_cigar8"], wire_cols["cigar16"], wire_cols["cigar_ext"] = api.compact_cigar_columns(cols["cig_off"], cols["cigar"])
+                names = ("pos", "flag", "mapq", "strand", "nh", "n_cigar8", "cigar16", "cigar_ext")
+            for name in names + (("md_off", "md") if args.mode == 1 else ()):
+                t = wire_cols[name]
                 ht = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
                 ht.copy_(t)
-                host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32, "md_off": np.uint32, "flag": np.uint16, "nh": np.uint16}.get(name, ht.numpy().dtype))
+                host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32, "md_off": np.uint32, "flag": np.uint16, "nh": np.uint16, "cigar16": np.uint16, "cigar_ext": np.uint32}.get(name, ht.numpy().dtype))
                 h2d += ht.numel() * ht.element_size()
             cap = max(G + 1024, 1)
             hout_t = dict(rep_index=torch.empty(cap, dtype=torch.int32, pin_memory=True), yc=torch.empty(cap, dtype=torch.float32, pin_memory=True),
@@ -376,13 +400,13 @@ def main():
             ok = int(t.item())
         if not ok:
             host = None
-            line["e2e"] = {"unavailable": "pinned host buffers for the end-to-end leg could not be allocated on every rank"}
+            line["e2e"] = {"unavailable": "host buffers for the end-to-end leg could not be prepared on every rank" + (": " + e2e_err if "e2e_err" in dir() else "")}
         else:
             host["n_cig"] = n_cig
             if args.mode == 1:
                 host["n_md"] = int(cols["n_md"])
             # the device-resident copy is not needed any more: the host path stages its own (full size: 25 GB each)
-            del cols, out, res
+            del cols, out, res, wire_cols
             torch.cuda.empty_cache()
             hout = {kk: v.numpy().view(np.uint32) if kk in ("rep_index", "yx") else v.numpy() for kk, v in hout_t.items()}
             es = max(1, min(args.steps, 3))
@@ -402,15 +426,15 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 e2e_ms = float(t.item())
             line["e2e"] = {"value": world * n / (e2e_ms / 1000.0), "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(16 * r2["n_groups"] + 128),
-                           "ms_per_step": e2e_ms, "steps": es, "wall_ms_per_step": 1000.0 * (time.perf_counter() - t0) / es}
+                           "ms_per_step": e2e_ms, "steps": es, "wall_ms_per_step": 1000.0 * (time.perf_counter() - t0) / es,
+                           "wire_format": args.wire + (" (n_cigar8 + cigar16 + cigar_ext; the device rebuilds cig_off / cigar inside the timed region)" if args.wire == "compact" else " (cig_off + cigar u32)")}
     sampler.stop_flag.set(); sampler.join(timeout=3)
     line["clocks"] = clocks.summary()
 
     # ---- CPU baseline: the oracle port on a bounded coordinate slice of the same window (rank 0, N=1 only) ----
-    if rank == 0 and world == 1 and args.cpu_sample > 0:
+    if cpu_sub is not None:
         from oracle import oracle
-        hostc = host if host is not None else synth.to_host({kk: cols[kk] for kk in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar") + (("md_off", "md") if args.mode == 1 else ())})
-        sub, sub_off = host_slice_sample(hostc, run_off, args.cpu_sample)
+        sub, sub_off = cpu_sub
         t0 = time.perf_counter()
         ro = oracle.collapse(sub, sub_off, mode=args.mode)
         dt = time.perf_counter() - t0

@@ -79,6 +79,16 @@ typedef struct {
   int64_t  n_cig;          /* words in `cigar` (== cig_off[n]); the packer knows it, the device need not sync */
   int64_t  n_md;           /* bytes in `md` (== md_off[n]), 0 when unused                         */
   int32_t  pos_lo, pos_hi; /* every record has pos in [pos_lo, pos_hi): the window the packer cut  */
+  /* Optional COMPACT WIRE FORMAT of the two CIGAR columns (host->device copies are the end-to-end bound: 24.8 -> 17.4 bytes
+   * per alignment on the synthetic cohort). Either replaces its wide counterpart when that one is NULL; the device
+   * rebuilds cig_off / cigar before anything else runs, so results are identical by construction.
+   *   n_cigar8  [n]       ops per record (every record < 256 ops)                       replaces cig_off
+   *   cigar16   [n_cig]   op | len << 4 per op, len < 4095; len field 0xFFF = the length  replaces cigar
+   *   cigar_ext [n_ext]   is the next entry of cigar_ext (full 28-bit lengths, in op order) */
+  const uint8_t*  n_cigar8;
+  const uint16_t* cigar16;
+  const uint32_t* cigar_ext;
+  int64_t  n_ext;
 } tb_soa_in;
 
 /* Collapsed groups of one window in FINAL OUTPUT ORDER (flushPData order, tiebrush.cpp:501-530).

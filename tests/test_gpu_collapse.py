@@ -281,3 +281,30 @@ def test_collapse_baseline_size_properties_and_oracle_prefix():
     assert np.array_equal(idx[torch.as_tensor(exp["rep_index"].astype(np.int64), device="cuda")].cpu().numpy(), rep[:Gs].cpu().numpy())
     assert np.array_equal(yc[:Gs].cpu().numpy(), exp["yc"]) and np.array_equal(yx[:Gs].cpu().numpy().view(np.uint32), exp["yx"])
     assert np.array_equal(yd[:Gs].cpu().numpy(), exp["yd"])
+
+
+@pytest.mark.parametrize("mode", [0, 3])
+def test_collapse_compact_wire_format_equals_wide(mode):
+    """n_cigar8 + cigar16 (+ cigar_ext for lengths >= 4095, here the long introns) must give exactly the wide-format result,
+    from host buffers and from device-resident tensors."""
+    import torch
+    from oracle import oracle
+    from tiebrush_b200 import api, synth
+    k = 16
+    cols, run_off, pr = synth.cohort_window(k, 20000, seed=17, n_tx=300, device="cpu")
+    host = synth.to_host(cols)
+    n8, c16, ext = api.compact_cigar_columns(host["cig_off"], host["cigar"])
+    assert len(ext) > 0 and c16.dtype == np.uint16 and n8.dtype == np.uint8
+    compact = {kk: host[kk] for kk in ("pos", "flag", "mapq", "strand", "nh")}
+    compact.update(n_cigar8=n8, cigar16=c16, cigar_ext=ext)
+    exp = oracle.collapse(host, run_off, mode=mode)
+    with api.Context(device=0, n_samples=k, mode=mode) as ctx:
+        wide = ctx.collapse_window(host, run_off)
+        got = ctx.collapse_window(compact, run_off)
+        dcols = {kk: torch.as_tensor(v.view(np.int16) if v.dtype == np.uint16 else (v.view(np.int32) if v.dtype == np.uint32 else v)).cuda() for kk, v in compact.items()}
+        dgot = ctx.collapse_window(dcols, run_off, pos_range=pr)
+    for key in ("rep_index", "yc", "yx", "yd"):
+        assert np.array_equal(np.asarray(got[key]), exp[key]), key
+        assert np.array_equal(np.asarray(got[key]), np.asarray(wide[key])), key
+        G = dgot["n_groups"]
+        assert np.array_equal(dgot[key][:G].cpu().numpy().view(np.asarray(exp[key]).dtype), exp[key]), key

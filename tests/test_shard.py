@@ -165,3 +165,20 @@ def test_sharded_gloo(what, world):
         assert p.exitcode == 0
     tag, ok, a, b = q.get(timeout=10)
     assert tag == what and ok and a > 0
+
+
+def test_compact_cigar_wire_format_round_trip():
+    """api.compact_cigar_columns: n_cigar8 / cigar16 / cigar_ext expand back to the wide CSR columns (the rule the device applies)."""
+    import numpy as np
+    from tiebrush_b200 import api, synth
+    cols, run_off, _ = synth.cohort_window(6, 5000, seed=2, n_tx=200, device="cpu")
+    host = synth.to_host(cols)
+    n8, c16, ext = api.compact_cigar_columns(host["cig_off"], host["cigar"])
+    off = np.zeros(len(n8) + 1, np.uint32); off[1:] = np.cumsum(n8)
+    esc = (c16 >> 4) == 0xFFF
+    ln = (c16 >> 4).astype(np.uint32)
+    ln[esc] = ext
+    wide = (c16 & 0xF).astype(np.uint32) | (ln << 4)
+    assert np.array_equal(off, host["cig_off"]) and np.array_equal(wide, host["cigar"]) and esc.sum() == len(ext) > 0
+    t8, t16, text = api.compact_cigar_columns(cols["cig_off"], cols["cigar"])   # torch path
+    assert np.array_equal(t8.numpy(), n8) and np.array_equal(t16.numpy().view(np.uint16), c16) and np.array_equal(text.numpy().view(np.uint32), ext)

@@ -21,7 +21,8 @@ class SoaIn(C.Structure):
                 ("strand", C.c_void_p), ("nh", C.c_void_p), ("cig_off", C.c_void_p), ("cigar", C.c_void_p),
                 ("md_off", C.c_void_p), ("md", C.c_void_p), ("qhash", C.c_void_p), ("yc_in", C.c_void_p),
                 ("yx_in", C.c_void_p), ("yd_in", C.c_void_p), ("on_device", C.c_int32),
-                ("n_cig", C.c_int64), ("n_md", C.c_int64), ("pos_lo", C.c_int32), ("pos_hi", C.c_int32)]
+                ("n_cig", C.c_int64), ("n_md", C.c_int64), ("pos_lo", C.c_int32), ("pos_hi", C.c_int32),
+                ("n_cigar8", C.c_void_p), ("cigar16", C.c_void_p), ("cigar_ext", C.c_void_p), ("n_ext", C.c_int64)]
 
 
 class GroupsOut(C.Structure):

@@ -21,6 +21,39 @@ class TieBrushError(RuntimeError):
     pass
 
 
+def compact_cigar_columns(cig_off, cigar):
+    """Host packer of the compact wire format: (n_cigar8, cigar16, cigar_ext) from the wide CSR columns (numpy or torch)."""
+    if _is_torch(cigar):   # chunked, 32-bit arithmetic on the bit patterns: a full-size window has 2.7e9 CIGAR words
+        import torch
+        n = int(cig_off.shape[0]) - 1
+        n8 = torch.empty(n, dtype=torch.uint8, device=cigar.device)
+        step = 1 << 27
+        for a0 in range(0, n, step):
+            a1 = min(n, a0 + step)
+            d = cig_off[a0 + 1:a1 + 1] - cig_off[a0:a1]          # wraps correctly in int32 (u32 bit patterns)
+            if int(d.max()) >= 256 or int(d.min()) < 0:
+                raise ValueError("a record with >= 256 CIGAR ops needs the wide format")
+            n8[a0:a1] = d.to(torch.uint8)
+        m = int(cigar.shape[0])
+        c16 = torch.empty(m, dtype=torch.int16, device=cigar.device)
+        exts = []
+        for a0 in range(0, m, step):
+            w = cigar[a0:a0 + step]
+            ln = (w >> 4) & 0x0FFFFFFF
+            esc = ln >= 0xFFF
+            c16[a0:a0 + step] = ((w & 0xF) | (torch.where(esc, torch.full_like(ln, 0xFFF), ln) << 4)).to(torch.int16)
+            exts.append(ln[esc])
+        return n8, c16, torch.cat(exts) if exts else torch.empty(0, dtype=torch.int32, device=cigar.device)
+    off = np.asarray(cig_off).astype(np.int64); w = np.asarray(cigar).astype(np.int64)
+    nc = off[1:] - off[:-1]
+    if len(nc) and nc.max() >= 256:
+        raise ValueError("a record with >= 256 CIGAR ops needs the wide format")
+    ln = w >> 4
+    esc = ln >= 0xFFF
+    c16 = ((w & 0xF) | (np.where(esc, 0xFFF, ln) << 4)).astype(np.uint16)
+    return nc.astype(np.uint8), c16, ln[esc].astype(np.uint32)
+
+
 def _is_torch(a):
     return hasattr(a, "data_ptr")
 
@@ -105,13 +138,16 @@ class Context:
         pos, flag, mapq = col("pos", np.int32), col("flag", np.uint16), col("mapq", np.uint8)
         strand, nh = col("strand", np.uint8), col("nh", np.uint16)
         cig_off, cigar = col("cig_off", np.uint32), col("cigar", np.uint32)
+        # compact wire format of the CIGAR columns (see include/tiebrush_b200.h); used when the wide column is absent
+        n8, c16, cext = col("n_cigar8", np.uint8), col("cigar16", np.uint16), col("cigar_ext", np.uint32)
         md_off, md = col("md_off", np.uint32), col("md", np.uint8)
         qh = col("qhash", np.uint64)
         fm = _host(file_merged, np.uint8) if file_merged is not None else None
         yc_in = col("yc_in", np.float32) if fm is not None else None
         yx_in = col("yx_in", np.int32) if fm is not None else None
         yd_in = col("yd_in", np.int32) if fm is not None else None
-        n_cig = int(cols["n_cig"]) if "n_cig" in cols else (int(cig_off[-1]) if n else 0)
+        n_cig = int(cols["n_cig"]) if "n_cig" in cols else (int(cig_off[-1]) if (n and cig_off is not None) else (int(c16.shape[0]) if c16 is not None else 0))
+        n_ext = int(cext.shape[0]) if cext is not None else 0
         n_md = int(cols["n_md"]) if "n_md" in cols else (int(md_off[-1]) if (md_off is not None and n) else 0)
         if pos_range is None:
             if dev:
@@ -119,7 +155,7 @@ class Context:
             pos_range = (int(pos.min()), int(pos.max()) + 1) if n else (0, 0)
         sin = _lib.SoaIn(n, k, tid, _ptr(run_off), _ptr(fm), _ptr(pos), _ptr(flag), _ptr(mapq), _ptr(strand), _ptr(nh),
                          _ptr(cig_off), _ptr(cigar), _ptr(md_off), _ptr(md), _ptr(qh), _ptr(yc_in), _ptr(yx_in), _ptr(yd_in),
-                         1 if dev else 0, n_cig, n_md, pos_range[0], pos_range[1])
+                         1 if dev else 0, n_cig, n_md, pos_range[0], pos_range[1], _ptr(n8), _ptr(c16), _ptr(cext), n_ext)
         cap = max(n, 1)
         if out is None:
             if dev:

@@ -39,6 +39,22 @@ __global__ void __launch_bounds__(256) col_hist_kernel(ColIn in, uint32_t* __res
   }
 }
 
+// compact wire format (tb_soa_in.n_cigar8 / cigar16 / cigar_ext): rebuild the wide CIGAR columns on the device
+struct Nc8In { const uint8_t* c; __device__ uint32_t operator()(int64_t i) const { return c[i]; } };
+struct OffOut {
+  uint32_t* off; int64_t n;
+  __device__ void operator()(int64_t i, uint32_t exc, uint32_t inc) const { off[i] = exc; if (i == n - 1) off[n] = inc; }
+};
+struct EscIn { const uint16_t* c; __device__ uint32_t operator()(int64_t j) const { return (c[j] >> 4) == 0xFFFu ? 1u : 0u; } };
+struct ExpandOut {
+  const uint16_t* c; const uint32_t* ext; uint32_t* out;
+  __device__ void operator()(int64_t j, uint32_t exc, uint32_t inc) const {
+    const uint32_t w = c[j];
+    const uint32_t len = inc != exc ? ext[exc] : (w >> 4);   // escaped length = the next entry of cigar_ext, in op order
+    out[j] = (w & 0xfu) | (len << 4);
+  }
+};
+
 struct HistIn { const uint32_t* c; __device__ uint32_t operator()(int64_t i) const { return c[i]; } };
 struct HistOut { uint32_t* p; __device__ void operator()(int64_t i, uint32_t exc, uint32_t) const { p[i] = exc; } };
 
@@ -75,8 +91,27 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
   if (tb_stage_in(ctx, ctx->in_stage[2], hin->mapq, (size_t)n, dev, &in.mapq)) return 1;
   if (tb_stage_in(ctx, ctx->in_stage[3], hin->strand, (size_t)n, dev, &in.strand)) return 1;
   if (tb_stage_in(ctx, ctx->in_stage[4], hin->nh, (size_t)n, dev, &in.nh)) return 1;
-  if (tb_stage_in(ctx, ctx->in_stage[5], hin->cig_off, (size_t)n + 1, dev, &in.cig_off)) return 1;
-  if (tb_stage_in(ctx, ctx->in_stage[6], hin->cigar, (size_t)hin->n_cig, dev, &in.cigar)) return 1;
+  if (!hin->cig_off && !hin->n_cigar8) { ctx->set_error("tb_collapse_window: neither cig_off nor n_cigar8 given"); return 1; }
+  if (!hin->cigar && !(hin->cigar16 && (hin->cigar_ext || hin->n_ext == 0))) { ctx->set_error("tb_collapse_window: neither cigar nor cigar16 (+cigar_ext) given"); return 1; }
+  if (hin->cig_off) { if (tb_stage_in(ctx, ctx->in_stage[5], hin->cig_off, (size_t)n + 1, dev, &in.cig_off)) return 1; }
+  else {   // offsets = exclusive scan of the per-record op counts
+    const uint8_t* n8 = nullptr;
+    if (tb_stage_in(ctx, ctx->in_stage[13], hin->n_cigar8, (size_t)n, dev, &n8)) return 1;
+    TB_CUDA(ctx->in_stage[5].ensure(sizeof(uint32_t) * ((size_t)n + 1) + 16));
+    TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks(n) + 8) * sizeof(uint64_t)));
+    TB_CUDA((tb_device_scan<OpSumU32>(ctx, Nc8In{n8}, n, B[XB_AGG].as<uint32_t>(), OffOut{ctx->in_stage[5].as<uint32_t>(), n})));
+    in.cig_off = ctx->in_stage[5].as<uint32_t>();
+  }
+  if (hin->cigar) { if (tb_stage_in(ctx, ctx->in_stage[6], hin->cigar, (size_t)hin->n_cig, dev, &in.cigar)) return 1; }
+  else {   // 16-bit ops widened to BAM words, escaped lengths taken from cigar_ext in op order
+    const uint16_t* c16 = nullptr; const uint32_t* ext = nullptr;
+    if (tb_stage_in(ctx, ctx->in_stage[14], hin->cigar16, (size_t)hin->n_cig, dev, &c16)) return 1;
+    if (hin->n_ext > 0) { if (tb_stage_in(ctx, ctx->in_stage[15], hin->cigar_ext, (size_t)hin->n_ext, dev, &ext)) return 1; }
+    TB_CUDA(ctx->in_stage[6].ensure(sizeof(uint32_t) * ((size_t)hin->n_cig + 4) + 16));
+    TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks(hin->n_cig) + 8) * sizeof(uint64_t)));
+    TB_CUDA((tb_device_scan<OpSumU32>(ctx, EscIn{c16}, hin->n_cig, B[XB_AGG].as<uint32_t>(), ExpandOut{c16, ext, ctx->in_stage[6].as<uint32_t>()})));
+    in.cigar = ctx->in_stage[6].as<uint32_t>();
+  }
   if (ctx->mode == TB_MODE_FULL) {
     if (tb_stage_in(ctx, ctx->in_stage[7], hin->md_off, (size_t)n + 1, dev, &in.md_off)) return 1;
     if (tb_stage_in(ctx, ctx->in_stage[8], hin->md, (size_t)hin->n_md, dev, &in.md)) return 1;

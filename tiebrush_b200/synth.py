@@ -196,6 +196,38 @@ def md_columns_torch(cols, chunk=32_000_000):
     return off.to(torch.int32), md, int(off[-1])
 
 
+def prefix_slice(cols, run_off, target):
+    """Coordinate prefix of a (device-resident) window holding about `target` records: every file's records with pos < hi,
+    gathered on the columns' device and returned as HOST columns + the new run offsets (CPU baseline / oracle checks)."""
+    dev = cols["pos"].device
+    n = int(cols["pos"].shape[0])
+    a0, b0 = int(run_off[0]), int(run_off[1])
+    frac = min(1.0, target / max(n, 1))
+    hi = int(cols["pos"][a0 + min(b0 - a0 - 1, int((b0 - a0) * frac))].item()) if frac < 1.0 else int(cols["pos"].max().item()) + 1
+    parts, new_off = [], [0]
+    for f in range(len(run_off) - 1):
+        a, b = int(run_off[f]), int(run_off[f + 1])
+        c = a + int(torch.searchsorted(cols["pos"][a:b], torch.tensor([hi], device=dev, dtype=cols["pos"].dtype))[0])
+        parts.append(torch.arange(a, c, device=dev))
+        new_off.append(new_off[-1] + (c - a))
+    idx = torch.cat(parts)
+    sub = {k: cols[k][idx].cpu().numpy() for k in ("pos", "flag", "mapq", "strand", "nh")}
+    sub["flag"] = sub["flag"].view(np.uint16); sub["nh"] = sub["nh"].view(np.uint16)
+
+    def gather_csr(off_key, arena_key):
+        c0 = cols[off_key][idx].long() & 0xFFFFFFFF
+        ln = (cols[off_key][idx + 1].long() & 0xFFFFFFFF) - c0
+        off = torch.zeros(len(idx) + 1, dtype=torch.long, device=dev); off[1:] = torch.cumsum(ln, 0)
+        rep = torch.repeat_interleave(torch.arange(len(idx), device=dev), ln)
+        src = c0[rep] + (torch.arange(int(off[-1]), device=dev) - off[:-1][rep])
+        return off.cpu().numpy().astype(np.uint32), cols[arena_key][src].cpu().numpy()
+
+    sub["cig_off"], cig = gather_csr("cig_off", "cigar"); sub["cigar"] = cig.view(np.uint32)
+    if "md_off" in cols:
+        sub["md_off"], md = gather_csr("md_off", "md"); sub["md"] = md.view(np.uint8)
+    return sub, np.asarray(new_off, np.int64)
+
+
 def _cat_csr(parts, key_off="cig_off", key_arena="cigar"):
     offs, base = [torch.zeros(1, dtype=torch.int64, device=parts[0][key_off].device)], 0
     for p in parts:
