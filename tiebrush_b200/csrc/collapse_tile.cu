@@ -60,34 +60,31 @@ __global__ void __launch_bounds__(256) col_off_init_kernel(uint32_t* __restrict_
   off[x] = (uint32_t)run_off[f + 1];
 }
 
+// A record whose position differs from its predecessor's moves its file's cursor into a later slot only when the two
+// positions lie in different slots — one record in ~T/k — so the slots are compared first and the file is looked up
+// (binary search over the k run offsets) only for those records and at the k-1 run boundaries. Run starts themselves are
+// written by col_off_heads_kernel.
 __global__ void __launch_bounds__(256) col_off_kernel(ColIn in, const long long* __restrict__ run_off, const uint32_t* __restrict__ P, uint32_t T,
                                                       uint32_t* __restrict__ off, long long* __restrict__ status) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= in.n) return;
+  if (i >= in.n || i == 0) return;
   const int32_t p = in.pos[i];
   const uint32_t rel = (uint32_t)(p - in.pos_lo);
   if (rel >= in.span) return;  // already reported by C1
-  int64_t sprev = -1;
-  bool first = false;
-  int f = -1;
-  if (i > 0) {
-    const int32_t pp = in.pos[i - 1];
-    if (pp == p) return;                       // same position as the previous record: same slot, and if i starts a run the
-                                               // check below would need f; handle run starts explicitly
-    // different position: either a file boundary or a forward step inside the file
-    int lo = 0, hi = in.k;                     // run containing i: last f with run_off[f] <= i
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (run_off[mid] <= i) lo = mid; else hi = mid; }
-    f = lo;
-    first = (i == run_off[f]);
-    if (!first) {
-      if (pp > p) { status[CS_ERR] = ERR_UNSORTED; atomicMin((unsigned long long*)&status[CS_ERRIDX], (unsigned long long)i); return; }
-      const uint32_t prel = (uint32_t)(pp - in.pos_lo);
-      if (prel >= in.span) return;
-      sprev = (int64_t)(P[prel] / T);
-    }
-  } else { f = 0; while (f + 1 < in.k && run_off[f + 1] <= 0) ++f; first = true; }
-  (void)first;
-  const int64_t scur = (int64_t)(P[rel] / T);
+  const int32_t pp = in.pos[i - 1];
+  if (pp == p) return;
+  int64_t sprev = 0, scur = 0;
+  if (pp < p) {
+    const uint32_t prel = (uint32_t)(pp - in.pos_lo);
+    if (prel >= in.span) return;
+    sprev = (int64_t)(P[prel] / T); scur = (int64_t)(P[rel] / T);
+    if (scur <= sprev) return;                 // same slot: nothing moves
+  }
+  int lo = 0, hi = in.k;                       // run containing i: last f with run_off[f] <= i
+  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (run_off[mid] <= i) lo = mid; else hi = mid; }
+  const int f = lo;
+  if (i == run_off[f]) return;                 // a run start: col_off_heads_kernel
+  if (pp > p) { status[CS_ERR] = ERR_UNSORTED; atomicMin((unsigned long long*)&status[CS_ERRIDX], (unsigned long long)i); return; }
   for (int64_t s = sprev + 1; s <= scur; ++s) off[(uint64_t)s * in.k + f] = (uint32_t)i;
 }
 
