@@ -19,7 +19,8 @@
 //       last_pos cache).
 //   So: Y1 group descriptors + union bitmap U of all exon positions; Y2 rank(U) gives compact coordinates (runs of links
 //   are preserved: a link at p implies p+1 is covered); Y3-Y5 chain member lists by a stable counting scatter over the
-//   sample bitsets, cut into independent sub-chains where a member starts beyond every earlier end of its chain;
+//   sample bitsets, cut into independent sub-chains where a member starts beyond every earlier end of its chain (one
+//   single-pass look-back kernel: segmented prefix max of the ends, head test, head list);
 //   Y6 the frontier recurrence per sub-chain (one scalar, lane-parallel; long sub-chains are walked by a whole warp with
 //   prefetch) -> kept-exon count per member; Y7 kept exons OR their links into the chain's bitmap; Y8 prefix max of
 //   "last clear link" over 512-bit blocks; Y9 one lookup per member, atomicMax into the group.
@@ -193,27 +194,6 @@ __global__ void __launch_bounds__(256) yd_fill_mchain_kernel(const unsigned long
     while (c + 1 < nchains && colbase[c + 1] <= i) ++c;
     mchain[i] = (uint16_t)c;
   }
-}
-
-// sub-chain heads: prefix max of (chain<<32 | end) over the member array is a segmented prefix max (chain ids ascend).
-// mchain[i] = chain of member i (written by the scatter); flag[i] = head | chain << 1 for the later stages.
-struct MemberKeyIn {
-  const uint32_t* chain; const uint32_t* gend; const uint16_t* mchain;
-  __device__ unsigned long long operator()(int64_t i) const { return ((unsigned long long)mchain[i] << 32) | gend[chain[i]]; }
-};
-struct MemberHeadOut {
-  MemberKeyIn mk; const uint32_t* gstart; uint32_t* flag;
-  __device__ void operator()(int64_t i, unsigned long long exc, unsigned long long) const {
-    const uint32_t c = mk.mchain[i];
-    uint32_t h = 1u;
-    if (i > 0 && (uint32_t)(exc >> 32) == c) h = gstart[mk.chain[i]] > (uint32_t)exc ? 1u : 0u;
-    flag[i] = h | (c << 1);
-  }
-};
-struct FlagIn { const uint32_t* f; __device__ uint32_t operator()(int64_t i) const { return f[i] & 1u; } };
-struct HeadListOut { uint32_t* heads; __device__ void operator()(int64_t i, uint32_t exc, uint32_t inc) const { if (inc != exc) heads[exc] = (uint32_t)i; } };
-__global__ void yd_subchain_total_kernel(const uint32_t* tot, uint32_t* heads, uint32_t n_members, unsigned long long* work) {
-  heads[*tot] = n_members; work[0] = 0; work[1] = *tot;
 }
 
 // Y5 in ONE pass over the members (decoupled look-back, see tb_common.cuh): the segmented prefix maximum of the group ends

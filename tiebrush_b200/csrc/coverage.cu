@@ -1,7 +1,8 @@
 // coverage.cu — tiecov's hot path on the device (reference src/tiecov.cpp:62-120, 194-241, 435-528).
 //
 //   K6  bundle breaks   : prefix-max of (tid,end) over the record stream; a record opens a bundle iff its
-//                         tid differs from, or its start exceeds, the running max end   (tiecov.cpp:443)
+//                         tid differs from, or its start exceeds, the running max end   (tiecov.cpp:443);
+//                         one pass with decoupled look-back (cov_bundle_kernel)
 //   K7  coverage        : difference array over BUNDLE-COMPACTED coordinates (gaps between bundles are
 //                         skipped; one sentinel cell closes each bundle), +w at every M-block start and
 //                         -w one past its end, 64-bit fixed-point atomics                (addCov :194-223)
