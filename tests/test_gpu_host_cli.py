@@ -99,10 +99,12 @@ def test_tiebrush_cli_matches_reference(sams, opts):
 def test_tiebrush_cli_small_windows_and_collapse_same(sams):
     """Many small windows (cut at coverage gaps) must give the same bytes as one window; -A on recycled read names."""
     tmp, paths, paired = sams
-    for name, files, opts in (("w", paths, []), ("a", paired, ["-A"]), ("af", paired, ["-A", "-F", "192"])):
+    for name, files, opts, extra in (("w", paths, [], {}), ("a", paired, ["-A"], {}), ("af", paired, ["-A", "-F", "192"], {}),
+                                     ("ww", paths, ["-E"], {"TB_WIRE_WIDE": "1"})):   # the last one: wide CIGAR columns instead of the compact wire format
         ref_out, our_out = os.path.join(tmp, f"ref_{name}.bam"), os.path.join(tmp, f"gpu_{name}.bam")
         _run([os.path.join(REF, "tiebrush")] + opts + ["-o", ref_out] + files)
-        msg = _run([os.path.join(HOST, "tiebrush_gpu")] + opts + ["-o", our_out] + files, env={"TB_WINDOW_RECORDS": "300", "TB_WINDOW_SPAN": "2000", "TB_DECODE_THREADS": "3", "TB_TIMING": "1"})
+        msg = _run([os.path.join(HOST, "tiebrush_gpu")] + opts + ["-o", our_out] + files,
+                   env=dict({"TB_WINDOW_RECORDS": "300", "TB_WINDOW_SPAN": "2000", "TB_DECODE_THREADS": "3", "TB_TIMING": "1"}, **extra))
         assert _records(our_out) == _records(ref_out)
         assert "windows" in msg
 

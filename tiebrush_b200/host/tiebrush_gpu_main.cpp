@@ -58,7 +58,8 @@ struct TbWindowPacker {
   std::vector<int32_t> pos, yx_in, yd_in;
   std::vector<uint16_t> flag, nh;
   std::vector<uint8_t> mapq, strand, md;
-  std::vector<uint32_t> cig_off, cigar, md_off;
+  std::vector<uint32_t> cig_off, cigar, md_off, cigar_ext;
+  std::vector<uint8_t> n_cigar8; std::vector<uint16_t> cigar16;   // compact wire format of the CIGAR columns (tiebrush_b200.h)
   std::vector<uint64_t> qhash;
   std::vector<float> yc_in;
   std::vector<GSamRecord*> held;                    // window index -> record
@@ -88,6 +89,8 @@ struct TbWindowPacker {
     run_off.assign(k + 1, 0);
     pos.resize(n); flag.resize(n); mapq.resize(n); strand.resize(n); nh.resize(n); cig_off.resize(n + 1);
     cigar.clear(); held.resize(n);
+    n_cigar8.resize(n); cigar16.clear(); cigar_ext.clear();
+    bool compact = getenv("TB_WIRE_WIDE") == NULL;   // falls back to the wide columns when a record has >= 256 ops
     if (want_md) { md_off.resize(n + 1); md.clear(); }
     if (want_q) qhash.resize(n);
     if (any_merged) { yc_in.resize(n); yx_in.resize(n); yd_in.resize(n); }
@@ -109,6 +112,15 @@ struct TbWindowPacker {
         cig_off[i] = (uint32_t)cigar.size();
         const uint32_t* c = bam_get_cigar(b);
         cigar.insert(cigar.end(), c, c + b->core.n_cigar);
+        if (b->core.n_cigar >= 256) compact = false;
+        if (compact) {
+          n_cigar8[i] = (uint8_t)b->core.n_cigar;
+          for (uint32_t q = 0; q < b->core.n_cigar; ++q) {
+            const uint32_t len = c[q] >> 4;
+            if (len >= 0xFFFu) { cigar16.push_back((uint16_t)((c[q] & 0xfu) | (0xFFFu << 4))); cigar_ext.push_back(len); }
+            else cigar16.push_back((uint16_t)((c[q] & 0xfu) | (len << 4)));
+          }
+        }
         if (want_md) {
           md_off[i] = (uint32_t)md.size();
           const char* m = r->tag_str("MD");                          // cmpFull, tiebrush.cpp:285-304
@@ -127,12 +139,15 @@ struct TbWindowPacker {
     cig_off[n] = (uint32_t)cigar.size();
     if (want_md) md_off[n] = (uint32_t)md.size();
     if (cigar.empty()) cigar.push_back(0);
+    if (cigar16.empty()) cigar16.push_back(0);
     if (want_md && md.empty()) md.push_back(0);
 
     tb_soa_in in; memset(&in, 0, sizeof(in));
     in.n = (int64_t)n; in.n_files = k; in.tid = tid; in.run_off = run_off.data(); in.file_merged = any_merged ? file_merged.data() : NULL;
     in.pos = pos.data(); in.flag = flag.data(); in.mapq = mapq.data(); in.strand = strand.data(); in.nh = nh.data();
-    in.cig_off = cig_off.data(); in.cigar = cigar.data(); in.n_cig = (int64_t)cig_off[n];
+    in.n_cig = (int64_t)cig_off[n];
+    if (compact) { in.n_cigar8 = n_cigar8.data(); in.cigar16 = cigar16.data(); in.cigar_ext = cigar_ext.empty() ? NULL : cigar_ext.data(); in.n_ext = (int64_t)cigar_ext.size(); }
+    else { in.cig_off = cig_off.data(); in.cigar = cigar.data(); }
     if (want_md) { in.md_off = md_off.data(); in.md = md.data(); in.n_md = (int64_t)md_off[n]; }
     if (want_q) in.qhash = qhash.data();
     if (any_merged) { in.yc_in = yc_in.data(); in.yx_in = yx_in.data(); in.yd_in = yd_in.data(); }
