@@ -662,7 +662,15 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
     if (thr == 1024) { if (dflt) TB_TILE_LAUNCH(1024, TB_MODE_CIGAR); else TB_TILE_LAUNCH(1024, -1); }
     else if (thr == 512) { if (dflt) TB_TILE_LAUNCH(512, TB_MODE_CIGAR); else TB_TILE_LAUNCH(512, -1); }
     else if (thr == 128) { if (dflt) TB_TILE_LAUNCH(128, TB_MODE_CIGAR); else TB_TILE_LAUNCH(128, -1); }
-    else { if (dflt) TB_TILE_LAUNCH(256, TB_MODE_CIGAR); else TB_TILE_LAUNCH(256, -1); }
+    else {   // the default geometry has one instantiation per merge strategy
+      switch (in.mode) {
+        case TB_MODE_CIGAR: TB_TILE_LAUNCH(256, TB_MODE_CIGAR); break;
+        case TB_MODE_FULL: TB_TILE_LAUNCH(256, TB_MODE_FULL); break;
+        case TB_MODE_CLIP: TB_TILE_LAUNCH(256, TB_MODE_CLIP); break;
+        case TB_MODE_EXON: TB_TILE_LAUNCH(256, TB_MODE_EXON); break;
+        default: TB_TILE_LAUNCH(256, -1); break;
+      }
+    }
 #undef TB_TILE_LAUNCH
     ctx->launches++;
     return cudaGetLastError();
