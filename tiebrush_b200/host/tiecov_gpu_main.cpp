@@ -91,22 +91,18 @@ int main(int argc, char* argv[]) {
   if (bigwig) GError("Error: -W (BigWig) is not available in tiecov_gpu (libBigWig is not part of the device path)\n");
   if (!sfname.is_empty()) GError("Error: -s (sample heat-map) is not available in tiecov_gpu yet; use -c / -j\n");
   GSamReader samreader(infname.chars(), SAM_QNAME | SAM_FLAG | SAM_RNAME | SAM_POS | SAM_CIGAR | SAM_AUX);
-  // output files: names, suffixes and track lines exactly as tiecov.cpp:352-411
-  if (!covfname.is_empty()) {
-    if (covfname == "-" || covfname == "stdout") coutf = stdout;
-    else {
-      if (std::strcmp(covfname.substr(covfname.length() - 9, 9).chars(), ".bedgraph") != 0) covfname.append(".bedgraph");
-      coutf = fopen(covfname.chars(), "w");
-      if (coutf == NULL) GError("Error creating file %s\n", covfname.chars());
-      fprintf(coutf, "track type=bedGraph\n");
-    }
-  }
-  if (!jfname.is_empty()) {
-    if (std::strcmp(jfname.substr(jfname.length() - 4, 4).chars(), ".bed") != 0) jfname.append(".bed");
-    joutf = fopen(jfname.chars(), "w");
-    if (joutf == NULL) GError("Error creating file %s\n", jfname.chars());
-    fprintf(joutf, "track name=junctions\n");
-  }
+  // output files: same naming rule (suffix appended unless already there), same track lines as tiecov.cpp:352-411
+  auto open_track = [](GStr& name, const char* suffix, const char* track_line) -> FILE* {
+    const int sl = (int)strlen(suffix);
+    if (name.length() < sl || strcmp(name.chars() + name.length() - sl, suffix) != 0) name.append(suffix);
+    FILE* f = fopen(name.chars(), "w");
+    if (f == NULL) GError("Error creating file %s\n", name.chars());
+    fputs(track_line, f);
+    return f;
+  };
+  if (!covfname.is_empty())
+    coutf = (covfname == "-" || covfname == "stdout") ? stdout : open_track(covfname, ".bedgraph", "track type=bedGraph\n");
+  if (!jfname.is_empty()) joutf = open_track(jfname, ".bed", "track name=junctions\n");
   const char* dev_env = getenv("TB_DEVICE");
   tb_ctx* ctx = tb_create(dev_env ? atoi(dev_env) : 0, 1, TB_MODE_CIGAR, 0, TB_NO_MAX_NH, -1, 0, 0);
   if (!ctx) GError("%s\n", tb_last_error(NULL));
