@@ -182,3 +182,27 @@ def test_compact_cigar_wire_format_round_trip():
     assert np.array_equal(off, host["cig_off"]) and np.array_equal(wide, host["cigar"]) and esc.sum() == len(ext) > 0
     t8, t16, text = api.compact_cigar_columns(cols["cig_off"], cols["cigar"])   # torch path
     assert np.array_equal(t8.numpy(), n8) and np.array_equal(t16.numpy().view(np.uint16), c16) and np.array_equal(text.numpy().view(np.uint32), ext)
+
+
+def test_prefix_slice_is_a_coordinate_prefix_of_every_file():
+    """synth.prefix_slice (the bench's CPU-baseline sample and the full-size tests' oracle prefix): every file contributes
+    exactly its records below one coordinate, CSR columns stay consistent, and the oracle on the slice equals the head of
+    the oracle on the whole window (groups and YD only look left)."""
+    import numpy as np
+    from oracle import oracle
+    from tiebrush_b200 import synth
+    cols, run_off, _ = synth.cohort_window(7, 3000, seed=8, n_tx=60, device="cpu")
+    host = synth.to_host(cols)
+    sub, sub_off = synth.prefix_slice(cols, run_off, 6000)
+    hi = int(sub["pos"].max()) + 1
+    assert len(sub_off) == len(run_off) and sub_off[-1] == len(sub["pos"]) == int(sub["cig_off"].shape[0]) - 1
+    for f in range(len(run_off) - 1):
+        a, b = int(run_off[f]), int(run_off[f + 1])
+        want = host["pos"][a:b]
+        m = int(sub_off[f + 1] - sub_off[f])
+        assert np.array_equal(sub["pos"][sub_off[f]:sub_off[f + 1]], want[:m]) and (m == b - a or want[m] >= hi)
+    full, part = oracle.collapse(host, run_off), oracle.collapse(sub, sub_off)
+    g = len(part["rep_index"])
+    assert 0 < g < len(full["rep_index"])
+    for key in ("yc", "yx", "yd"):
+        assert np.array_equal(part[key], full[key][:g]), key
