@@ -129,3 +129,33 @@ def coverage(cols: dict, want_runs=True, want_juncs=True, cap_runs=None):
     r, j = runs.n_runs, juncs.n_juncs
     return dict(runs=(rt[:r].copy(), rs[:r].copy(), re[:r].copy(), rv[:r].copy()),
                 juncs=(jt[:j].copy(), js[:j].copy(), je[:j].copy(), jc[:j].copy(), jv[:j].copy()))
+
+
+def sample_heatmap(cols: dict, cap_runs=None):
+    """Oracle tiecov -s of one stream (GROUNDWORK for SURVEY §8f.2, no device path yet): rows (tid, start0, end0, ival) of the
+    sample-count heat-map; `cols` needs tid, pos, yx (YX tag, 1 when absent), cig_off, cigar. hval of a row is
+    heatmap_value(ival, n_samples)."""
+    n = len(cols["pos"])
+    a = dict(tid=_c(cols["tid"], np.int32), pos=_c(cols["pos"], np.int32), yx=_c(cols["yx"], np.int32),
+             cig_off=_c(cols["cig_off"], np.uint32), cigar=_c(cols["cigar"], np.uint32))
+    ncig = int(a["cig_off"][-1]) if n else 0
+    cin = _CovIn(n, _p(a["tid"]), _p(a["pos"]), None, None, _p(a["cig_off"]), _p(a["cigar"]), 0, ncig)
+    cap = cap_runs if cap_runs is not None else 2 * ncig + 16
+    rt = np.zeros(cap, np.int32); rs = np.zeros(cap, np.int32); re = np.zeros(cap, np.int32); rv = np.zeros(cap, np.uint64)
+    nout, bad = C.c_int64(0), C.c_int64(-1)
+    f = lib().tbo_sample_heatmap
+    f.restype = C.c_int
+    vp = lambda x: C.c_void_p(_p(x))   # bare pointer arguments: ctypes would truncate plain ints to 32 bits
+    rc = f(C.byref(cin), vp(a["yx"]), C.c_int64(cap), C.byref(nout), vp(rt), vp(rs), vp(re), vp(rv), C.byref(bad))
+    if rc == 2:
+        raise ValueError(f"unsupported CIGAR op in record {bad.value}")
+    if rc != 0:
+        raise RuntimeError(f"tbo_sample_heatmap rc={rc}")
+    r = nout.value
+    return rt[:r].copy(), rs[:r].copy(), re[:r].copy(), rv[:r].copy()
+
+
+def heatmap_value(ival, n_samples):
+    """normalize(bsam, 0.1, 1.5, n_samples) of src/tiecov.cpp:311-318 in float32, as printed with %f."""
+    mult = np.float32(np.float32(1.5) - np.float32(0.1))
+    return np.float32(np.float32(np.float32(ival) / np.float32(n_samples)) * mult + np.float32(0.1))

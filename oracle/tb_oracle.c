@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+#include <math.h>
 #include "../include/tiebrush_b200.h"
 
 typedef struct {
@@ -487,5 +488,83 @@ int tbo_coverage(const tc_soa_in* in, tc_runs_out* runs, tc_juncs_out* jout, int
   }
   if (!rc && prev_tid >= 0) { if (flush_coverage(&S, prev_tid, b_start) || flush_juncs(&S, prev_tid)) rc = 1; }
   free(ex); free(S.bcov); free(S.juncs);
+  return rc;
+}
+
+
+/* ---- tiecov -s (sample heat-map), src/tiecov.cpp:155-185 (addMean), :277-323 (flushCoverage of the pair vector, discretize,
+ * normalize) and the main loop :443-499. GROUNDWORK for SURVEY §8f.2: the device path for -s does not exist yet; this
+ * restatement is pinned against the compiled reference (tests/test_oracle.py) so that the next round starts from a
+ * checked oracle. Per base of a bundle the reference keeps pair<float,uint64_t>{0,1}: for every covering record, in stream
+ * order, first += ((int)YX - first) / second (float arithmetic, second converted to float), second++. At the bundle flush:
+ * second = ceil(first), then runs of equal `second` (non-zero) are printed as chr, start0, end0, second, hval with
+ * hval = ((float)second / n_samples) * (1.5f - 0.1f) + 0.1f. Outputs here: one row per run (tid, start0, end0, ival). */
+int tbo_sample_heatmap(const tc_soa_in* in, const int32_t* yx, int64_t capacity, int64_t* n_out, int32_t* o_tid, int32_t* o_start,
+                       int32_t* o_end, uint64_t* o_ival, int64_t* bad_rec) {
+  if (in->on_device) return -1;
+  float* mean = NULL; uint64_t* cnt = NULL; int64_t bcount = 0, bcap = 0;
+  int prev_tid = -1, b_end = 0, b_start = 0, rc = 0;
+  int64_t nout = 0;
+  int64_t maxc = 1;
+  for (int64_t i = 0; i < in->n; i++) { int64_t c = (int64_t)in->cig_off[i + 1] - in->cig_off[i]; if (c > maxc) maxc = c; }
+  seg_t* ex = (seg_t*)malloc(sizeof(seg_t) * (size_t)(maxc + 1));
+#define TBO_FLUSH_SAMPLE()                                                                                              \
+  do {                                                                                                                  \
+    int64_t x = 0;                                                                                                      \
+    while (x < bcount) { /* discretize + flushCoverage(pair vector) */                                                  \
+      uint64_t iv = (uint64_t)ceilf(mean[x]);                                                                           \
+      int64_t y = x + 1;                                                                                                \
+      while (y < bcount && (uint64_t)ceilf(mean[y]) == iv) y++;                                                         \
+      if (iv != 0) {                                                                                                    \
+        if (nout >= capacity) { rc = 1; break; }                                                                        \
+        o_tid[nout] = prev_tid; o_start[nout] = (int32_t)(b_start - 1 + x); o_end[nout] = (int32_t)(b_start - 1 + y);   \
+        o_ival[nout] = iv; nout++;                                                                                      \
+      }                                                                                                                 \
+      x = y;                                                                                                            \
+    }                                                                                                                   \
+  } while (0)
+#define TBO_RESIZE_SAMPLE(newn)                                                                                         \
+  do {                                                                                                                  \
+    int64_t nn = (newn);                                                                                                \
+    if (nn > bcap) { bcap = nn * 2 + 1024; mean = (float*)realloc(mean, sizeof(float) * (size_t)bcap);                  \
+                     cnt = (uint64_t*)realloc(cnt, sizeof(uint64_t) * (size_t)bcap); }                                  \
+    for (int64_t q = bcount; q < nn; q++) { mean[q] = 0.f; cnt[q] = 1; }                                                 \
+    bcount = nn;                                                                                                        \
+  } while (0)
+  for (int64_t i = 0; i < in->n && !rc; i++) {
+    const uint32_t* cig = in->cigar + in->cig_off[i]; uint32_t nc = in->cig_off[i + 1] - in->cig_off[i];
+    uint32_t start, end; (void)setup_coordinates(in->pos[i], cig, nc, ex, &start, &end);
+    int tid = in->tid[i];
+    if (tid != prev_tid || (int)start > b_end) { /* :443 */
+      if (prev_tid >= 0) { TBO_FLUSH_SAMPLE(); if (rc) break; }
+      b_start = (int)start; b_end = (int)end;
+      bcount = 0; TBO_RESIZE_SAMPLE((int64_t)b_end - b_start + 1);
+      prev_tid = tid;
+    } else if (b_end < (int)end) { b_end = (int)end; TBO_RESIZE_SAMPLE((int64_t)b_end - b_start + 1); }
+    if (nc >= 256) { rc = 2; if (bad_rec) *bad_rec = i; break; } /* uint8_t loop counter, :158 */
+    int val = yx[i];
+    int pos = in->pos[i]; int bs = b_start - 1;
+    for (uint32_t c = 0; c < nc && !rc; c++) { /* addMean :155-185 */
+      uint32_t op = cig[c] & 0xf; int len = (int)(cig[c] >> 4);
+      switch (op) {
+        case 1: case 4: break;
+        case 2: case 3: pos += len; break;
+        case 0:
+          for (int q = 0; q < len; q++) {
+            int64_t x = pos - bs;
+            mean[x] += ((float)val - mean[x]) / (float)cnt[x];   /* (val - first): int converted to float, / uint64 converted to float */
+            cnt[x]++;
+            pos++;
+          }
+          break;
+        default: rc = 2; if (bad_rec) *bad_rec = i; break;
+      }
+    }
+  }
+  if (!rc && prev_tid >= 0) TBO_FLUSH_SAMPLE();
+#undef TBO_FLUSH_SAMPLE
+#undef TBO_RESIZE_SAMPLE
+  free(ex); free(mean); free(cnt);
+  *n_out = nout;
   return rc;
 }
