@@ -167,6 +167,14 @@ int tb_collapse_window(tb_ctx*, const tb_soa_in* in, tb_groups_out* out);
  * reference aborts on (tiecov.cpp:219-220). */
 int tc_coverage_window(tb_ctx*, const tc_soa_in* in, tc_runs_out* runs, tc_juncs_out* juncs);
 
+/* ---- tiecov -s: sample heat-map of one window -------------------------------- */
+/* replaces addMean + discretize + flushCoverage(pair vector) (tiecov.cpp:155-185, 277-309). `yx` [n] = YX tag of every
+ * record (1 when absent, tiecov.cpp:495), host or device like the other columns. rows: runs of equal, non-zero
+ * ceil(running mean of YX) per bundle, in file order; value[i] is that integer. The caller prints
+ * "chr\tstart0\tend0\t%ld\t%f" with hval = ((float)value / n_samples) * (1.5f - 0.1f) + 0.1f (normalize, :311-318),
+ * n_samples = number of @CO SAMPLE lines of the header (load_sample_info, commons.h). */
+int tc_sample_window(tb_ctx*, const tc_soa_in* in, const int32_t* yx, tc_runs_out* rows);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Kernels launched by this library since the context was created (for bench.py's gpu_launches). */
 int64_t tb_launch_count(tb_ctx*);

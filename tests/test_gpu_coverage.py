@@ -1,5 +1,7 @@
 """GPU parity tests (through the C ABI): tiecov coverage / junction / bedgraph kernels vs the oracle and
 vs golden outputs of the compiled reference."""
+import os
+
 import numpy as np
 import pytest
 
@@ -140,4 +142,30 @@ def test_coverage_unaligned_columns_take_the_scalar_path(ctx, monkeypatch):
     cols = synth.to_host(synth.coverage_stream(60_001, seed=21, n_tx=40, chroms=3))
     got, exp = ctx.coverage_window(cols), oracle.coverage(cols)
     for a, b in zip(got["runs"] + got["juncs"], exp["runs"] + exp["juncs"]):
+        assert np.array_equal(np.asarray(a), b)
+
+
+@pytest.mark.parametrize("case", ["t1", "t2"])
+def test_sample_heatmap_golden(ctx, case):
+    """tiecov -s on the device against the reference's own fixtures (columns 1-4 of test/t{1,2}/t{1,2}.sample.bedgraph)."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sample_heatmap.npz"))
+    cols = {k: z[f"{case}/in/{k}"] for k in ("tid", "pos", "cig_off", "cigar")}
+    n = len(cols["pos"])
+    cols.update(yx=z[f"{case}/in/yx_in"], yc=np.ones(n, np.float32), strand=np.full(n, ord("."), np.uint8))
+    t, s, e, iv = ctx.sample_window(cols)
+    assert np.array_equal(t, z[f"{case}/out/tid"]) and np.array_equal(s, z[f"{case}/out/start"])
+    assert np.array_equal(e, z[f"{case}/out/end"]) and np.array_equal(iv, z[f"{case}/out/ival"])
+
+
+@pytest.mark.parametrize("n,n_tx,chroms,seed", [(40_000, 30, 2, 1), (120_000, 400, 3, 2), (30_000, 3, 1, 3)])
+def test_sample_heatmap_matches_oracle(ctx, n, n_tx, chroms, seed):
+    """tiecov -s: float32 running mean of YX per base in stream order, ceil, runs — device against the oracle, bit for bit
+    (spliced reads, deep pile-ups, several chromosomes, YX from 1 to 60)."""
+    from oracle import oracle
+    from tiebrush_b200 import synth
+    cols = synth.to_host(synth.coverage_stream(n, seed=seed, n_tx=n_tx, chroms=chroms))
+    cols["yx"] = np.random.default_rng(seed).integers(1, 61, size=n).astype(np.int32)
+    got, exp = ctx.sample_window(cols), oracle.sample_heatmap(cols)
+    assert len(exp[0]) > 100
+    for a, b in zip(got, exp):
         assert np.array_equal(np.asarray(a), b)

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtiebrush_b200.so")
 
 SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_set_stream", "tb_get_stream", "tb_sync",
-           "tb_collapse_window", "tc_coverage_window", "tb_launch_count", "tb_set_profiling",
+           "tb_collapse_window", "tc_coverage_window", "tc_sample_window", "tb_launch_count", "tb_set_profiling",
            "tb_last_kernel_ms", "tb_version", "tb_last_path", "tb_last_yd_path", "tb_last_heavy_slots"]
 
 
@@ -69,6 +69,7 @@ def load():
     lib.tb_sync.argtypes = [C.c_void_p]
     lib.tb_collapse_window.argtypes = [C.c_void_p, C.POINTER(SoaIn), C.POINTER(GroupsOut)]
     lib.tc_coverage_window.argtypes = [C.c_void_p, C.POINTER(CovIn), C.POINTER(RunsOut), C.POINTER(JuncsOut)]
+    lib.tc_sample_window.argtypes = [C.c_void_p, C.POINTER(CovIn), C.c_void_p, C.POINTER(RunsOut)]
     lib.tb_launch_count.argtypes = [C.c_void_p]
     lib.tb_launch_count.restype = C.c_int64
     lib.tb_set_profiling.argtypes = [C.c_void_p, C.c_int]

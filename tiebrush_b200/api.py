@@ -174,6 +174,26 @@ class Context:
         return dict(rep_index=out["rep_index"][:g], yc=out["yc"][:g], yx=out["yx"][:g], yd=out["yd"][:g], n_kept=int(o.n_kept), n_groups=g)
 
     # ------------------------------------------------------------------------------------------
+    def sample_window(self, cols, cap_rows=None):
+        """tiecov -s of one window (whole bundles): rows (tid, start0, end0, ival) of the sample-count heat-map; `cols` needs
+        tid, pos, yc, strand, cig_off, cigar as for coverage_window plus yx (YX tag, 1 when absent). Host columns only."""
+        n = int(cols["pos"].shape[0])
+        keep = [_host(cols[k], dt) for k, dt in (("tid", np.int32), ("pos", np.int32), ("yc", np.float32), ("strand", np.uint8),
+                                                 ("cig_off", np.uint32), ("cigar", np.uint32), ("yx", np.int32))]
+        tid, pos, yc, strand, cig_off, cigar, yx = keep
+        n_cig = int(cig_off[-1]) if n else 0
+        cin = _lib.CovIn(n, _ptr(tid), _ptr(pos), _ptr(yc), _ptr(strand), _ptr(cig_off), _ptr(cigar), 0, n_cig)
+        cap = cap_rows if cap_rows is not None else 2 * n_cig + 16
+        rt, rs, re, rv = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.float64)
+        rows = _lib.RunsOut(cap, 0, _ptr(rt), _ptr(rs), _ptr(re), _ptr(rv), 0)
+        rc = self.lib.tc_sample_window(self.h, C.byref(cin), _ptr(yx), C.byref(rows))
+        if rc == 2:
+            raise ValueError(self._err())
+        if rc != 0:
+            raise TieBrushError(self._err())
+        r = int(rows.n_runs)
+        return rt[:r], rs[:r], re[:r], rv[:r].astype(np.uint64)
+
     def coverage_window(self, cols, want_runs=True, want_juncs=True, cap_runs=None, cap_juncs=None, out=None):
         """One window of tiecov -c/-j. Returns dict(runs=(tid,start0,end0,value), juncs=(tid,start,end,strand,value))."""
         dev = _is_torch(cols["pos"])

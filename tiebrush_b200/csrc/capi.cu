@@ -12,7 +12,7 @@ void tb_ctx::set_error(const char* fmt, ...) {
   err = buf;
 }
 
-int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* in, tc_runs_out* runs, tc_juncs_out* juncs);
+int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* in, tc_runs_out* runs, tc_juncs_out* juncs, const int32_t* yx);
 int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* in, tb_groups_out* out);
 
 static void global_error(const char* fmt, ...) {
@@ -96,7 +96,14 @@ int tc_coverage_window(tb_ctx* ctx, const tc_soa_in* in, tc_runs_out* runs, tc_j
   if (!ctx) return 1;
   if (!in || (!runs && !juncs)) { ctx->set_error("tc_coverage_window: at least one of runs/juncs required"); return 1; }
   ctx->err.clear();
-  return tc_coverage_impl(ctx, in, runs, juncs);
+  return tc_coverage_impl(ctx, in, runs, juncs, nullptr);
+}
+
+int tc_sample_window(tb_ctx* ctx, const tc_soa_in* in, const int32_t* yx, tc_runs_out* rows) {
+  if (!ctx) return 1;
+  if (!in || !yx || !rows || (in->n > 0 && !in->yc)) { ctx->set_error("tc_sample_window: in (with yc), yx and rows are required"); return 1; }
+  ctx->err.clear();
+  return tc_coverage_impl(ctx, in, rows, nullptr, yx);
 }
 
 }  // extern "C"

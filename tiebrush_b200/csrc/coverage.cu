@@ -48,6 +48,8 @@ enum {  // workspace slots in ctx->buf
   CB_RSAGG,
   CB_TIDKEYS,     // u64 [J]
   CB_TIDKEYS2,
+  CB_PMEND,       // u32 [n]  -s: inclusive prefix maximum of the record ends (1-based), monotone inside a tid
+  CB_RFIRST,      // u32 [n]  -s: first record of every bundle
   CB_COUNT_
 };
 
@@ -83,7 +85,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(CBK_THREADS, TB_CBK_MINB) cov_bundle_kernel(CovIn in, int check_ops, unsigned long long* __restrict__ st_max,
                                                                  unsigned long long* __restrict__ st_cnt, unsigned long long* __restrict__ ticket,
                                                                  uint32_t* __restrict__ bid, int32_t* __restrict__ bstart, int32_t* __restrict__ bend,
-                                                                 int32_t* __restrict__ btid, long long* __restrict__ status) {
+                                                                 int32_t* __restrict__ btid, uint32_t* __restrict__ pmend, uint32_t* __restrict__ rfirst,
+                                                                 long long* __restrict__ status) {
   __shared__ unsigned long long s_scan64[33];
   __shared__ uint32_t s_scan32[33];
   __shared__ unsigned long long s_tile, s_pa, s_pb;
@@ -180,9 +183,11 @@ __global__ void __launch_bounds__(CBK_THREADS, TB_CBK_MINB) cov_bundle_kernel(Co
       const uint32_t b = cnt++;
       bstart[b] = pos[k] + 1; btid[b] = tidv[k];
       if (b > 0) bend[b - 1] = (int)(uint32_t)run;   // this head closes the previous bundle
+      if (rfirst) rfirst[b] = (uint32_t)i;
     }
     bid[i] = cnt - 1;
     run = key[k] > run ? key[k] : run;
+    if (pmend) pmend[i] = (uint32_t)run;
     if (i == in.n - 1) { bend[cnt - 1] = (int)(uint32_t)run; status[ST_NBUNDLES] = cnt; }
   }
 }
@@ -415,6 +420,55 @@ struct ChangeOut {
   }
 };
 
+// ---- tiecov -s (sample heat-map, src/tiecov.cpp:155-185, 277-323): per base the float32 running mean of YX over the
+// covering records IN STREAM ORDER (first += (YX - first) / second; second++), then ceil. One thread per bundle-compacted
+// cell walks the records of its bundle that can cover it — from the first record whose running maximum end reaches the
+// base (pmend is monotone inside a tid) to the last record starting at or before it — and tests each CIGAR; the arithmetic
+// is the reference's, operation by operation (IEEE single: subtract, divide, add; nothing to contract).
+__global__ void __launch_bounds__(256) cov_sample_cell_kernel(CovIn in, const int32_t* __restrict__ yx, int64_t NB, const long long* __restrict__ bbase,
+                                                              const int32_t* __restrict__ bstart, const int32_t* __restrict__ bend,
+                                                              const uint32_t* __restrict__ rfirst, const uint32_t* __restrict__ pmend,
+                                                              long long* __restrict__ ival, int64_t L) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= L) return;
+  int64_t lo = 0, hi = NB;   // last bundle with base <= x
+  while (hi - lo > 1) { const int64_t m = (lo + hi) >> 1; if (bbase[m] <= x) lo = m; else hi = m; }
+  const int64_t b = lo;
+  const int64_t rel = x - bbase[b];
+  if (rel > (int64_t)bend[b] - bstart[b]) { ival[x] = 0; return; }   // the sentinel cell behind the bundle
+  const int g = bstart[b] + (int)rel;                                 // 1-based coordinate of the cell
+  const uint32_t r0 = rfirst[b], r1 = b + 1 < NB ? rfirst[b + 1] : (uint32_t)in.n;
+  uint32_t a = r0, z = r1;   // first record with pmend >= g
+  while (a < z) { const uint32_t m = a + ((z - a) >> 1); if (pmend[m] >= (uint32_t)g) z = m; else a = m + 1; }
+  const uint32_t first = a;
+  a = first; z = r1;         // first record with start (pos + 1) > g
+  while (a < z) { const uint32_t m = a + ((z - a) >> 1); if (in.pos[m] >= g) z = m; else a = m + 1; }
+  const uint32_t last = a;
+  float mean = 0.f; unsigned long long cnt = 1;
+  for (uint32_t i = first; i < last; ++i) {
+    int p = in.pos[i] + 1;
+    bool covered = false;
+    const uint32_t c1 = in.cig_off[i + 1];
+    for (uint32_t c = in.cig_off[i]; c < c1 && p <= g; ++c) {
+      const uint32_t w = in.cigar[c];
+      const uint32_t op = w & 0xf; const int len = (int)(w >> 4);
+      if (op == TB_OP_M) { if (g < p + len) { covered = true; break; } p += len; }
+      else if (op == TB_OP_D || op == TB_OP_N) p += len;
+    }
+    if (covered) { mean += ((float)yx[i] - mean) / (float)cnt; ++cnt; }
+  }
+  ival[x] = (long long)(unsigned long long)ceilf(mean);
+}
+struct ChgIn {
+  const long long* v;
+  __device__ uint32_t operator()(int64_t x) const { return v[x] != (x ? v[x - 1] : 0) ? 1u : 0u; }
+};
+struct ChgOut {
+  const long long* v; long long* cppos; long long* cpdepth;
+  __device__ void operator()(int64_t x, uint32_t exc, uint32_t inc) const { if (inc != exc) { cppos[exc] = x; cpdepth[exc] = v[x]; } }
+};
+__global__ void cov_store_nchange_kernel(const uint32_t* tot, long long* status) { status[ST_NCHANGE] = *tot; }
+
 struct RunValidIn {
   const long long* cpdepth; const long long* status;
   __device__ uint32_t operator()(int64_t k) const {
@@ -425,7 +479,7 @@ struct RunValidIn {
 struct RunOut {
   const long long* cppos; const long long* cpdepth; long long* status;
   const long long* bbase; const int32_t* bstart; const int32_t* btid;
-  int32_t* o_tid; int32_t* o_start; int32_t* o_end; double* o_val; long long capacity;
+  int32_t* o_tid; int32_t* o_start; int32_t* o_end; double* o_val; long long capacity; double scale;
   __device__ void operator()(int64_t k, uint32_t exc, uint32_t inc) const {
     if (inc == exc) return;
     if ((long long)exc >= capacity) { status[ST_RUNOVERFLOW] = 1; return; }
@@ -437,7 +491,7 @@ struct RunOut {
     o_tid[exc] = btid[lo];
     o_start[exc] = (int32_t)(c + off);
     o_end[exc] = (int32_t)(c2 + off);
-    o_val[exc] = (double)cpdepth[k] / COV_FX_SCALE;
+    o_val[exc] = (double)cpdepth[k] / scale;
   }
 };
 
@@ -495,14 +549,15 @@ static int stage_in(tb_ctx* ctx, DevBuf& b, const T* src, size_t count, int on_d
 
 }  // namespace
 
-int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_juncs_out* juncs) {
+int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_juncs_out* juncs, const int32_t* yx_in) {
   TB_CUDA(cudaSetDevice(ctx->device));
   const int64_t n = hin->n;
   if (runs) runs->n_runs = 0;
   if (juncs) juncs->n_juncs = 0;
   if (n == 0) return 0;
   if (n >= (1LL << 31)) { ctx->set_error("tc_coverage_window: n=%lld too large for one window", (long long)n); return 1; }
-  const int do_cov = runs != nullptr, do_junc = juncs != nullptr;
+  const bool sample = yx_in != nullptr;   // tiecov -s: runs = rows of the sample heat-map (value = ceil of the running mean of YX)
+  const int do_cov = runs != nullptr, do_junc = juncs != nullptr && !sample;
   cudaStream_t st = ctx->stream;
 
   // ---- inputs on the device ----
@@ -514,8 +569,13 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
   if (stage_in(ctx, ctx->in_stage[3], hin->strand, (size_t)n, hin->on_device, &in.strand)) return 1;
   if (stage_in(ctx, ctx->in_stage[4], hin->cig_off, (size_t)n + 1, hin->on_device, &in.cig_off)) return 1;
   if (stage_in(ctx, ctx->in_stage[5], hin->cigar, (size_t)ncig, hin->on_device, &in.cigar)) return 1;
+  const int32_t* d_yx = nullptr;
+  if (sample) { if (stage_in(ctx, ctx->in_stage[6], yx_in, (size_t)n, hin->on_device, &d_yx)) return 1; }
 
   DevBuf* B = ctx->buf;
+  if (sample) { TB_CUDA(B[CB_PMEND].ensure(sizeof(uint32_t) * n)); TB_CUDA(B[CB_RFIRST].ensure(sizeof(uint32_t) * n)); }
+  uint32_t* d_pmend = sample ? B[CB_PMEND].as<uint32_t>() : nullptr;
+  uint32_t* d_rfirst = sample ? B[CB_RFIRST].as<uint32_t>() : nullptr;
   TB_CUDA(B[CB_KEY].ensure(sizeof(uint64_t) * (2 * (size_t)((n + CBK_TILE - 1) / CBK_TILE) + 16)));
   TB_CUDA(B[CB_BID].ensure(sizeof(uint32_t) * n));
   TB_CUDA(B[CB_BSTART].ensure(sizeof(int32_t) * n));
@@ -543,10 +603,10 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     const bool vec = (((uintptr_t)in.pos | (uintptr_t)in.tid | (uintptr_t)in.cig_off | (uintptr_t)in.yc) & 15u) == 0 && !getenv("TB_COV_NOVEC");
     if (vec)
       cov_bundle_kernel<true><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, do_cov, st_max, st_cnt, ticket, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(),
-                                                                       B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_status);
+                                                                       B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_pmend, d_rfirst, d_status);
     else
       cov_bundle_kernel<false><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, do_cov, st_max, st_cnt, ticket, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(),
-                                                                        B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_status);
+                                                                        B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_pmend, d_rfirst, d_status);
     ctx->launches++;
   }
   // the bundle count decides the size of the next scan
@@ -581,6 +641,14 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     while ((int64_t)jcap < want) jcap <<= 1;
   }
   uint64_t seed = 0x9e3779b97f4a7c15ULL;
+  if (sample) {   // the cell array takes the place of the difference array
+    TB_CUDA(B[CB_DIFF].ensure(sizeof(int64_t) * (L + 1)));
+    if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
+    cov_sample_cell_kernel<<<grid_for(L, 256), 256, 0, st>>>(in, d_yx, NB, B[CB_BBASE].as<long long>(), B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(),
+                                                            d_rfirst, d_pmend, B[CB_DIFF].as<long long>(), L);
+    ctx->launches++;
+    if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[1], st));
+  } else
   for (int attempt = 0;; ++attempt) {
     if (do_junc) {
       TB_CUDA(B[CB_JTAG].ensure(sizeof(uint64_t) * jcap));
@@ -623,8 +691,13 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     long long* d_diff = B[CB_DIFF].as<long long>();
     long long* cppos = B[CB_CPPOS].as<long long>();
     long long* cpdepth = B[CB_CPDEPTH].as<long long>();
-    TB_CUDA((tb_device_scan<OpSumNz>(ctx, DiffIn{d_diff}, L, B[CB_AGG].as<SumNz>(), ChangeOut{d_diff, cppos, cpdepth})));
-    cov_store_total_kernel<<<1, 1, 0, st>>>(B[CB_AGG].as<SumNz>() + tb_scan_blocks(L), nullptr, d_status);
+    if (sample) {
+      TB_CUDA((tb_device_scan<OpSumU32>(ctx, ChgIn{d_diff}, L, B[CB_AGG].as<uint32_t>(), ChgOut{d_diff, cppos, cpdepth})));
+      cov_store_nchange_kernel<<<1, 1, 0, st>>>(B[CB_AGG].as<uint32_t>() + tb_scan_blocks(L), d_status);
+    } else {
+      TB_CUDA((tb_device_scan<OpSumNz>(ctx, DiffIn{d_diff}, L, B[CB_AGG].as<SumNz>(), ChangeOut{d_diff, cppos, cpdepth})));
+      cov_store_total_kernel<<<1, 1, 0, st>>>(B[CB_AGG].as<SumNz>() + tb_scan_blocks(L), nullptr, d_status);
+    }
     ctx->launches++;
     // the number of change points is only known on the device
     TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
@@ -642,7 +715,7 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
       o_val = ctx->out_stage[3].as<double>();
     }
     RunOut ro{cppos, cpdepth, d_status, B[CB_BBASE].as<long long>(), B[CB_BSTART].as<int32_t>(), B[CB_BTID].as<int32_t>(),
-              o_tid, o_start, o_end, o_val, stage_cap};
+              o_tid, o_start, o_end, o_val, stage_cap, sample ? 1.0 : COV_FX_SCALE};
     TB_CUDA((tb_device_scan<OpSumU32>(ctx, RunValidIn{cpdepth, d_status}, K, B[CB_AGG].as<uint32_t>(), ro)));
     cov_store_total_kernel<<<1, 1, 0, st>>>(nullptr, B[CB_AGG].as<uint32_t>() + tb_scan_blocks(K), d_status);
     ctx->launches++;
