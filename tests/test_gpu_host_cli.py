@@ -128,3 +128,10 @@ def test_recollapse_and_tiecov_cli_match_reference(sams):
         assert open(gc + ".bedgraph").read() == open(rc + ".bedgraph").read()
         assert open(gj + ".bed").read() == open(rj + ".bed").read()
         assert len(open(rc + ".bedgraph").read().split("\n")) > 10
+    # -s (sample heat-map) needs the @CO SAMPLE lines of a TieBrush-made header: the collapsed files only
+    for src, tag in ((ref_out, "re"), (a, "half")):
+        rs, gs = os.path.join(tmp, f"ref_{tag}_heat"), os.path.join(tmp, f"gpu_{tag}_heat")
+        _run([os.path.join(REF, "tiecov"), "-s", rs, src])
+        _run([os.path.join(HOST, "tiecov_gpu"), "-s", gs, "-c", gs + "_c", src], env={"TB_WINDOW_RECORDS": "700"})
+        assert open(gs + ".bedgraph").read() == open(rs + ".bedgraph").read()
+        assert len(open(rs + ".bedgraph").read().split("\n")) > 10

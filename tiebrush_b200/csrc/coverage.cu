@@ -8,6 +8,8 @@
 //                         -w one past its end, 64-bit fixed-point atomics                (addCov :194-223)
 //   K8  bedgraph runs   : scan of the difference array -> change points -> stream compaction of the
 //                         non-zero-depth runs; runs never join across bundles     (flushCoverage :226-241)
+//   -s  sample heat-map : per compacted cell the float32 running mean of YX over its covering records in stream order,
+//                         ceil, runs of equal value (addMean / discretize / flushCoverage :155-185, 277-309): tc_sample_window
 //   K9  junctions       : intron (start,end,strand) keys reduced in a device hash table (fingerprint CAS,
 //                         min/max verified, so exactness never rests on the hash), then radix-sorted
 //                         into print order                                   (addJunction/flushJuncs :100-120)

@@ -1,4 +1,5 @@
-// tiecov_gpu — the reference `tiecov` command line (-c coverage bedGraph, -j junction BED) with its hot loop on a B200.
+// tiecov_gpu — the reference `tiecov` command line (-c coverage bedGraph, -j junction BED, -s sample heat-map) with its hot
+// loops on a B200.
 //
 // Compiles the UNMODIFIED reference source (src/tiecov.cpp, from where it lies under the reference checkout given with
 // -I) with its main() renamed, and supplies a new main() that keeps option parsing (processOptions, tiecov.cpp:533-581),
@@ -7,8 +8,9 @@
 //     bundle logic + addCov + flushCoverage + addJunction + flushJuncs           (tiecov.cpp:435-512)
 // by a window packer and one tc_coverage_window() call per window (include/tiebrush_b200.h).
 // A window is cut only where a new bundle starts (tid change or start > running max end, tiecov.cpp:443), so windows
-// hold whole bundles. -s (sample heat-map) and -W (BigWig) are not on the device path: asking for them
-// exits with an error rather than silently running the CPU code.
+// hold whole bundles. -s (addMean / discretize / normalize / flushCoverage of the pair vector, tiecov.cpp:155-185, 277-323)
+// goes through tc_sample_window(). -W (BigWig) is not on the device path (libBigWig is not vendored): asking for it exits
+// with an error rather than silently running CPU code.
 #define main tc_reference_main_unused
 #include "src/tiecov.cpp"
 #undef main
@@ -24,7 +26,9 @@ struct TcWindowPacker {
   std::vector<float> yc;
   std::vector<uint8_t> strand;
   std::vector<uint32_t> cig_off, cigar;
-  std::vector<int32_t> r_tid, r_start, r_end, j_tid, j_start, j_end; std::vector<double> r_val, j_val; std::vector<uint8_t> j_strand;
+  std::vector<int32_t> yx;                                          // -s: YX tag per record
+  int n_samples = 0;                                                // -s: @CO SAMPLE lines of the header
+  std::vector<int32_t> r_tid, r_start, r_end, j_tid, j_start, j_end, s_tid, s_start, s_end; std::vector<double> r_val, j_val, s_val; std::vector<uint8_t> j_strand;
   double t_device = 0, t_print = 0; int64_t n_windows = 0;
 
   size_t n() const { return pos.size(); }
@@ -36,6 +40,7 @@ struct TcWindowPacker {
     if (brec.find_tag("YC") != NULL) w = brec.tag_float("YC");
     yc.push_back((float)w);
     strand.push_back((uint8_t)brec.spliceStrand());
+    if (soutf) yx.push_back((int32_t)brec.tag_int("YX", 1));          // tiecov.cpp:495
     cig_off.push_back((uint32_t)cigar.size());
     const uint32_t* c = bam_get_cigar(b);
     cigar.insert(cigar.end(), c, c + b->core.n_cigar);
@@ -63,8 +68,16 @@ struct TcWindowPacker {
       j_tid.resize(cap_j); j_start.resize(cap_j); j_end.resize(cap_j); j_val.resize(cap_j); j_strand.resize(cap_j);
       js.capacity = cap_j; js.tid = j_tid.data(); js.start = j_start.data(); js.end = j_end.data(); js.strand = j_strand.data(); js.value = j_val.data();
     }
-    const int rc = tc_coverage_window(ctx, &in, coutf ? &runs : NULL, joutf ? &js : NULL);
-    if (rc) GError("%s\n", tb_last_error(ctx));                      // incl. the "unknown opcode" abort of tiecov.cpp:219-220
+    if (coutf || joutf) {
+      const int rc = tc_coverage_window(ctx, &in, coutf ? &runs : NULL, joutf ? &js : NULL);
+      if (rc) GError("%s\n", tb_last_error(ctx));                    // incl. the "unknown opcode" abort of tiecov.cpp:219-220
+    }
+    tc_runs_out rows; memset(&rows, 0, sizeof(rows));
+    if (soutf) {
+      s_tid.resize(cap_r); s_start.resize(cap_r); s_end.resize(cap_r); s_val.resize(cap_r);
+      rows.capacity = cap_r; rows.tid = s_tid.data(); rows.start0 = s_start.data(); rows.end0 = s_end.data(); rows.value = s_val.data();
+      if (tc_sample_window(ctx, &in, yx.data(), &rows)) GError("%s\n", tb_last_error(ctx));
+    }
     auto t1 = clk::now();
     if (coutf)
       for (int64_t i = 0; i < runs.n_runs; ++i)                      // flushCoverage, tiecov.cpp:237
@@ -74,7 +87,16 @@ struct TcWindowPacker {
         juncCount++;
         fprintf(joutf, "%s\t%d\t%d\tJUNC%08d\t%.3f\t%c\n", hdr->target_name[j_tid[i]], j_start[i] - 1, j_end[i], juncCount, j_val[i], (char)j_strand[i]);
       }
-    tid.clear(); pos.clear(); yc.clear(); strand.clear(); cig_off.clear(); cigar.clear();
+    if (soutf) {   // normalize(bsam, 0.1, 1.5, n_samples) + flushCoverage of the pair vector (tiecov.cpp:293-318)
+      const float mint = 0.1, maxt = 1.5;
+      const float denom = n_samples, mult = (maxt - mint);
+      for (int64_t i = 0; i < rows.n_runs; ++i) {
+        const uint64_t ival = (uint64_t)s_val[i];
+        const float hval = ((float)ival / denom) * mult + mint;
+        fprintf(soutf, "%s\t%d\t%d\t%ld\t%f\n", hdr->target_name[s_tid[i]], s_start[i], s_end[i], (long)ival, hval);
+      }
+    }
+    tid.clear(); pos.clear(); yc.clear(); strand.clear(); cig_off.clear(); cigar.clear(); yx.clear();
     ++n_windows;
     auto t2 = clk::now();
     t_device += std::chrono::duration<double>(t1 - t0).count();
@@ -89,7 +111,6 @@ int main(int argc, char* argv[]) {
   auto t_begin = clk::now();
   processOptions(argc, argv);
   if (bigwig) GError("Error: -W (BigWig) is not available in tiecov_gpu (libBigWig is not part of the device path)\n");
-  if (!sfname.is_empty()) GError("Error: -s (sample heat-map) is not available in tiecov_gpu yet; use -c / -j\n");
   GSamReader samreader(infname.chars(), SAM_QNAME | SAM_FLAG | SAM_RNAME | SAM_POS | SAM_CIGAR | SAM_AUX);
   // output files: same naming rule (suffix appended unless already there), same track lines as tiecov.cpp:352-411
   auto open_track = [](GStr& name, const char* suffix, const char* track_line) -> FILE* {
@@ -103,6 +124,8 @@ int main(int argc, char* argv[]) {
   if (!covfname.is_empty())
     coutf = (covfname == "-" || covfname == "stdout") ? stdout : open_track(covfname, ".bedgraph", "track type=bedGraph\n");
   if (!jfname.is_empty()) joutf = open_track(jfname, ".bed", "track name=junctions\n");
+  if (!sfname.is_empty())
+    soutf = open_track(sfname, ".bedgraph", "track type=bedGraph name=\"Sample Count Heatmap\" description=\"Sample Count Heatmap\" visibility=full graphType=\"heatmap\" color=200,100,0 altColor=0,100,200\n");
   const char* dev_env = getenv("TB_DEVICE");
   tb_ctx* ctx = tb_create(dev_env ? atoi(dev_env) : 0, 1, TB_MODE_CIGAR, 0, TB_NO_MAX_NH, -1, 0, 0);
   if (!ctx) GError("%s\n", tb_last_error(NULL));
@@ -110,6 +133,10 @@ int main(int argc, char* argv[]) {
   if (const char* e = getenv("TB_WINDOW_RECORDS")) { long v = atol(e); if (v > 0) window_min = (size_t)v; }
 
   TcWindowPacker packer;
+  if (soutf) {   // needs the @CO SAMPLE lines of a TieBrush-made header (aborts without them, like the reference)
+    load_sample_info(samreader.header(), sample_info);
+    packer.n_samples = (int)sample_info.size();
+  }
   int prev_tid = -1, b_end = 0;
   GSamRecord brec;
   while (samreader.next(brec)) {
@@ -124,6 +151,7 @@ int main(int argc, char* argv[]) {
   packer.flush(ctx, samreader.header());
   if (coutf && coutf != stdout) fclose(coutf);
   if (joutf) fclose(joutf);
+  if (soutf) fclose(soutf);
   tb_destroy(ctx);
   if (getenv("TB_TIMING"))
     fprintf(stderr, "tb_b200 timing: total %.3f s | device (H2D+kernels+D2H) %.3f | print %.3f | windows %ld\n",
