@@ -37,3 +37,15 @@ def test_gpu_collapse_shards(ctx, world):
     for key in ("rep_index", "yc", "yx", "yd"):
         got = np.concatenate([np.asarray(p[key]) for p in parts])
         assert np.array_equal(got.astype(np.float64), np.asarray(exp[key]).astype(np.float64)), key
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_gpu_sample_heatmap_shards(ctx, world):
+    """Sharded tiecov -s with the device path as the per-shard engine: cuts inside bundles, rows stitched at the cuts."""
+    cols = T._sample_cols(30000, 23, chroms=2, n_tx=60)
+    exp = oracle.sample_heatmap(cols)
+    cuts = [(t, p + 29) for t, p in shard.cov_cuts(cols, world)]
+    bounds = [None] + cuts + [None]
+    parts = [shard.sample_shard_local(ctx.sample_window, cols, bounds[g], bounds[g + 1]) for g in range(world)]
+    for a, b in zip(shard._stitch_sample(parts), exp):
+        assert np.array_equal(a, b)

@@ -137,6 +137,14 @@ def _worker(rank, world, port, what, q):
                 exp = oracle.coverage(cols)
                 ok = all(np.array_equal(a, b) for a, b in zip(runs, exp["runs"])) and all(np.array_equal(a, b) for a, b in zip(juncs, exp["juncs"]))
                 q.put(("cov", bool(ok), len(runs[0]), len(juncs[0])))
+        elif what == "sample":
+            cols = _cov_stream(6000, 13, chroms=2)
+            cols["yx"] = np.random.default_rng(13).integers(1, 40, size=6000).astype(np.int32)
+            cuts = [(t, p + 41) for t, p in shard.cov_cuts(cols, world)]   # inside bundles
+            got = shard.sample_sharded(oracle.sample_heatmap, cols, cuts)
+            if rank == 0:
+                exp = oracle.sample_heatmap(cols)
+                q.put(("sample", bool(all(np.array_equal(a, b) for a, b in zip(got, exp))), len(got[0]), 0))
         else:
             cols, run_off, _ = synth.cohort_window(5, 2000, seed=9, n_tx=25, device="cpu")
             host = synth.to_host(cols)
@@ -151,7 +159,7 @@ def _worker(rank, world, port, what, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("what,world", [("cov", 2), ("cov", 3), ("col", 2)])
+@pytest.mark.parametrize("what,world", [("cov", 2), ("cov", 3), ("col", 2), ("sample", 2), ("sample", 3)])
 def test_sharded_gloo(what, world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
@@ -206,3 +214,24 @@ def test_prefix_slice_is_a_coordinate_prefix_of_every_file():
     assert 0 < g < len(full["rep_index"])
     for key in ("yc", "yx", "yd"):
         assert np.array_equal(part[key], full[key][:g]), key
+
+
+def _sample_cols(n, seed, chroms=1, n_tx=40):
+    cols = _cov_stream(n, seed, chroms=chroms, n_tx=n_tx)
+    cols["yx"] = np.random.default_rng(seed).integers(1, 40, size=n).astype(np.int32)
+    return cols
+
+
+@pytest.mark.parametrize("seed,world,chroms", [(1, 2, 1), (2, 3, 2), (3, 8, 3)])
+def test_sample_heatmap_shards_equal_whole_stream(seed, world, chroms):
+    """Sharded tiecov -s (all ranks simulated in one process): balanced cuts and cuts nudged into the middle of bundles give
+    the rows of the unsharded stream."""
+    cols = _sample_cols(20000, seed, chroms=chroms)
+    exp = oracle.sample_heatmap(cols)
+    for shift in (0, 37):
+        cuts = [(t, p + shift) for t, p in shard.cov_cuts(cols, world)]
+        bounds = [None] + cuts + [None]
+        parts = [shard.sample_shard_local(oracle.sample_heatmap, cols, bounds[g], bounds[g + 1]) for g in range(world)]
+        got = shard._stitch_sample(parts)
+        for a, b in zip(got, exp):
+            assert np.array_equal(a, b), (seed, world, shift)

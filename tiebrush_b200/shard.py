@@ -418,3 +418,78 @@ def collapse_sharded(compute, cols, run_off, cuts, group=None):
         reps.append(v[1:1 + g]); ycs.append(v[1 + g:1 + 2 * g].astype(np.uint32).view(np.float32))
         yxs.append(v[1 + 2 * g:1 + 3 * g].astype(np.uint32)); yds.append(v[1 + 3 * g:1 + 4 * g].astype(np.int32))
     return dict(rep_index=np.concatenate(reps), yc=np.concatenate(ycs), yx=np.concatenate(yxs), yd=np.concatenate(yds))
+
+
+# --------------------------------------------------------------------------------------------------
+# tiecov -s (sample heat-map) over coordinate shards
+# --------------------------------------------------------------------------------------------------
+def sample_shard_local(compute, cols, lo, hi):
+    """One rank of the sharded tiecov -s over a stream every rank can read. The running mean of a base folds ALL records
+    covering it in stream order, and those lie in the base's own bundle, so the rank computes from the head of the bundle
+    that is open at `lo` up to `hi` and keeps the part of every row inside [lo, hi). `compute(cols)` -> rows
+    (tid, start0, end0, ival) of whole bundles, cols incl. `yx`. Returns (rows, lo_inside_bundle)."""
+    key = _key(cols["tid"], cols["pos"])
+    n = len(key)
+    a = 0 if lo is None else int(np.searchsorted(key, (lo[0] << 32) | lo[1], side="left"))
+    b = n if hi is None else int(np.searchsorted(key, (hi[0] << 32) | hi[1], side="left"))
+    empty = tuple(np.zeros(0, dt) for dt in (np.int32, np.int32, np.int32, np.uint64))
+    head = bundle_heads(np.asarray(cols["tid"]), np.asarray(cols["pos"]), ref_end(cols))
+    inside = bool(lo is not None and a < n and not head[a])          # the cut at lo falls inside a bundle
+    if a >= b:
+        return empty, inside
+    a0 = a
+    while not head[a0]:
+        a0 -= 1
+    idx = np.arange(a0, b, dtype=np.int64)
+    sub = _cov_take(cols, idx)
+    sub["yx"] = np.asarray(cols["yx"])[idx]
+    t, s, e, v = (np.asarray(x) for x in compute(sub))
+    # clip to [lo, hi): a row is kept for the part whose 0-based positions start at or after lo (records before lo belong to
+    # the left neighbour's range), and nothing can reach beyond this rank's last record start + its span except through
+    # records starting before hi, which are all here; positions >= hi on the same tid belong to the right neighbour
+    s = s.astype(np.int64).copy(); e = e.astype(np.int64).copy()
+    if lo is not None:
+        on = t == lo[0]
+        s[on] = np.maximum(s[on], lo[1])
+        keep = (t > lo[0]) | (on & (e > s))
+    else:
+        keep = np.ones(len(t), bool)
+    if hi is not None:
+        on = t == hi[0]
+        e[on] = np.minimum(e[on], hi[1])
+        keep &= (t < hi[0]) | (on & (e > s))
+    return (t[keep].astype(np.int32), s[keep].astype(np.int32), e[keep].astype(np.int32), v[keep].astype(np.uint64)), inside
+
+
+def _stitch_sample(parts):
+    """Rank-ordered rows; a row that ends exactly where the next rank's first row starts, same tid and value, is one row of
+    the unsharded output iff the cut fell inside a bundle (rows never join across bundles, tiecov.cpp:293-309)."""
+    out = [[], [], [], []]
+    for rows, inside in parts:
+        t, s, e, v = rows
+        if len(t) and len(out[0]) and inside:
+            lt, ls, le, lv = out[0][-1], out[1][-1], out[2][-1], out[3][-1]
+            if len(lt) and lt[-1] == t[0] and le[-1] == s[0] and lv[-1] == v[0]:
+                le[-1] = e[0]
+                t, s, e, v = t[1:], s[1:], e[1:], v[1:]
+        for q, x in zip(out, (t, s, e, v)):
+            q.append(np.array(x, copy=True))
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+    return cat(out[0], np.int32), cat(out[1], np.int32), cat(out[2], np.int32), cat(out[3], np.uint64)
+
+
+def sample_sharded(compute, cols, cuts, group=None):
+    """Sharded tiecov -s: rank g owns the coordinate range [cuts[g-1], cuts[g]) of a stream all ranks can read; rows are
+    gathered in rank order (one variable-size all_gather) and stitched at the cuts. Every rank returns the full rows."""
+    d = _dist()
+    rank = d.get_rank(group) if d is not None else 0
+    bounds = [None] + list(cuts) + [None]
+    rows, inside = sample_shard_local(compute, cols, bounds[rank], bounds[rank + 1])
+    vec = np.concatenate([[len(rows[0]), int(inside)], rows[0].astype(np.int64), rows[1].astype(np.int64), rows[2].astype(np.int64),
+                          rows[3].astype(np.int64)]).astype(np.int64)
+    parts = []
+    for v in allgather_var(vec, group):
+        m, ins = int(v[0]), bool(v[1])
+        body = v[2:]
+        parts.append(((body[:m].astype(np.int32), body[m:2 * m].astype(np.int32), body[2 * m:3 * m].astype(np.int32), body[3 * m:4 * m].astype(np.uint64)), ins))
+    return _stitch_sample(parts)
