@@ -356,6 +356,7 @@ def main():
                                    + (f", -N {args.max_nh}" if args.max_nh != 0x7fffffff else "") + (f", -Q {args.min_qual}" if args.min_qual >= 0 else "")
                                    + (f", -F {args.flag_mask}" if args.flag_mask else "") + ", one window per GPU",
                        "front_end_path": int(ctx.last_path()) if hasattr(ctx, "last_path") else None,
+                       "tile_gen": int(ctx.last_tile_gen()), "heavy_slots": int(ctx.last_heavy_slots()), "tile_stats": ctx.last_tile_stats(),
                        "records_per_step_per_gpu": n, "groups_out": G, "mean_cigar_ops": cbar, "l2": "inputs (>=20 GB at full size) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"coordinate shards x{world}, no data-path collective", "gen_seconds": t_gen, "host_affinity": numa},
             "roofline": roofline, "gpu_launches": int(launches),

@@ -109,6 +109,14 @@ class Context:
     def last_heavy_slots(self):
         return int(self.lib.tb_last_heavy_slots(self.h))
 
+    def last_tile_gen(self):
+        """2 = TMA-staged tile kernel (col_tile2_kernel), 1 = col_tile_kernel."""
+        return int(self.lib.tb_last_tile_gen(self.h))
+
+    def last_tile_stats(self):
+        """Generation-2 tile kernel, last call: slots done in several passes, deferred (staging), deferred (table), slots."""
+        return dict(zip(("multi_pass", "deferred_staging", "deferred_table", "slots"), (int(self.lib.tb_last_tile_stat(self.h, i)) for i in range(4))))
+
     def last_yd_path(self):
         """0 parallel YD formulation, 1 sequential segment lists."""
         return int(self.lib.tb_last_yd_path(self.h))

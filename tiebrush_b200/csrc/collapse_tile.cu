@@ -590,6 +590,9 @@ __global__ void col_store_total_kernel(const uint32_t* tot, long long* status) {
 
 constexpr int TILE_THREADS_DEFAULT = 256;
 
+#include "collapse_tile2.cuh"
+constexpr int TILE2_THREADS = 512;
+
 }  // namespace
 
 int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& out, int64_t* n_groups, int64_t* n_kept) {
@@ -613,14 +616,43 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
     if (tile_smem_bytes((uint32_t)k, E, W) > lim1) { ctx->set_error("tb_collapse_window: %d samples do not fit the shared-memory group table", k); return 1; }
   }
   const uint32_t cap_records = (uint32_t)(((uint64_t)(E - 1) * 4) / 5);   // floor(1.25*n)+1 <= E
+  // full-size table of the second launch (pile-up positions, slots the first launch deferred)
+  const size_t lim_full = smem_sm - 1024 - 512;
+  uint32_t E_full = 8192;
+  while (E_full > 64 && tile_smem_bytes((uint32_t)k, E_full, W) > lim_full) E_full -= 64;
+  const uint32_t cap_full = (uint32_t)(((uint64_t)(E_full - 1) * 4) / 5);
+  // ---- generation 2 (col_tile2_kernel): slices staged by the TMA unit, one optimistic table per slot. Needs k <= 128
+  // (one producer thread per file in the first four warps, 7 bits of the match key), 16-byte aligned pos / cig_off / cigar
+  // columns (cp.async.bulk) and a slot of a few hundred records at least. TB_TILE_GEN=1 forces generation 1. ----
+  bool gen2 = k <= 128 && !ctx->tile2_off && threads != 1024 && tile_smem_bytes((uint32_t)k, E_full, W) <= lim_full &&
+              (((uintptr_t)in.pos | (uintptr_t)in.cig_off | (uintptr_t)in.cigar) & 15u) == 0 && g.n_cig > 0 && g.n_cig < (1LL << 32);
+  if (const char* e = getenv("TB_TILE_GEN")) { if (atoi(e) == 1) gen2 = false; }
+  uint32_t T2 = 0, rs_cap = 0, cw_cap = 0;
+  const uint32_t E2g = 1024, logE2g = 10;
+  if (gen2) {
+    const size_t lim2 = smem_sm / 2 - 1024 - 1024;
+    uint32_t t = 8128;
+    if (t > cap_full) t = cap_full & ~63u;
+    for (; t >= 512; t -= 64) {
+      rs_cap = (t + 7u * (uint32_t)k + 8u + 3u) & ~3u;
+      cw_cap = (t * 13u / 4u + 6u * (uint32_t)k + 8u + 3u) & ~3u;
+      if (rs_cap < 65536u && cw_cap < 65536u && tile2_smem_bytes((uint32_t)k, E2g, W, t, rs_cap, cw_cap) <= lim2) break;
+    }
+    if (t >= 512) T2 = t; else gen2 = false;
+  }
   // slot size: a slot holds < T records of ordinary positions plus its last position; a slot that outgrows the table
   // splits that last position off as a pile-up sub-tile (tile kernel), so any T <= cap_records is correct. Larger T =
   // fewer, fuller slots (less per-slot work), but more slots that need the split. TB_TILE_T8 = T in eighths of the table.
   uint32_t t8 = 7;
   if (const char* e = getenv("TB_TILE_T8")) { const int t = atoi(e); if (t >= 1 && t <= 8) t8 = (uint32_t)t; }
-  const uint32_t T = (uint32_t)(((uint64_t)cap_records * t8) / 8);
+  uint32_t T = (uint32_t)(((uint64_t)cap_records * t8) / 8);
+  if (gen2) {
+    T = T2;
+    if (const char* e = getenv("TB_TILE2_T")) { const int t = atoi(e); if (t >= 64 && (uint32_t)t <= T2) T = (uint32_t)t; }
+  }
   if (T < 8) { ctx->set_error("tb_collapse_window: %d samples leave no room for a shared-memory tile", k); return 1; }
   const uint32_t M = (uint32_t)((n + T - 1) / T);
+  ctx->last_tile_gen = gen2 ? 2 : 1;
 
   TB_CUDA(B[XB_SLOTPOS].ensure(sizeof(uint32_t) * ((size_t)M + 2)));
   TB_CUDA(B[XB_OFF].ensure(sizeof(uint32_t) * ((size_t)M + 1) * k));
@@ -675,26 +707,54 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
     ctx->launches++;
     return cudaGetLastError();
   };
-  // launch 1: every slot, small tables (several CTAs per SM). A pile-up position with more distinct alignments than such a
-  // table holds sends its slot to the heavy list; launch 2 redoes those slots with one full-size table per SM.
-  if (threads != 1024) {
+  // launch 1: every slot — generation 2 (TMA-staged slices, one optimistic table per slot) or generation 1 (small
+  // position-partitioned tables, several CTAs per SM). Slots it cannot finish (a pile-up position with more distinct
+  // alignments than the table holds; generation 2: anything irregular) go to the heavy list; launch 2 redoes those slots
+  // with generation 1's full-size table, one CTA per SM.
+  if (threads != 1024 || gen2) {
     TB_CUDA(B[XB_HEAVY].ensure(sizeof(uint32_t) * ((size_t)M + 1)));
     tp.heavy_list = B[XB_HEAVY].as<uint32_t>();
   }
   long long* h_status = ctx->pinned[0].as<long long>();
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
-  TB_CUDA(launch(threads, tp, M));
+  if (gen2) {
+    Tile2Params t2p; memset(&t2p, 0, sizeof(t2p));
+    t2p.M = M; t2p.E = E2g; t2p.logE = logE2g; t2p.W = W; t2p.T = T2; t2p.rs_cap = rs_cap; t2p.cw_cap = cw_cap; t2p.k = (uint32_t)k;
+    t2p.P = g.P; t2p.slotpos = tp.slotpos; t2p.off = tp.off; t2p.gcount = tp.gcount; t2p.st_rep = tp.st_rep; t2p.st_yc = tp.st_yc;
+    t2p.st_yx = tp.st_yx; t2p.st_bits = tp.st_bits; t2p.status = tp.status; t2p.slot_counter = tp.slot_counter; t2p.seed = 0x85A308D3u;
+    t2p.heavy_list = tp.heavy_list; t2p.n = (uint32_t)n; t2p.n_cig = (uint32_t)g.n_cig;
+    const size_t smem2 = tile2_smem_bytes((uint32_t)k, E2g, W, T2, rs_cap, cw_cap);
+    const unsigned want = (unsigned)ctx->sm_count * (1024u / TILE2_THREADS);
+    const unsigned grid = M < want ? M : want;
+    TB_CUDA(cudaMemsetAsync(tp.slot_counter, 0, 64, st));
+#define TB_TILE2_LAUNCH(MODE)                                                                                                          \
+  do {                                                                                                                                 \
+    TB_CUDA(cudaFuncSetAttribute(col_tile2_kernel<TILE2_THREADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));     \
+    col_tile2_kernel<TILE2_THREADS, MODE><<<grid, TILE2_THREADS, smem2, st>>>(in, t2p);                                               \
+  } while (0)
+    switch (in.mode) {
+      case TB_MODE_CIGAR: TB_TILE2_LAUNCH(TB_MODE_CIGAR); break;
+      case TB_MODE_FULL: TB_TILE2_LAUNCH(TB_MODE_FULL); break;
+      case TB_MODE_CLIP: TB_TILE2_LAUNCH(TB_MODE_CLIP); break;
+      default: TB_TILE2_LAUNCH(TB_MODE_EXON); break;
+    }
+#undef TB_TILE2_LAUNCH
+    ctx->launches++;
+    TB_CUDA(cudaGetLastError());
+  } else {
+    TB_CUDA(launch(threads, tp, M));
+  }
   if (tp.heavy_list) {
     TB_CUDA(cudaMemcpyAsync(h_status, g.d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
     TB_CUDA(cudaStreamSynchronize(st));
     const int64_t nheavy = h_status[CS_NHEAVY];
     ctx->last_heavy = nheavy;
+    ctx->last_tile_stat[0] = h_status[CS_T2_MULTI]; ctx->last_tile_stat[1] = h_status[CS_T2_STAGE]; ctx->last_tile_stat[2] = h_status[CS_T2_TABLE];
+    ctx->last_tile_stat[3] = (int64_t)M;
+    if (gen2 && M >= 64 && nheavy > (int64_t)(M / 4)) ctx->tile2_off = 1;   // few duplicates: the optimistic table does not pay
     if (nheavy > 0 && !h_status[CS_TABLE_OVERFLOW]) {
       TileParams t2 = tp;
-      const size_t lim1 = smem_sm - 1024 - 512;
-      uint32_t E2 = 8192;
-      while (E2 > 64 && tile_smem_bytes((uint32_t)k, E2, W) > lim1) E2 -= 64;
-      t2.ecap = E2; t2.cap_records = (uint32_t)(((uint64_t)(E2 - 1) * 4) / 5);
+      t2.ecap = E_full; t2.cap_records = cap_full;
       t2.slot_list = tp.heavy_list; t2.n_list = (uint32_t)nheavy; t2.heavy_list = nullptr;
       TB_CUDA(launch(1024, t2, (unsigned)nheavy));
     }

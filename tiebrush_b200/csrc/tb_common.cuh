@@ -73,6 +73,9 @@ struct tb_ctx {
   int64_t last_heavy = 0;   // slots redone by the full-size tile launch in the last collapse call
   int last_yd_path = 0;     // YD stage of the last collapse call: 0 parallel (frontier + link bitmaps), 1 sequential lists
   int last_path = 0;        // front end of the last collapse call: 0 tile, 1 ordered (by options), 2 ordered (table overflow fallback)
+  int last_tile_gen = 0;    // tile kernel generation of the last collapse call: 2 = TMA-staged slices (col_tile2_kernel), 1 = col_tile_kernel
+  int64_t last_tile_stat[4] = {};   // generation 2, last call: slots done in several passes | deferred (staging area) | deferred (table / pile-up) | slots
+  int tile2_off = 0;        // sticky: a call deferred more than a quarter of its slots (few duplicates) -> later calls use generation 1
   std::string err;
   DevBuf buf[TB_NBUF];   // workspace slots (see the enum in each pipeline)
   DevBuf in_stage[20];   // device copies of host input arrays
