@@ -191,11 +191,13 @@ int tb_last_yd_path(tb_ctx*);
 int64_t tb_last_heavy_slots(tb_ctx*);
 /* Tile kernel generation the last tile-path call launched first: 2 = col_tile2_kernel (slices staged into shared memory by
  * cp.async.bulk / mbarrier, one optimistic table per slot; needs <= 128 files and 16-byte aligned pos / cig_off / cigar
- * columns), 1 = col_tile_kernel (position-partitioned tables, plain loads). TB_TILE_GEN=1 forces generation 1. Results are
- * identical; slots generation 2 defers show up in tb_last_heavy_slots(). */
+ * columns; opt-in with TB_TILE_GEN=2: exact, but measured slower than generation 1 on the C2 cohort), 1 = col_tile_kernel
+ * (position-partitioned tables, plain loads; the default). Results are identical; slots generation 2 defers show up in
+ * tb_last_heavy_slots(). */
 int tb_last_tile_gen(tb_ctx*);
-/* Generation-2 statistics of the last call: 0 slots done in several passes (more groups than one table), 1 slots deferred
- * because their slices do not fit the staging area, 2 slots deferred for a pile-up of distinct alignments, 3 slots in all. */
+/* Generation-2 statistics of the last call: 0 slots done in several passes (more groups than one table), 1 records of the
+ * deferred slots, 2 slots deferred (a pile-up of more distinct alignments at one position than the table holds, or CIGARs
+ * beyond the staging area), 3 slots in all. */
 int64_t tb_last_tile_stat(tb_ctx*, int which);
 /* Device time in ms of one stage of the last call, measured with CUDA events on the launching stream
  * (enabled by tb_set_profiling(ctx,1)):

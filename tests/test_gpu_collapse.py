@@ -33,6 +33,41 @@ def test_collapse_merged(case):
     H.assert_collapse_equal(H.run_collapse(gpu_collapse, files, opts, fm), exp, case)
 
 
+@pytest.fixture(params=[1, 2])
+def tile_gen(request, monkeypatch):
+    """Both tile kernels: generation 1 (default) and generation 2 (slices staged by cp.async.bulk + mbarrier, opt-in)."""
+    monkeypatch.setenv("TB_TILE_GEN", str(request.param))
+    return request.param
+
+
+@pytest.mark.parametrize("case", H.case_names("collapse_fixture.npz"))
+def test_collapse_fixture_tile_gen2(case, monkeypatch):
+    monkeypatch.setenv("TB_TILE_GEN", "2")
+    files, opts, fm, exp = H.load_collapse_case("collapse_fixture.npz", case)
+    H.assert_collapse_equal(H.run_collapse(gpu_collapse, files, opts, fm), exp, case)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("n_tx,k,reads", [(40, 12, 20000), (2000, 40, 5000), (3, 5, 30000), (300, 100, 3000)])
+def test_collapse_tile_gen2_vs_oracle(mode, n_tx, k, reads, monkeypatch):
+    """Generation-2 tile kernel (TMA-staged chunks, arena-verified groups, multi-pass slots, deferred pile-ups) against the
+    oracle, bit for bit, in every merge strategy."""
+    from oracle import oracle
+    from tiebrush_b200 import api, synth
+    monkeypatch.setenv("TB_TILE_GEN", "2")
+    cols, run_off, pr = synth.cohort_window(k, reads, seed=5, n_tx=n_tx, device="cpu", with_md=(mode == 1))
+    host = synth.to_host(cols)
+    if mode == 1:
+        host["md_off"], host["md"] = synth.md_columns(cols)
+    with api.Context(device=0, n_samples=k, mode=mode) as ctx:
+        got = ctx.collapse_window(host, run_off)
+        assert ctx.last_path() == 0 and ctx.last_tile_gen() == 2
+    exp = oracle.collapse(host, run_off, mode=mode)
+    assert got["n_kept"] == exp["n_kept"]
+    for key in ("rep_index", "yc", "yx", "yd"):
+        assert np.array_equal(np.asarray(got[key]), exp[key]), key
+
+
 @pytest.fixture(params=["par", "seq"])
 def yd_path(request, monkeypatch):
     """Both YD implementations: the parallel formulation (frontier + link bitmaps) and the sequential segment lists."""

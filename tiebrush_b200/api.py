@@ -114,8 +114,8 @@ class Context:
         return int(self.lib.tb_last_tile_gen(self.h))
 
     def last_tile_stats(self):
-        """Generation-2 tile kernel, last call: slots done in several passes, deferred (staging), deferred (table), slots."""
-        return dict(zip(("multi_pass", "deferred_staging", "deferred_table", "slots"), (int(self.lib.tb_last_tile_stat(self.h, i)) for i in range(4))))
+        """Generation-2 tile kernel, last call: slots done in several passes, records of deferred slots, deferred slots, slots."""
+        return dict(zip(("multi_pass", "deferred_records", "deferred_slots", "slots"), (int(self.lib.tb_last_tile_stat(self.h, i)) for i in range(4))))
 
     def last_yd_path(self):
         """0 parallel YD formulation, 1 sequential segment lists."""

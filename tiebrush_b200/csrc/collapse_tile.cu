@@ -626,19 +626,22 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
   // columns (cp.async.bulk) and a slot of a few hundred records at least. TB_TILE_GEN=1 forces generation 1. ----
   bool gen2 = k <= 128 && !ctx->tile2_off && threads != 1024 && tile_smem_bytes((uint32_t)k, E_full, W) <= lim_full &&
               (((uintptr_t)in.pos | (uintptr_t)in.cig_off | (uintptr_t)in.cigar) & 15u) == 0 && g.n_cig > 0 && g.n_cig < (1LL << 32);
-  if (const char* e = getenv("TB_TILE_GEN")) { if (atoi(e) == 1) gen2 = false; }
+  // Measured (profiles/r02a_*): generation 2 is exact but NOT faster on the C2 cohort (69-80 ms against 55.6 ms for the tile
+  // stage at 1e9 alignments): its table (1024 entries beside the staging area) is too small for the pile-up positions that
+  // hold a quarter of the records, and the instruction count per record did not drop. It stays opt-in: TB_TILE_GEN=2.
+  { const char* e = getenv("TB_TILE_GEN"); if (!e || atoi(e) != 2) gen2 = false; }
   uint32_t T2 = 0, rs_cap = 0, cw_cap = 0;
-  const uint32_t E2g = 1024, logE2g = 10;
+  const uint32_t E2g = 1024, logE2g = 10, arena2 = tile2_arena_words(E2g, in.mode);
   if (gen2) {
     const size_t lim2 = smem_sm / 2 - 1024 - 1024;
     uint32_t t = 8128;
     if (t > cap_full) t = cap_full & ~63u;
-    for (; t >= 512; t -= 64) {
+    for (; t >= 256; t -= 64) {
       rs_cap = (t + 7u * (uint32_t)k + 8u + 3u) & ~3u;
       cw_cap = (t * 13u / 4u + 6u * (uint32_t)k + 8u + 3u) & ~3u;
-      if (rs_cap < 65536u && cw_cap < 65536u && tile2_smem_bytes((uint32_t)k, E2g, W, t, rs_cap, cw_cap) <= lim2) break;
+      if (tile2_smem_bytes((uint32_t)k, E2g, W, t, rs_cap, cw_cap, arena2) <= lim2) break;
     }
-    if (t >= 512) T2 = t; else gen2 = false;
+    if (t >= 256) T2 = t; else gen2 = false;
   }
   // slot size: a slot holds < T records of ordinary positions plus its last position; a slot that outgrows the table
   // splits that last position off as a pile-up sub-tile (tile kernel), so any T <= cap_records is correct. Larger T =
@@ -719,11 +722,11 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
   if (gen2) {
     Tile2Params t2p; memset(&t2p, 0, sizeof(t2p));
-    t2p.M = M; t2p.E = E2g; t2p.logE = logE2g; t2p.W = W; t2p.T = T2; t2p.rs_cap = rs_cap; t2p.cw_cap = cw_cap; t2p.k = (uint32_t)k;
+    t2p.M = M; t2p.E = E2g; t2p.logE = logE2g; t2p.W = W; t2p.T = T; t2p.rs_cap = rs_cap; t2p.cw_cap = cw_cap; t2p.arena = arena2; t2p.k = (uint32_t)k;
     t2p.P = g.P; t2p.slotpos = tp.slotpos; t2p.off = tp.off; t2p.gcount = tp.gcount; t2p.st_rep = tp.st_rep; t2p.st_yc = tp.st_yc;
     t2p.st_yx = tp.st_yx; t2p.st_bits = tp.st_bits; t2p.status = tp.status; t2p.slot_counter = tp.slot_counter; t2p.seed = 0x85A308D3u;
     t2p.heavy_list = tp.heavy_list; t2p.n = (uint32_t)n; t2p.n_cig = (uint32_t)g.n_cig;
-    const size_t smem2 = tile2_smem_bytes((uint32_t)k, E2g, W, T2, rs_cap, cw_cap);
+    const size_t smem2 = tile2_smem_bytes((uint32_t)k, E2g, W, T2, rs_cap, cw_cap, arena2);
     const unsigned want = (unsigned)ctx->sm_count * (1024u / TILE2_THREADS);
     const unsigned grid = M < want ? M : want;
     TB_CUDA(cudaMemsetAsync(tp.slot_counter, 0, 64, st));
