@@ -175,6 +175,48 @@ int tc_coverage_window(tb_ctx*, const tc_soa_in* in, tc_runs_out* runs, tc_juncs
  * n_samples = number of @CO SAMPLE lines of the header (load_sample_info, commons.h). */
 int tc_sample_window(tb_ctx*, const tc_soa_in* in, const int32_t* yx, tc_runs_out* rows);
 
+/* ---- tiecov over a long stream: windows cut at bundle heads -------------------------------- */
+/* `in` = one coordinate-sorted slice (host or device arrays) of any length whose CIGAR arena fits 32-bit offsets. It is
+ * processed in windows of at most `window` records; a window whose last bundle is continued by the record behind it
+ * leaves that bundle to the next window, so the concatenated rows are those of ONE pass of the reference's loop
+ * (tiecov.cpp:435-528). next_tid_pos = {tid, pos} of the record that follows the slice in the stream, or NULL: when it
+ * continues the slice's last bundle that bundle is left unprocessed and *consumed < in->n tells the caller where to
+ * resume (prepend the rest to the next slice). Rows are written from index 0 of runs / juncs. */
+int tc_coverage_stream(tb_ctx*, const tc_soa_in* in, int64_t window, const int32_t* next_tid_pos,
+                       tc_runs_out* runs, tc_juncs_out* juncs, int64_t* consumed);
+
+/* ---- several GPUs: one context per GPU, sharded by reference coordinate ------- */
+/* The reference's only parallel mode is tiewrap.py's batch tree (tiewrap.py:42-123); its main loops are sequential. Here a
+ * coordinate-sorted stream is split in stream order over `world` ranks (one process or thread per GPU). NCCL carries
+ * the open-bundle state (ncclAllGather), the records of a bundle that a cut separated from its head (grouped ncclSend /
+ * ncclRecv to the rank that holds the head) and the final ordered gather; everything else is local.
+ * tb_comm_unique_id: rank 0 fills 128 bytes (ncclUniqueId) that the launcher distributes; tb_comm_init: every rank,
+ * collectively. libnccl.so.2 is loaded at run time; single-GPU use never needs it. */
+int tb_comm_unique_id(void* id128);
+int tb_comm_init(tb_ctx*, int rank, int world, const void* id128);
+int tb_comm_destroy(tb_ctx*);
+int tb_comm_rank(tb_ctx*);
+int tb_comm_world(tb_ctx*);
+/* This rank's slice of the stream as n_segs DEVICE-resident segments in stream order (a rank cuts its slice into segments
+ * only at reference-id boundaries; the cuts BETWEEN ranks are arbitrary). Collective. On return runs / juncs hold the rows
+ * of the bundles whose first record this rank holds, in stream order: the concatenation over the ranks equals the
+ * single-GPU output row for row. Without a communicator (or world 1) it is tc_coverage_stream over the segments. */
+int tc_shard_coverage(tb_ctx*, const tc_soa_in* segs, int n_segs, int64_t window, tc_runs_out* runs, tc_juncs_out* juncs);
+/* Ordered gather on rank 0 (collective): all_runs / all_juncs (device arrays, rank 0 only, may be NULL elsewhere) receive
+ * the rows of rank 0, 1, ... ; junc_base (host, [world+1], every rank) = junctions of the ranks before r, the offset of
+ * the global JUNC%08d counter (tiecov.cpp:92-94). */
+int tc_shard_gather(tb_ctx*, const tc_runs_out* runs, const tc_juncs_out* juncs, tc_runs_out* all_runs, tc_juncs_out* all_juncs,
+                    int64_t* junc_base);
+/* Statistics of the last tc_shard_coverage / tc_shard_gather call: 0 lead records received, 1 lead records sent, 2 ranks
+ * received from, 3 bytes sent in the halo exchange, 4 records of the seam window, 5 bytes this rank moved in the gather. */
+int64_t tc_shard_stat(tb_ctx*, int which);
+/* Windows the last tc_coverage_stream / tc_shard_coverage call processed. */
+int64_t tc_stream_windows(tb_ctx*);
+/* 1 when the last coverage call took the exact path: some weight was not a multiple of 2^-20 (YC written by `tiebrush
+ * --store-frac`), so coverage and junction values were summed as doubles in stream order like the reference does
+ * (tiecov.cpp:194-223, :100-112) instead of in 2^-20 fixed point. */
+int tc_last_exact(tb_ctx*);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Kernels launched by this library since the context was created (for bench.py's gpu_launches). */
 int64_t tb_launch_count(tb_ctx*);
@@ -204,7 +246,9 @@ int64_t tb_last_tile_stat(tb_ctx*, int which);
  *   0 collapse tile kernel (dominant)      1 coverage accumulate kernel (dominant)
  *   2 collapse C1+C2 histogram+scan        3 collapse C3+C4 slots + run offsets
  *   4 collapse C6 compaction               5 collapse C7 YD (descriptors, bundles, chains)
- *   6 coverage K6 bundles                  7 coverage K8 runs      8 coverage K9 junction extraction */
+ *   6 coverage K6 bundles                  7 coverage K8 runs      8 coverage K9 junction extraction
+ *   9 tc_shard_coverage: halo exchange (allgathers + send / receive of the lead records)
+ * After tc_coverage_stream / tc_shard_coverage, 1, 6 and 7 are sums over the windows of the call. */
 int   tb_set_profiling(tb_ctx*, int on);
 float tb_last_kernel_ms(tb_ctx*, int which);
 

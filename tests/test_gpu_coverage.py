@@ -169,3 +169,67 @@ def test_sample_heatmap_matches_oracle(ctx, n, n_tx, chroms, seed):
     assert len(exp[0]) > 100
     for a, b in zip(got, exp):
         assert np.array_equal(np.asarray(a), b)
+
+
+# ---- long streams: windows cut at bundle heads (tc_coverage_stream) -------------------------------------------------
+def _same_rows(a, b):
+    assert a["n_runs"] == b["n_runs"] and a["n_juncs"] == b["n_juncs"]
+    for x, y in zip(a["runs"] + a["juncs"], b["runs"] + b["juncs"]):
+        x = x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
+        y = y.cpu().numpy() if hasattr(y, "cpu") else np.asarray(y)
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("window", [1024, 5000, 70000])
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_coverage_stream_equals_one_window(ctx, window, where):
+    """The stream cut into small windows at bundle heads gives the rows of one window (= the oracle), host and device arrays."""
+    import torch
+    from oracle import oracle
+    from tiebrush_b200 import api, synth
+    cols = synth.coverage_stream(60000, seed=4, n_tx=60, chroms=3, device="cuda" if where == "device" else "cpu")
+    host = synth.to_host(cols)
+    exp = oracle.coverage(host)
+    src = cols if where == "device" else host
+    cap = 2 * int(host["cig_off"][-1]) + 16
+    out = api.cov_out_buffers(cap, cap, device="cuda" if where == "device" else None)
+    got = ctx.coverage_stream(src, window, out)
+    assert got["consumed"] == len(host["pos"]) and (got["windows"] >= 5 if window < 20000 else got["windows"] >= 1)
+    _same_rows(got, dict(runs=exp["runs"], juncs=exp["juncs"], n_runs=len(exp["runs"][0]), n_juncs=len(exp["juncs"][0])))
+
+
+def test_coverage_stream_leaves_the_open_bundle(ctx):
+    """A slice that ends inside a bundle: with the following record given, that bundle is left to the caller."""
+    from oracle import oracle
+    from tiebrush_b200 import api, synth
+    host = synth.to_host(synth.coverage_stream(30000, seed=6, n_tx=20, chroms=1))
+    n = len(host["pos"])
+    cut = n // 2
+    while synth.bundle_cut(host, cut) == cut:     # move the cut inside a bundle
+        cut += 1
+    part = synth.take_prefix(host, cut)
+    cap = 2 * int(host["cig_off"][-1]) + 16
+    got = ctx.coverage_stream(part, 4096, api.cov_out_buffers(cap, cap), next_tid_pos=(host["tid"][cut], host["pos"][cut]))
+    prev_head = got["consumed"]
+    assert prev_head < cut and synth.bundle_cut(host, prev_head) == prev_head and synth.bundle_cut(host, prev_head + 1) > cut
+    exp = oracle.coverage(synth.take_prefix(host, prev_head))
+    _same_rows(got, dict(runs=exp["runs"], juncs=exp["juncs"], n_runs=len(exp["runs"][0]), n_juncs=len(exp["juncs"][0])))
+
+
+# ---- weights that are not multiples of 2^-20 (tiebrush --store-frac): exact ordered double sums -------------------------
+@pytest.mark.parametrize("seed", [1, 2])
+def test_coverage_fractional_yc_takes_the_exact_path(ctx, seed):
+    """YC = 1/3, 1/5, 1/7 ... (float32): fixed point would round every weight; the device sums doubles in stream order like
+    the reference (tiecov.cpp:194-223, :100-112) and says so."""
+    from oracle import oracle
+    from tiebrush_b200 import synth
+    host = synth.to_host(synth.coverage_stream(40000, seed=seed, n_tx=25, chroms=2))
+    rng = np.random.default_rng(seed)
+    host["yc"] = (rng.integers(1, 40, len(host["pos"])).astype(np.float32) / rng.choice(np.asarray([3, 5, 7, 9, 11], np.float32), len(host["pos"]))).astype(np.float32)
+    got, exp = ctx.coverage_window(host), oracle.coverage(host)
+    assert ctx.last_cov_exact() == 1
+    for a, b in zip(got["runs"] + got["juncs"], exp["runs"] + exp["juncs"]):
+        assert np.array_equal(np.asarray(a), b)
+    host["yc"] = np.ones_like(host["yc"])
+    ctx.coverage_window(host)
+    assert ctx.last_cov_exact() == 0

@@ -49,3 +49,18 @@ def test_gpu_sample_heatmap_shards(ctx, world):
     parts = [shard.sample_shard_local(ctx.sample_window, cols, bounds[g], bounds[g + 1]) for g in range(world)]
     for a, b in zip(shard._stitch_sample(parts), exp):
         assert np.array_equal(a, b)
+
+
+def test_shard_nccl_c4_multi_gpu():
+    """The C++ / NCCL sharded tiecov path (tc_shard_coverage + tc_shard_gather) on every GPU of the box: gathered rows equal
+    the single-GPU stream and the oracle (tools/shard_nccl_c4_check.py under torchrun). Needs >= 2 GPUs."""
+    import os, subprocess, sys
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(ngpu, 8)}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", os.path.join(root, "tools", "shard_nccl_c4_check.py"), "300000"],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0 and "SHARD_NCCL_C4_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

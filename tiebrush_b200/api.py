@@ -246,3 +246,123 @@ class Context:
         return dict(runs=(out["r_tid"][:r], out["r_start"][:r], out["r_end"][:r], out["r_val"][:r]),
                     juncs=(out["j_tid"][:j], out["j_start"][:j], out["j_end"][:j], out["j_strand"][:j], out["j_val"][:j]),
                     n_runs=r, n_juncs=j)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tiecov over long streams / several GPUs (csrc/shard.cu): thin ctypes plumbing, no logic of its own
+# ---------------------------------------------------------------------------------------------------------------------
+def _cov_in(cols, keep):
+    """tc_soa_in for a column dict (numpy or torch); `keep` collects the arrays that must outlive the call."""
+    dev = _is_torch(cols["pos"])
+    n = int(cols["pos"].shape[0])
+    arrs = []
+    for name, dt in (("tid", np.int32), ("pos", np.int32), ("yc", np.float32), ("strand", np.uint8), ("cig_off", np.uint32), ("cigar", np.uint32)):
+        a = cols[name]
+        if not dev:
+            a = _host(a, dt)
+        keep.append(a)
+        arrs.append(a)
+    n_cig = int(cols["n_cig"]) if "n_cig" in cols else (int(arrs[4][-1]) - int(arrs[4][0]) if n else 0)
+    return _lib.CovIn(n, *[_ptr(a) for a in arrs], 1 if dev else 0, n_cig)
+
+
+def cov_out_buffers(cap_runs, cap_juncs, device=None):
+    """Output arrays of a coverage call (torch on `device`, or numpy when device is None)."""
+    if device is not None:
+        import torch
+        i32 = lambda m: torch.empty(m, dtype=torch.int32, device=device)
+        return dict(r_tid=i32(cap_runs), r_start=i32(cap_runs), r_end=i32(cap_runs), r_val=torch.empty(cap_runs, dtype=torch.float64, device=device),
+                    j_tid=i32(cap_juncs), j_start=i32(cap_juncs), j_end=i32(cap_juncs), j_strand=torch.empty(cap_juncs, dtype=torch.uint8, device=device),
+                    j_val=torch.empty(cap_juncs, dtype=torch.float64, device=device))
+    return dict(r_tid=np.empty(cap_runs, np.int32), r_start=np.empty(cap_runs, np.int32), r_end=np.empty(cap_runs, np.int32), r_val=np.empty(cap_runs, np.float64),
+                j_tid=np.empty(cap_juncs, np.int32), j_start=np.empty(cap_juncs, np.int32), j_end=np.empty(cap_juncs, np.int32),
+                j_strand=np.empty(cap_juncs, np.uint8), j_val=np.empty(cap_juncs, np.float64))
+
+
+def _out_structs(out):
+    odev = 1 if _is_torch(out["r_tid"]) else 0
+    runs = _lib.RunsOut(int(out["r_tid"].shape[0]), 0, _ptr(out["r_tid"]), _ptr(out["r_start"]), _ptr(out["r_end"]), _ptr(out["r_val"]), odev)
+    juncs = _lib.JuncsOut(int(out["j_tid"].shape[0]), 0, _ptr(out["j_tid"]), _ptr(out["j_start"]), _ptr(out["j_end"]), _ptr(out["j_strand"]), _ptr(out["j_val"]), odev)
+    return runs, juncs
+
+
+def _rows(out, r, j):
+    return dict(runs=(out["r_tid"][:r], out["r_start"][:r], out["r_end"][:r], out["r_val"][:r]),
+                juncs=(out["j_tid"][:j], out["j_start"][:j], out["j_end"][:j], out["j_strand"][:j], out["j_val"][:j]), n_runs=r, n_juncs=j)
+
+
+def _coverage_stream(self, cols, window, out, next_tid_pos=None):
+    """tc_coverage_stream: one slice in windows cut at bundle heads. Returns the rows and `consumed`."""
+    keep = []
+    cin = _cov_in(cols, keep)
+    runs, juncs = _out_structs(out)
+    nx = None
+    if next_tid_pos is not None:
+        nx = (C.c_int32 * 2)(int(next_tid_pos[0]), int(next_tid_pos[1]))
+    consumed = C.c_int64(0)
+    rc = self.lib.tc_coverage_stream(self.h, C.byref(cin), int(window), nx, C.byref(runs), C.byref(juncs), C.byref(consumed))
+    if rc == 2:
+        raise ValueError(self._err())
+    if rc != 0:
+        raise TieBrushError(self._err())
+    res = _rows(out, int(runs.n_runs), int(juncs.n_juncs))
+    res["consumed"] = int(consumed.value)
+    res["windows"] = int(self.lib.tc_stream_windows(self.h))
+    return res
+
+
+def _comm_unique_id():
+    buf = (C.c_ubyte * 128)()
+    lib = _lib.load()
+    if lib.tb_comm_unique_id(buf) != 0:
+        raise TieBrushError(lib.tb_last_error(None).decode())
+    return bytes(buf)
+
+
+def _comm_init(self, rank, world, unique_id):
+    buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+    if self.lib.tb_comm_init(self.h, int(rank), int(world), buf) != 0:
+        raise TieBrushError(self._err())
+
+
+def _shard_coverage(self, segs, window, out):
+    """tc_shard_coverage over this rank's device-resident segments (list of column dicts). Collective."""
+    keep = []
+    arr = (_lib.CovIn * len(segs))(*[_cov_in(s, keep) for s in segs])
+    runs, juncs = _out_structs(out)
+    rc = self.lib.tc_shard_coverage(self.h, arr, len(segs), int(window), C.byref(runs), C.byref(juncs))
+    if rc == 2:
+        raise ValueError(self._err())
+    if rc != 0:
+        raise TieBrushError(self._err())
+    res = _rows(out, int(runs.n_runs), int(juncs.n_juncs))
+    res["windows"] = int(self.lib.tc_stream_windows(self.h))
+    res["stats"] = dict(zip(("lead_received", "lead_sent", "ranks_received_from", "halo_bytes_sent", "seam_records"),
+                            (int(self.lib.tc_shard_stat(self.h, i)) for i in range(5))))
+    return res
+
+
+def _shard_gather(self, local, all_out, world):
+    """tc_shard_gather: ordered gather of `local` (result of shard_coverage, device rows) into `all_out` on rank 0. Collective."""
+    lr = _lib.RunsOut(int(local["n_runs"]), int(local["n_runs"]), *[_ptr(a) for a in local["runs"]], 1)
+    lj = _lib.JuncsOut(int(local["n_juncs"]), int(local["n_juncs"]), *[_ptr(a) for a in local["juncs"]], 1)
+    base = (C.c_int64 * (world + 1))()
+    if all_out is not None:
+        ar, aj = _out_structs(all_out)
+        rc = self.lib.tc_shard_gather(self.h, C.byref(lr), C.byref(lj), C.byref(ar), C.byref(aj), base)
+    else:
+        rc = self.lib.tc_shard_gather(self.h, C.byref(lr), C.byref(lj), None, None, base)
+    if rc != 0:
+        raise TieBrushError(self._err())
+    res = dict(junc_base=[int(x) for x in base], gather_bytes=int(self.lib.tc_shard_stat(self.h, 5)))
+    if all_out is not None:
+        res.update(_rows(all_out, int(ar.n_runs), int(aj.n_juncs)))
+    return res
+
+
+Context.coverage_stream = _coverage_stream
+Context.comm_init = _comm_init
+Context.shard_coverage = _shard_coverage
+Context.shard_gather = _shard_gather
+Context.last_cov_exact = lambda self: int(self.lib.tc_last_exact(self.h))
+comm_unique_id = _comm_unique_id

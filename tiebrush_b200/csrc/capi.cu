@@ -12,7 +12,7 @@ void tb_ctx::set_error(const char* fmt, ...) {
   err = buf;
 }
 
-int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* in, tc_runs_out* runs, tc_juncs_out* juncs, const int32_t* yx);
+int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* in, tc_runs_out* runs, tc_juncs_out* juncs, const int32_t* yx, CovExt* ext);
 int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* in, tb_groups_out* out);
 
 static void global_error(const char* fmt, ...) {
@@ -22,6 +22,8 @@ static void global_error(const char* fmt, ...) {
   va_end(ap);
   g_tb_global_error = buf;
 }
+
+extern "C" int tb_comm_destroy(tb_ctx* ctx);
 
 extern "C" {
 
@@ -63,6 +65,8 @@ void tb_destroy(tb_ctx* ctx) {
   for (auto& b : ctx->in_stage) b.release();
   for (auto& b : ctx->out_stage) b.release();
   for (auto& b : ctx->pinned) b.release();
+  for (auto& b : ctx->shard_buf) b.release();
+  tb_comm_destroy(ctx);
   for (int i = 0; i < 16; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -82,6 +86,8 @@ int64_t tb_launch_count(tb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int tb_last_path(tb_ctx* ctx) { return ctx ? ctx->last_path : -1; }
 int tb_last_yd_path(tb_ctx* ctx) { return ctx ? ctx->last_yd_path : -1; }
 int64_t tb_last_heavy_slots(tb_ctx* ctx) { return ctx ? ctx->last_heavy : -1; }
+int64_t tc_stream_windows(tb_ctx* ctx) { return ctx ? ctx->stream_windows : -1; }
+int tc_last_exact(tb_ctx* ctx) { return ctx ? ctx->last_cov_exact : -1; }
 int tb_last_tile_gen(tb_ctx* ctx) { return ctx ? ctx->last_tile_gen : -1; }
 int64_t tb_last_tile_stat(tb_ctx* ctx, int which) { return (ctx && which >= 0 && which < 4) ? ctx->last_tile_stat[which] : -1; }
 int tb_set_profiling(tb_ctx* ctx, int on) { if (!ctx) return 1; ctx->profiling = on; return 0; }
@@ -98,14 +104,14 @@ int tc_coverage_window(tb_ctx* ctx, const tc_soa_in* in, tc_runs_out* runs, tc_j
   if (!ctx) return 1;
   if (!in || (!runs && !juncs)) { ctx->set_error("tc_coverage_window: at least one of runs/juncs required"); return 1; }
   ctx->err.clear();
-  return tc_coverage_impl(ctx, in, runs, juncs, nullptr);
+  return tc_coverage_impl(ctx, in, runs, juncs, nullptr, nullptr);
 }
 
 int tc_sample_window(tb_ctx* ctx, const tc_soa_in* in, const int32_t* yx, tc_runs_out* rows) {
   if (!ctx) return 1;
   if (!in || !yx || !rows || (in->n > 0 && !in->yc)) { ctx->set_error("tc_sample_window: in (with yc), yx and rows are required"); return 1; }
   ctx->err.clear();
-  return tc_coverage_impl(ctx, in, rows, nullptr, yx);
+  return tc_coverage_impl(ctx, in, rows, nullptr, yx, nullptr);
 }
 
 }  // extern "C"

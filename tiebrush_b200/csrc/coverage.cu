@@ -56,7 +56,8 @@ enum {  // workspace slots in ctx->buf
 };
 
 // status block layout (int64 each)
-enum { ST_ERRIDX = 0, ST_NBUNDLES, ST_DENSE_LEN, ST_NCHANGE, ST_NRUNS, ST_NJUNC, ST_JOVERFLOW, ST_JCOLLISION, ST_RUNOVERFLOW, ST_INEXACT, ST_LBFAIL, ST_N_ };
+enum { ST_ERRIDX = 0, ST_NBUNDLES, ST_DENSE_LEN, ST_NCHANGE, ST_NRUNS, ST_NJUNC, ST_JOVERFLOW, ST_JCOLLISION, ST_RUNOVERFLOW, ST_INEXACT, ST_LBFAIL, ST_N_,
+       ST_TAIL_END = 12, ST_TAIL_TID = 13, ST_TAIL_FIRST = 14 };   // slot 11 (ST_N_) is the junction compaction counter; 12-14: last bundle of the window
 
 struct CovIn {
   int64_t n;
@@ -471,6 +472,54 @@ struct ChgOut {
 };
 __global__ void cov_store_nchange_kernel(const uint32_t* tot, long long* status) { status[ST_NCHANGE] = *tot; }
 
+// last bundle of the window: its end, reference id and first record (the caller decides whether the record that follows the
+// window continues it — then the bundle is left to the next window, tc_coverage_stream)
+__global__ void cov_tail_kernel(const int32_t* bend, const int32_t* btid, const uint32_t* rfirst, long long* status) {
+  const long long nb = status[ST_NBUNDLES];
+  if (nb < 1) return;
+  status[ST_TAIL_END] = bend[nb - 1]; status[ST_TAIL_TID] = btid[nb - 1]; status[ST_TAIL_FIRST] = rfirst[nb - 1];
+}
+__global__ void cov_set_nbundles_kernel(long long* status, long long nb) { status[ST_NBUNDLES] = nb; }
+
+// EXACT path for weights that are not multiples of 2^-20 (YC written by `tiebrush --store-frac`: 1/3, 1/5 ...): the
+// reference adds each record's weight to a double per base IN STREAM ORDER (addCov, src/tiecov.cpp:194-223), and the
+// rounding of that sum depends on the order. Same walk as the -s kernel: one thread per bundle-compacted cell visits the
+// records that can cover it in stream order and adds (double)yc; the cell keeps the bit pattern of the double.
+__global__ void __launch_bounds__(256) cov_exact_cell_kernel(CovIn in, int64_t NB, const long long* __restrict__ bbase,
+                                                             const int32_t* __restrict__ bstart, const int32_t* __restrict__ bend,
+                                                             const uint32_t* __restrict__ rfirst, const uint32_t* __restrict__ pmend,
+                                                             long long* __restrict__ ival, int64_t L) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= L) return;
+  int64_t lo = 0, hi = NB;   // last bundle with base <= x
+  while (hi - lo > 1) { const int64_t m = (lo + hi) >> 1; if (bbase[m] <= x) lo = m; else hi = m; }
+  const int64_t b = lo;
+  const int64_t rel = x - bbase[b];
+  if (rel > (int64_t)bend[b] - bstart[b]) { ival[x] = 0; return; }   // the sentinel cell behind the bundle
+  const int g = bstart[b] + (int)rel;                                 // 1-based coordinate of the cell
+  const uint32_t r0 = rfirst[b], r1 = b + 1 < NB ? rfirst[b + 1] : (uint32_t)in.n;
+  uint32_t a = r0, z = r1;   // first record with pmend >= g
+  while (a < z) { const uint32_t m = a + ((z - a) >> 1); if (pmend[m] >= (uint32_t)g) z = m; else a = m + 1; }
+  const uint32_t first = a;
+  a = first; z = r1;         // first record with start (pos + 1) > g
+  while (a < z) { const uint32_t m = a + ((z - a) >> 1); if (in.pos[m] >= g) z = m; else a = m + 1; }
+  const uint32_t last = a;
+  double sum = 0.0;
+  for (uint32_t i = first; i < last; ++i) {
+    int p = in.pos[i] + 1;
+    bool covered = false;
+    const uint32_t c1 = in.cig_off[i + 1];
+    for (uint32_t c = in.cig_off[i]; c < c1 && p <= g; ++c) {
+      const uint32_t w = in.cigar[c];
+      const uint32_t op = w & 0xf; const int len = (int)(w >> 4);
+      if (op == TB_OP_M) { if (g < p + len) { covered = true; break; } p += len; }
+      else if (op == TB_OP_D || op == TB_OP_N) p += len;
+    }
+    if (covered) sum += (double)in.yc[i];
+  }
+  ival[x] = __double_as_longlong(sum);
+}
+
 struct RunValidIn {
   const long long* cpdepth; const long long* status;
   __device__ uint32_t operator()(int64_t k) const {
@@ -493,7 +542,7 @@ struct RunOut {
     o_tid[exc] = btid[lo];
     o_start[exc] = (int32_t)(c + off);
     o_end[exc] = (int32_t)(c2 + off);
-    o_val[exc] = (double)cpdepth[k] / scale;
+    o_val[exc] = scale > 0.0 ? (double)cpdepth[k] / scale : __longlong_as_double(cpdepth[k]);
   }
 };
 
@@ -538,6 +587,59 @@ __global__ void __launch_bounds__(256) junc_emit_kernel(JTable jt, const uint32_
   o_val[k] = (double)jt.val[s] / COV_FX_SCALE;
 }
 
+// EXACT junction values for weights that are not multiples of 2^-20: the reference adds each record's weight to a double per
+// junction in stream order (addJunction, src/tiecov.cpp:100-112). One thread per emitted junction row walks the records of
+// its bundle that start before the junction and reach beyond it, re-runs the exon state machine of setupCoordinates on each
+// and adds (double)yc when the record has this very junction on this strand.
+__global__ void __launch_bounds__(128) junc_exact_kernel(CovIn in, int64_t NB, const int32_t* __restrict__ btid, const int32_t* __restrict__ bstart,
+                                                         const uint32_t* __restrict__ rfirst, const uint32_t* __restrict__ pmend, int64_t J,
+                                                         const int32_t* __restrict__ o_tid, const int32_t* __restrict__ o_start, const int32_t* __restrict__ o_end,
+                                                         const uint8_t* __restrict__ o_strand, double* __restrict__ o_val) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= J) return;
+  const int tid = o_tid[k], js = o_start[k], je = o_end[k];
+  const unsigned sc = strand_code(o_strand[k]);
+  int64_t lo = 0, hi = NB;   // last bundle with (tid, start) <= (tid, js)
+  while (hi - lo > 1) { const int64_t m = (lo + hi) >> 1; if (btid[m] < tid || (btid[m] == tid && bstart[m] <= js)) lo = m; else hi = m; }
+  const uint32_t r0 = rfirst[lo], r1 = lo + 1 < NB ? rfirst[lo + 1] : (uint32_t)in.n;
+  uint32_t a = r0, z = r1;   // first record whose running maximum end reaches beyond the junction
+  while (a < z) { const uint32_t m = a + ((z - a) >> 1); if (pmend[m] > (uint32_t)je) z = m; else a = m + 1; }
+  const uint32_t first = a;
+  a = first; z = r1;         // first record that starts at or after the junction
+  while (a < z) { const uint32_t m = a + ((z - a) >> 1); if (in.pos[m] + 1 >= js) z = m; else a = m + 1; }
+  const uint32_t last = a;
+  double sum = 0.0;
+  for (uint32_t i = first; i < last; ++i) {
+    if (strand_code(in.strand[i]) != sc) continue;
+    const int pos = in.pos[i];
+    int l = 0, exstart = pos, nclosed = 0, last_end = 0;
+    bool intron = false, ins = false, hit = false;
+    const uint32_t c1 = in.cig_off[i + 1];
+    for (uint32_t c = in.cig_off[i]; c < c1 && !hit; ++c) {
+      const uint32_t cw = in.cigar[c];
+      const uint32_t op = cw & 0xf; const int len = (int)(cw >> 4);
+      if (op == TB_OP_N) {
+        if (!ins || !intron) {
+          if (nclosed > 0 && last_end + 1 == js && exstart == je) hit = true;
+          last_end = pos + l; nclosed++;
+        }
+        exstart = pos + l + len;
+      }
+      const bool refc = (0x18Du >> op) & 1u;
+      const bool known = (0x1BFu >> op) & 1u;
+      l += refc ? len : 0;
+      if (known) {
+        ins = (op == TB_OP_I) || (op == TB_OP_N && ins);
+        intron = (op == TB_OP_N) || (op == TB_OP_I && intron);
+      }
+      if (last_end + 1 > js) break;   // the exons closed so far already end beyond the junction's start
+    }
+    if (!hit && nclosed > 0 && last_end + 1 == js && exstart == je) hit = true;   // the junction that ends at the last exon
+    if (hit) sum += (double)in.yc[i];
+  }
+  o_val[k] = sum;
+}
+
 static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 template <class T>
@@ -551,9 +653,9 @@ static int stage_in(tb_ctx* ctx, DevBuf& b, const T* src, size_t count, int on_d
 
 }  // namespace
 
-int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_juncs_out* juncs, const int32_t* yx_in) {
+int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_juncs_out* juncs, const int32_t* yx_in, CovExt* ext) {
   TB_CUDA(cudaSetDevice(ctx->device));
-  const int64_t n = hin->n;
+  int64_t n = hin->n;   // records processed: all of the window, or (tc_coverage_stream) all but its open last bundle
   if (runs) runs->n_runs = 0;
   if (juncs) juncs->n_juncs = 0;
   if (n == 0) return 0;
@@ -570,14 +672,22 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
   if (stage_in(ctx, ctx->in_stage[2], hin->yc, (size_t)n, hin->on_device, &in.yc)) return 1;
   if (stage_in(ctx, ctx->in_stage[3], hin->strand, (size_t)n, hin->on_device, &in.strand)) return 1;
   if (stage_in(ctx, ctx->in_stage[4], hin->cig_off, (size_t)n + 1, hin->on_device, &in.cig_off)) return 1;
-  if (stage_in(ctx, ctx->in_stage[5], hin->cigar, (size_t)ncig, hin->on_device, &in.cigar)) return 1;
+  {
+    // host arrays: a window of a longer stream keeps its absolute CIGAR offsets (tc_coverage_stream): copy the window's
+    // words only and bias the device pointer so that cigar[cig_off[i]] still lands on them
+    const uint32_t cbase = (!hin->on_device && n > 0) ? hin->cig_off[0] : 0u;
+    const uint32_t* staged = nullptr;
+    if (stage_in(ctx, ctx->in_stage[5], hin->cigar ? hin->cigar + cbase : nullptr, (size_t)ncig, hin->on_device, &staged)) return 1;
+    in.cigar = staged - cbase;
+  }
   const int32_t* d_yx = nullptr;
   if (sample) { if (stage_in(ctx, ctx->in_stage[6], yx_in, (size_t)n, hin->on_device, &d_yx)) return 1; }
 
   DevBuf* B = ctx->buf;
-  if (sample) { TB_CUDA(B[CB_PMEND].ensure(sizeof(uint32_t) * n)); TB_CUDA(B[CB_RFIRST].ensure(sizeof(uint32_t) * n)); }
-  uint32_t* d_pmend = sample ? B[CB_PMEND].as<uint32_t>() : nullptr;
-  uint32_t* d_rfirst = sample ? B[CB_RFIRST].as<uint32_t>() : nullptr;
+  if (sample) TB_CUDA(B[CB_PMEND].ensure(sizeof(uint32_t) * n));
+  TB_CUDA(B[CB_RFIRST].ensure(sizeof(uint32_t) * n));
+  uint32_t* d_pmend = sample ? B[CB_PMEND].as<uint32_t>() : nullptr;   // also filled when the exact path turns out to be needed
+  uint32_t* d_rfirst = B[CB_RFIRST].as<uint32_t>();
   TB_CUDA(B[CB_KEY].ensure(sizeof(uint64_t) * (2 * (size_t)((n + CBK_TILE - 1) / CBK_TILE) + 16)));
   TB_CUDA(B[CB_BID].ensure(sizeof(uint32_t) * n));
   TB_CUDA(B[CB_BSTART].ensure(sizeof(int32_t) * n));
@@ -596,7 +706,7 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
   }
   // ---- K6 ----
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[8], st));
-  {
+  auto launch_k6 = [&]() -> int {
     const int64_t ntiles = (n + CBK_TILE - 1) / CBK_TILE;
     unsigned long long* st_max = B[CB_KEY].as<unsigned long long>();
     unsigned long long* st_cnt = st_max + ntiles;
@@ -610,11 +720,44 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
       cov_bundle_kernel<false><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, do_cov, st_max, st_cnt, ticket, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(),
                                                                         B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_pmend, d_rfirst, d_status);
     ctx->launches++;
-  }
+    return 0;
+  };
+  if (launch_k6()) return 1;
+  if (ext) { cov_tail_kernel<<<1, 1, 0, st>>>(B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_rfirst, d_status); ctx->launches++; }
   // the bundle count decides the size of the next scan
   TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
   if (h_status[ST_LBFAIL]) { ctx->set_error("tc_coverage_window: bundle scan did not make progress (internal error)"); return 1; }
+  if (ext) {
+    // tc_coverage_stream: the record that follows the window continues its last bundle -> leave that bundle to the next window
+    ext->consumed = n;
+    if (ext->has_next && ext->next_tid == (int32_t)h_status[ST_TAIL_TID] && (long long)ext->next_pos + 1 <= h_status[ST_TAIL_END]) {
+      if (h_status[ST_NBUNDLES] <= 1) { ext->consumed = 0; return 3; }   // one bundle spans the whole window: the caller enlarges it
+      const int64_t keep = h_status[ST_TAIL_FIRST];
+      ext->consumed = keep;
+      cov_set_nbundles_kernel<<<1, 1, 0, st>>>(d_status, h_status[ST_NBUNDLES] - 1);
+      ctx->launches++;
+      h_status[ST_NBUNDLES] -= 1;
+      in.n = keep;
+    }
+  }
+  const int64_t n_full = n;
+  n = in.n;
+  // weights that are not multiples of 2^-20 (YC of `tiebrush --store-frac`): the fixed-point sums would differ from the
+  // reference's ordered double sums -> exact path (one ordered walk per cell / per junction). Never silent.
+  const bool exact = !sample && h_status[ST_INEXACT] != 0 && !getenv("TB_COV_FIXED_ONLY");
+  ctx->last_cov_exact = exact ? 1 : 0;
+  if (exact) {
+    TB_CUDA(B[CB_PMEND].ensure(sizeof(uint32_t) * n_full));
+    d_pmend = B[CB_PMEND].as<uint32_t>();
+    const int64_t nb_keep = h_status[ST_NBUNDLES];
+    const int64_t n_eff = n;
+    in.n = n_full; n = n_full;
+    if (launch_k6()) return 1;          // second run: also the running maximum of the ends (pmend) for the ordered walks
+    in.n = n_eff; n = n_eff;
+    cov_set_nbundles_kernel<<<1, 1, 0, st>>>(d_status, nb_keep);
+    ctx->launches++;
+  }
   const int64_t NB = h_status[ST_NBUNDLES];
   size_t agg_bytes = (size_t)(tb_scan_blocks(n > 2 * ncig + 16 ? n : 2 * ncig + 16) + 8) * sizeof(SumNz);
   TB_CUDA(B[CB_AGG].ensure(agg_bytes));
@@ -643,14 +786,21 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     while ((int64_t)jcap < want) jcap <<= 1;
   }
   uint64_t seed = 0x9e3779b97f4a7c15ULL;
-  if (sample) {   // the cell array takes the place of the difference array
+  const bool cells = sample || (exact && do_cov);   // a per-cell value array takes the place of the difference array
+  if (cells) {
     TB_CUDA(B[CB_DIFF].ensure(sizeof(int64_t) * (L + 1)));
     if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
-    cov_sample_cell_kernel<<<grid_for(L, 256), 256, 0, st>>>(in, d_yx, NB, B[CB_BBASE].as<long long>(), B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(),
-                                                            d_rfirst, d_pmend, B[CB_DIFF].as<long long>(), L);
+    if (sample)
+      cov_sample_cell_kernel<<<grid_for(L, 256), 256, 0, st>>>(in, d_yx, NB, B[CB_BBASE].as<long long>(), B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(),
+                                                              d_rfirst, d_pmend, B[CB_DIFF].as<long long>(), L);
+    else
+      cov_exact_cell_kernel<<<grid_for(L, 256), 256, 0, st>>>(in, NB, B[CB_BBASE].as<long long>(), B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(),
+                                                             d_rfirst, d_pmend, B[CB_DIFF].as<long long>(), L);
     ctx->launches++;
     if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[1], st));
-  } else
+  }
+  const int acc_cov = do_cov && !cells;   // the accumulate kernel still finds the junction keys on the exact path
+  if (!sample && (acc_cov || do_junc))
   for (int attempt = 0;; ++attempt) {
     if (do_junc) {
       TB_CUDA(B[CB_JTAG].ensure(sizeof(uint64_t) * jcap));
@@ -661,16 +811,16 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
       junc_init_kernel<<<grid_for(jcap, 256), 256, 0, st>>>(jt, jcap);
       ctx->launches++;
     }
-    if (do_cov) {
+    if (acc_cov) {
       TB_CUDA(B[CB_DIFF].ensure(sizeof(int64_t) * (L + 1)));
       TB_CUDA(cudaMemsetAsync(B[CB_DIFF].p, 0, sizeof(int64_t) * (L + 1), st));
     }
     // ---- K7 (+K9 insert): the dominant kernel ----
-    if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
+    if (ctx->profiling && !cells) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
     cov_accumulate_kernel<<<grid_for(n, COV_THREADS * COV_RPT), COV_THREADS, 0, st>>>(in, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(), B[CB_BBASE].as<long long>(),
-                                                           B[CB_DIFF].as<long long>(), do_cov, do_junc, jt, d_status);
+                                                           B[CB_DIFF].as<long long>(), acc_cov, do_junc, jt, d_status);
     ctx->launches++;
-    if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[1], st));
+    if (ctx->profiling && !cells) TB_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (!do_junc) break;
     TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
     TB_CUDA(cudaStreamSynchronize(st));
@@ -693,7 +843,7 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     long long* d_diff = B[CB_DIFF].as<long long>();
     long long* cppos = B[CB_CPPOS].as<long long>();
     long long* cpdepth = B[CB_CPDEPTH].as<long long>();
-    if (sample) {
+    if (cells) {
       TB_CUDA((tb_device_scan<OpSumU32>(ctx, ChgIn{d_diff}, L, B[CB_AGG].as<uint32_t>(), ChgOut{d_diff, cppos, cpdepth})));
       cov_store_nchange_kernel<<<1, 1, 0, st>>>(B[CB_AGG].as<uint32_t>() + tb_scan_blocks(L), d_status);
     } else {
@@ -717,7 +867,7 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
       o_val = ctx->out_stage[3].as<double>();
     }
     RunOut ro{cppos, cpdepth, d_status, B[CB_BBASE].as<long long>(), B[CB_BSTART].as<int32_t>(), B[CB_BTID].as<int32_t>(),
-              o_tid, o_start, o_end, o_val, stage_cap, sample ? 1.0 : COV_FX_SCALE};
+              o_tid, o_start, o_end, o_val, stage_cap, sample ? 1.0 : (cells ? 0.0 : COV_FX_SCALE)};
     TB_CUDA((tb_device_scan<OpSumU32>(ctx, RunValidIn{cpdepth, d_status}, K, B[CB_AGG].as<uint32_t>(), ro)));
     cov_store_total_kernel<<<1, 1, 0, st>>>(nullptr, B[CB_AGG].as<uint32_t>() + tb_scan_blocks(K), d_status);
     ctx->launches++;
@@ -776,6 +926,11 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
       }
       junc_emit_kernel<<<grid_for(J, 256), 256, 0, st>>>(jt, rv2, J, o_tid, o_start, o_end, o_strand, o_val);
       ctx->launches++;
+      if (exact) {   // ordered double sums replace the fixed-point values
+        junc_exact_kernel<<<grid_for(J, 128), 128, 0, st>>>(in, NB, B[CB_BTID].as<int32_t>(), B[CB_BSTART].as<int32_t>(), d_rfirst, d_pmend, J,
+                                                           o_tid, o_start, o_end, o_strand, o_val);
+        ctx->launches++;
+      }
       if (!juncs->on_device) {
         TB_CUDA(cudaMemcpyAsync(juncs->tid, o_tid, sizeof(int32_t) * J, cudaMemcpyDeviceToHost, st));
         TB_CUDA(cudaMemcpyAsync(juncs->start, o_start, sizeof(int32_t) * J, cudaMemcpyDeviceToHost, st));

@@ -1,0 +1,519 @@
+// shard.cu — tiecov over long streams and over several GPUs (reference counterparts: the bundle invariant
+// src/tiecov.cpp:443-481, the global junction counter :92-94, and tiewrap.py:42-123, the reference's only parallel mode).
+//
+//   tc_coverage_stream   one coordinate-sorted stream slice, cut into windows of at most `window` records AT BUNDLE HEADS: a
+//                        window whose last bundle is continued by the record behind it leaves that bundle to the next
+//                        window (CovExt, coverage.cu), so every window holds whole bundles and the concatenated outputs are
+//                        those of one pass. Works on device-resident and on host arrays (one H2D copy per window).
+//   tc_shard_coverage    one rank's part of a run that is sharded by coordinate over the GPUs of a box, one process (or
+//                        thread) per GPU. A bundle belongs to the rank that holds its first record: the records a rank
+//                        holds of a bundle that was opened further left (its "lead") travel to that owner over NCCL
+//                        (ncclAllGather of the open-bundle state: maximum (tid,end) key and lead sizes; grouped
+//                        ncclSend / ncclRecv of the lead records' columns), the owner processes them with the rest of the
+//                        bundle. Every rank then works on whole bundles only: no stitching, results identical to one GPU.
+//   tc_shard_gather      ordered gather of the per-rank runs / junction rows on rank 0 (ncclAllGather of the counts,
+//                        grouped ncclSend / ncclRecv of the rows); the junction numbering base of every rank
+//                        (JUNC%08d is a global counter, tiecov.cpp:92-94) is the prefix sum of the counts.
+//
+// NCCL is loaded at run time (dlopen of libnccl.so.2: inside a PyTorch process that is the library torch already
+// mapped); a single-GPU run never touches it.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <algorithm>
+#include "tb_common.cuh"
+
+int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* in, tc_runs_out* runs, tc_juncs_out* juncs, const int32_t* yx, CovExt* ext);
+
+namespace {
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  std::string err;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+#define TB_NCCL_SYM(field, name) do { *(void**)(&field) = dlsym(lib, name); if (!field) { err = std::string("libnccl lacks ") + name; lib = nullptr; return false; } } while (0)
+    TB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); TB_NCCL_SYM(CommInitRank, "ncclCommInitRank"); TB_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    TB_NCCL_SYM(GetErrorString, "ncclGetErrorString"); TB_NCCL_SYM(AllGather, "ncclAllGather"); TB_NCCL_SYM(Send, "ncclSend");
+    TB_NCCL_SYM(Recv, "ncclRecv"); TB_NCCL_SYM(GroupStart, "ncclGroupStart"); TB_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+#undef TB_NCCL_SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+
+#define TB_NCCL(call)                                                                                           \
+  do {                                                                                                          \
+    ncclResult_t r__ = (call);                                                                                  \
+    if (r__ != ncclSuccess) { ctx->set_error("NCCL error %s at %s:%d: %s", #call, __FILE__, __LINE__, g_nccl.GetErrorString(r__)); return 1; } \
+  } while (0)
+
+// workspace slots of this file in ctx->shard_buf
+enum { SB_GATHER = 0, SB_SEND, SB_TAIL_TID, SB_TAIL_POS, SB_TAIL_YC, SB_TAIL_STRAND, SB_TAIL_OFF, SB_TAIL_CIG, SB_SEAM_TID, SB_SEAM_POS, SB_SEAM_YC,
+       SB_SEAM_STRAND, SB_SEAM_OFF, SB_SEAM_CIG, SB_COUNT_ };
+static_assert(SB_COUNT_ <= 16, "raise tb_ctx::shard_buf");
+
+// ---- open-bundle state of a slice: maximum (tid << 32 | end) key over its records ----
+__global__ void __launch_bounds__(256) shard_maxkey_kernel(int64_t n, const int32_t* __restrict__ tid, const int32_t* __restrict__ pos,
+                                                           const uint32_t* __restrict__ cig_off, const uint32_t* __restrict__ cigar, unsigned long long* __restrict__ out) {
+  unsigned long long m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int l = 0;
+    for (uint32_t c = cig_off[i]; c < cig_off[i + 1]; ++c) { const uint32_t w = cigar[c]; if ((0x18Du >> (w & 0xf)) & 1u) l += (int)(w >> 4); }
+    const unsigned long long key = ((unsigned long long)(uint32_t)tid[i] << 32) | (uint32_t)(pos[i] + l);
+    m = key > m ? key : m;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, d); m = o > m ? o : m; }
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// ---- lead of a slice: the records before its first bundle head, given the open-bundle state `ein` of everything left of
+// it (0 = nothing). One block walks the slice 1024 records at a time until a head shows up. out[0] = lead. ----
+__global__ void __launch_bounds__(1024) shard_lead_kernel(int64_t n, const int32_t* __restrict__ tid, const int32_t* __restrict__ pos,
+                                                          const uint32_t* __restrict__ cig_off, const uint32_t* __restrict__ cigar, unsigned long long ein,
+                                                          long long* __restrict__ out) {
+  __shared__ unsigned long long s_scan[33];
+  __shared__ long long s_first;
+  unsigned long long carry = ein;
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    unsigned long long key = 0;
+    if (i < n) {
+      int l = 0;
+      for (uint32_t c = cig_off[i]; c < cig_off[i + 1]; ++c) { const uint32_t w = cigar[c]; if ((0x18Du >> (w & 0xf)) & 1u) l += (int)(w >> 4); }
+      key = ((unsigned long long)(uint32_t)tid[i] << 32) | (uint32_t)(pos[i] + l);
+    }
+    if (threadIdx.x == 0) s_first = -1;
+    unsigned long long tot;
+    const unsigned long long exc = tb_block_exscan<OpMaxU64>(key, s_scan, &tot);   // barriers inside: s_first is visible
+    const unsigned long long run = exc > carry ? exc : carry;                       // maximum key of everything before record i
+    if (i < n) {
+      const bool head = run == 0 || tid[i] != (int)(run >> 32) || (pos[i] + 1) > (int)(uint32_t)run;   // tiecov.cpp:443
+      if (head) atomicMin((unsigned long long*)&s_first, (unsigned long long)i);
+    }
+    __syncthreads();
+    if (s_first >= 0) { if (threadIdx.x == 0) out[0] = s_first; return; }
+    carry = tot > carry ? tot : carry;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = n;   // no head at all: the whole slice continues a bundle opened further left
+}
+
+// offsets src[0..count) of a piece (absolute offsets of whoever filled it) -> dst[i] = src[i] - src[0] + dst0
+__global__ void __launch_bounds__(256) shard_copy_off_kernel(const uint32_t* __restrict__ src, int64_t count, uint32_t dst0, uint32_t* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = src[i] - src[0] + dst0;
+}
+
+static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// sub-window [w0, w0 + len) of a slice as its own tc_soa_in (absolute CIGAR offsets are kept)
+static tc_soa_in sub_window(const tc_soa_in& in, int64_t w0, int64_t len, int64_t words) {
+  tc_soa_in s = in;
+  s.n = len;
+  s.tid = in.tid + w0; s.pos = in.pos + w0; s.yc = in.yc + w0; s.strand = in.strand + w0; s.cig_off = in.cig_off + w0;
+  s.n_cig = words;
+  return s;
+}
+
+}  // namespace
+
+// One stream slice in windows cut at bundle heads. `skip` leading records are not processed (they belong to a bundle that
+// another rank owns). next = {tid, pos} of the record that follows the slice in the stream (host values), or NULL.
+// Outputs are appended to runs / juncs (n_runs / n_juncs on entry = rows already there). *consumed = records processed.
+int tc_stream_impl(tb_ctx* ctx, const tc_soa_in* in, int64_t skip, int64_t window, const int32_t* next, tc_runs_out* runs, tc_juncs_out* juncs, int64_t* consumed) {
+  TB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = in->n;
+  if (window < 1024) window = 1024;
+  if (window >= (1LL << 31)) window = (1LL << 31) - 1;
+  int64_t w0 = skip;
+  float ms_acc[3] = {0.f, 0.f, 0.f};
+  while (w0 < n) {
+    int64_t wlen = std::min(window, n - w0);
+    for (;;) {
+      const int64_t w1 = w0 + wlen;
+      CovExt ext; memset(&ext, 0, sizeof(ext));
+      uint32_t c01[2] = {0, 0};
+      int32_t nx[2] = {0, 0};
+      if (in->on_device) {
+        TB_CUDA(cudaMemcpyAsync(&c01[0], in->cig_off + w0, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TB_CUDA(cudaMemcpyAsync(&c01[1], in->cig_off + w1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (w1 < n) {
+          TB_CUDA(cudaMemcpyAsync(&nx[0], in->tid + w1, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+          TB_CUDA(cudaMemcpyAsync(&nx[1], in->pos + w1, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        TB_CUDA(cudaStreamSynchronize(ctx->stream));
+      } else {
+        c01[0] = in->cig_off[w0]; c01[1] = in->cig_off[w1];
+        if (w1 < n) { nx[0] = in->tid[w1]; nx[1] = in->pos[w1]; }
+      }
+      if (w1 < n) { ext.has_next = 1; ext.next_tid = nx[0]; ext.next_pos = nx[1]; }
+      else if (next) { ext.has_next = 1; ext.next_tid = next[0]; ext.next_pos = next[1]; }
+      tc_soa_in sub = sub_window(*in, w0, wlen, (int64_t)(c01[1] - c01[0]));
+      tc_runs_out r; tc_juncs_out j;
+      if (runs) {
+        r = *runs; r.capacity = runs->capacity - runs->n_runs; r.n_runs = 0;
+        r.tid = runs->tid + runs->n_runs; r.start0 = runs->start0 + runs->n_runs; r.end0 = runs->end0 + runs->n_runs; r.value = runs->value + runs->n_runs;
+      }
+      if (juncs) {
+        j = *juncs; j.capacity = juncs->capacity - juncs->n_juncs; j.n_juncs = 0;
+        j.tid = juncs->tid + juncs->n_juncs; j.start = juncs->start + juncs->n_juncs; j.end = juncs->end + juncs->n_juncs;
+        j.strand = juncs->strand + juncs->n_juncs; j.value = juncs->value + juncs->n_juncs;
+      }
+      const int rc = tc_coverage_impl(ctx, &sub, runs ? &r : nullptr, juncs ? &j : nullptr, nullptr, &ext);
+      if (rc == 3) {   // one bundle spans the window
+        if (w1 >= n) { *consumed = w0; goto done; }   // ... and the slice: the caller joins it with what follows
+        wlen = std::min(wlen * 2, n - w0);
+        continue;
+      }
+      if (rc) return rc;
+      if (runs) runs->n_runs += r.n_runs;
+      if (juncs) juncs->n_juncs += j.n_juncs;
+      ms_acc[0] += ctx->last_ms[6]; ms_acc[1] += ctx->last_ms[1]; ms_acc[2] += ctx->last_ms[7];
+      ctx->stream_windows++;
+      if (ext.consumed < wlen && w1 >= n) { *consumed = w0 + ext.consumed; goto done; }   // the open tail belongs with the records behind the slice
+      w0 += ext.consumed;
+      break;
+    }
+  }
+  *consumed = n;
+done:
+  ctx->last_ms[6] = ms_acc[0]; ctx->last_ms[1] = ms_acc[1]; ctx->last_ms[7] = ms_acc[2];   // sums over the windows of this call
+  return 0;
+}
+
+extern "C" {
+
+int tb_comm_unique_id(void* id128) {
+  if (!g_nccl.load()) { g_tb_global_error = "tb_comm_unique_id: " + g_nccl.err; return 1; }
+  ncclUniqueId id;
+  const ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) { g_tb_global_error = std::string("tb_comm_unique_id: ") + g_nccl.GetErrorString(r); return 1; }
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int tb_comm_init(tb_ctx* ctx, int rank, int world, const void* id128) {
+  if (!ctx) return 1;
+  if (!g_nccl.load()) { ctx->set_error("tb_comm_init: %s", g_nccl.err.c_str()); return 1; }
+  if (world < 1 || rank < 0 || rank >= world) { ctx->set_error("tb_comm_init: rank %d of %d", rank, world); return 1; }
+  TB_CUDA(cudaSetDevice(ctx->device));
+  ncclUniqueId id; memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm = nullptr;
+  TB_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
+  ctx->comm = (void*)comm; ctx->rank = rank; ctx->world = world;
+  return 0;
+}
+
+int tb_comm_destroy(tb_ctx* ctx) {
+  if (!ctx || !ctx->comm) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  g_nccl.CommDestroy((ncclComm_t)ctx->comm);
+  ctx->comm = nullptr; ctx->world = 1; ctx->rank = 0;
+  return 0;
+}
+
+int tb_comm_rank(tb_ctx* ctx) { return ctx ? ctx->rank : -1; }
+int tb_comm_world(tb_ctx* ctx) { return ctx ? ctx->world : -1; }
+
+int tc_coverage_stream(tb_ctx* ctx, const tc_soa_in* in, int64_t window, const int32_t* next_tid_pos, tc_runs_out* runs, tc_juncs_out* juncs, int64_t* consumed) {
+  if (!ctx) return 1;
+  if (!in || (!runs && !juncs) || !consumed) { ctx->set_error("tc_coverage_stream: in, consumed and one of runs / juncs are required"); return 1; }
+  ctx->err.clear();
+  if (runs) runs->n_runs = 0;
+  if (juncs) juncs->n_juncs = 0;
+  ctx->stream_windows = 0;
+  return tc_stream_impl(ctx, in, 0, window, next_tid_pos, runs, juncs, consumed);
+}
+
+int tc_shard_coverage(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t window, tc_runs_out* runs, tc_juncs_out* juncs) {
+  if (!ctx) return 1;
+  if (!segs || n_segs < 1 || (!runs && !juncs)) { ctx->set_error("tc_shard_coverage: segments and one of runs / juncs are required"); return 1; }
+  for (int s = 0; s < n_segs; ++s) if (!segs[s].on_device) { ctx->set_error("tc_shard_coverage: segments must be device resident"); return 1; }
+  ctx->err.clear();
+  TB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (runs) runs->n_runs = 0;
+  if (juncs) juncs->n_juncs = 0;
+  ctx->stream_windows = 0;
+  memset(ctx->shard_stat, 0, sizeof(ctx->shard_stat));
+  const int W = ctx->comm ? ctx->world : 1, R = ctx->comm ? ctx->rank : 0;
+  const tc_soa_in& first = segs[0];
+  const tc_soa_in& last = segs[n_segs - 1];
+  int64_t n_local = 0;
+  for (int s = 0; s < n_segs; ++s) n_local += segs[s].n;
+  int64_t lead = 0, tail_n = 0, tail_words = 0;
+  int32_t tail_next[2] = {0, 0};
+  DevBuf* SB = ctx->shard_buf;
+  cudaEvent_t e0 = ctx->ev[12], e1 = ctx->ev[13];
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(e0, st));
+  if (W > 1) {
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    // ---- 1. open-bundle state of every rank: allgather of {max key of the last segment, first record key, records} ----
+    TB_CUDA(SB[SB_GATHER].ensure(sizeof(unsigned long long) * 8 * (size_t)(W + 1)));
+    TB_CUDA(ctx->pinned[1].ensure(sizeof(unsigned long long) * 8 * (size_t)(W + 1)));
+    unsigned long long* d_mine = SB[SB_GATHER].as<unsigned long long>();
+    unsigned long long* d_all = d_mine + 8;
+    unsigned long long* h_all = ctx->pinned[1].as<unsigned long long>();
+    TB_CUDA(cudaMemsetAsync(d_mine, 0, sizeof(unsigned long long) * 8, st));
+    if (last.n > 0) {
+      shard_maxkey_kernel<<<std::min<unsigned>(grid_for(last.n, 256), 148u * 8u), 256, 0, st>>>(last.n, last.tid, last.pos, last.cig_off, last.cigar, d_mine);
+      ctx->launches++;
+    }
+    {
+      unsigned long long h_mine[3] = {0, 0, (unsigned long long)n_local};
+      if (first.n > 0) {
+        int32_t tp[2];
+        TB_CUDA(cudaMemcpyAsync(&tp[0], first.tid, 4, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(cudaMemcpyAsync(&tp[1], first.pos, 4, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(cudaStreamSynchronize(st));
+        h_mine[1] = ((unsigned long long)(uint32_t)tp[0] << 32) | (uint32_t)tp[1];
+      }
+      TB_CUDA(cudaMemcpyAsync(d_mine + 1, &h_mine[1], sizeof(unsigned long long) * 2, cudaMemcpyHostToDevice, st));
+    }
+    TB_NCCL(g_nccl.AllGather(d_mine, d_all, 4, ncclUint64, comm, st));
+    TB_CUDA(cudaMemcpyAsync(h_all, d_all, sizeof(unsigned long long) * 4 * W, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    unsigned long long ein = 0;
+    for (int r = 0; r < R; ++r) if (h_all[4 * r + 2] > 0 && h_all[4 * r] > ein) ein = h_all[4 * r];
+    std::vector<unsigned long long> firstkey(W), nrec(W);
+    for (int r = 0; r < W; ++r) { firstkey[r] = h_all[4 * r + 1]; nrec[r] = h_all[4 * r + 2]; }
+    // ---- 2. my lead; allgather of {lead, lead CIGAR words, has a head, records of the first segment} ----
+    long long* d_lead = (long long*)(d_mine + 4);
+    uint32_t lead_c[2] = {0, 0};
+    if (first.n > 0 && ein != 0) {
+      shard_lead_kernel<<<1, 1024, 0, st>>>(first.n, first.tid, first.pos, first.cig_off, first.cigar, ein, d_lead);
+      ctx->launches++;
+      TB_CUDA(cudaMemcpyAsync(&lead, d_lead, sizeof(long long), cudaMemcpyDeviceToHost, st));
+      TB_CUDA(cudaStreamSynchronize(st));
+      if (lead == first.n && n_segs > 1) { ctx->set_error("tc_shard_coverage: the first segment of rank %d lies inside one bundle; segments of a rank must end at reference-id boundaries", R); return 1; }
+      if (lead > 0) {
+        TB_CUDA(cudaMemcpyAsync(&lead_c[0], first.cig_off, 4, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(cudaMemcpyAsync(&lead_c[1], first.cig_off + lead, 4, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(cudaStreamSynchronize(st));
+      }
+    }
+    {
+      unsigned long long h2[4] = {(unsigned long long)lead, (unsigned long long)(lead_c[1] - lead_c[0]), (unsigned long long)(n_local > 0 && lead < n_local ? 1 : 0), (unsigned long long)first.n};
+      TB_CUDA(cudaMemcpyAsync(d_mine, h2, sizeof(h2), cudaMemcpyHostToDevice, st));
+    }
+    TB_NCCL(g_nccl.AllGather(d_mine, d_all, 4, ncclUint64, comm, st));
+    TB_CUDA(cudaMemcpyAsync(h_all, d_all, sizeof(unsigned long long) * 4 * W, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    std::vector<long long> leads(W), lwords(W), hashead(W);
+    for (int r = 0; r < W; ++r) { leads[r] = (long long)h_all[4 * r]; lwords[r] = (long long)h_all[4 * r + 1]; hashead[r] = (long long)h_all[4 * r + 2]; }
+    // ---- 3. who sends to whom: the lead of rank r goes to the nearest rank on its left that holds a bundle head ----
+    int owner = -1;
+    if (lead > 0) { for (int r = R - 1; r >= 0; --r) if (hashead[r]) { owner = r; break; } }
+    if (lead > 0 && owner < 0) { ctx->set_error("tc_shard_coverage: rank %d has a lead but no rank on its left holds a bundle head", R); return 1; }
+    std::vector<int> from;
+    if (hashead[R]) {
+      for (int r = R + 1; r < W; ++r) {
+        if (nrec[r] == 0) continue;
+        if (leads[r] > 0) from.push_back(r);
+        if (hashead[r]) break;
+      }
+    }
+    for (int r : from) { tail_n += leads[r]; tail_words += lwords[r]; }
+    if (!from.empty()) { const unsigned long long fk = firstkey[from[0]]; tail_next[0] = (int32_t)(fk >> 32); tail_next[1] = (int32_t)(uint32_t)fk; }
+    if (tail_words >= (1LL << 32) || tail_n >= (1LL << 31)) { ctx->set_error("tc_shard_coverage: %lld lead records do not fit one window", (long long)tail_n); return 1; }
+    if (tail_n > 0) {
+      TB_CUDA(SB[SB_TAIL_TID].ensure(sizeof(int32_t) * tail_n)); TB_CUDA(SB[SB_TAIL_POS].ensure(sizeof(int32_t) * tail_n));
+      TB_CUDA(SB[SB_TAIL_YC].ensure(sizeof(float) * tail_n)); TB_CUDA(SB[SB_TAIL_STRAND].ensure((size_t)tail_n));
+      TB_CUDA(SB[SB_TAIL_OFF].ensure(sizeof(uint32_t) * (tail_n + 1))); TB_CUDA(SB[SB_SEND].ensure(sizeof(uint32_t) * (tail_n + from.size() + 1)));
+      TB_CUDA(SB[SB_TAIL_CIG].ensure(sizeof(uint32_t) * (tail_words + 4)));
+    }
+    // ---- 4. the halo exchange proper: one grouped send / receive of the lead records' columns ----
+    TB_NCCL(g_nccl.GroupStart());
+    if (lead > 0) {
+      TB_NCCL(g_nccl.Send(first.tid, (size_t)lead * 4, ncclUint8, owner, comm, st));
+      TB_NCCL(g_nccl.Send(first.pos, (size_t)lead * 4, ncclUint8, owner, comm, st));
+      TB_NCCL(g_nccl.Send(first.yc, (size_t)lead * 4, ncclUint8, owner, comm, st));
+      TB_NCCL(g_nccl.Send(first.strand, (size_t)lead, ncclUint8, owner, comm, st));
+      TB_NCCL(g_nccl.Send(first.cig_off, (size_t)(lead + 1) * 4, ncclUint8, owner, comm, st));
+      TB_NCCL(g_nccl.Send(first.cigar + lead_c[0], (size_t)(lead_c[1] - lead_c[0]) * 4, ncclUint8, owner, comm, st));
+      ctx->shard_stat[1] = lead; ctx->shard_stat[3] = (int64_t)lead * 17 + 4 + (int64_t)(lead_c[1] - lead_c[0]) * 4;
+    }
+    {
+      int64_t ro = 0, wo = 0; size_t piece = 0;
+      for (int r : from) {
+        TB_NCCL(g_nccl.Recv(SB[SB_TAIL_TID].as<int32_t>() + ro, (size_t)leads[r] * 4, ncclUint8, r, comm, st));
+        TB_NCCL(g_nccl.Recv(SB[SB_TAIL_POS].as<int32_t>() + ro, (size_t)leads[r] * 4, ncclUint8, r, comm, st));
+        TB_NCCL(g_nccl.Recv(SB[SB_TAIL_YC].as<float>() + ro, (size_t)leads[r] * 4, ncclUint8, r, comm, st));
+        TB_NCCL(g_nccl.Recv(SB[SB_TAIL_STRAND].as<uint8_t>() + ro, (size_t)leads[r], ncclUint8, r, comm, st));
+        // the leads + 1 offsets of piece p land in a scratch area at [ro + p, ...) and are rebased into the tail below
+        TB_NCCL(g_nccl.Recv(SB[SB_SEND].as<uint32_t>() + ro + piece, (size_t)(leads[r] + 1) * 4, ncclUint8, r, comm, st));
+        TB_NCCL(g_nccl.Recv(SB[SB_TAIL_CIG].as<uint32_t>() + wo, (size_t)lwords[r] * 4, ncclUint8, r, comm, st));
+        ro += leads[r]; wo += lwords[r]; ++piece;
+      }
+    }
+    TB_NCCL(g_nccl.GroupEnd());
+    ctx->shard_stat[0] = tail_n; ctx->shard_stat[2] = (int64_t)from.size();
+    // ---- 5. received offsets -> offsets into the tail arena, piece by piece ----
+    if (tail_n > 0) {
+      int64_t ro = 0, wo = 0; size_t piece = 0;
+      for (int r : from) {
+        shard_copy_off_kernel<<<grid_for(leads[r] + 1, 256), 256, 0, st>>>(SB[SB_SEND].as<uint32_t>() + ro + piece, leads[r] + 1, (uint32_t)wo, SB[SB_TAIL_OFF].as<uint32_t>() + ro);
+        ctx->launches++;
+        ro += leads[r]; wo += lwords[r]; ++piece;
+      }
+    }
+  }
+  if (ctx->profiling) TB_CUDA(cudaEventRecord(e1, st));
+  // ---- 6. this rank's whole bundles, segment by segment ----
+  int64_t consumed_last = last.n;
+  for (int s = 0; s < n_segs; ++s) {
+    const bool is_last = s == n_segs - 1;
+    int64_t consumed = 0;
+    const int64_t skip = s == 0 ? lead : 0;
+    if (skip >= segs[s].n) { if (is_last) consumed_last = segs[s].n; continue; }
+    const int rc = tc_stream_impl(ctx, &segs[s], skip, window, (is_last && tail_n > 0) ? tail_next : nullptr, runs, juncs, &consumed);
+    if (rc) return rc;
+    if (is_last) consumed_last = consumed;
+    else if (consumed < segs[s].n) { ctx->set_error("tc_shard_coverage: segment %d of rank %d ends inside a bundle; segments of a rank must end at reference-id boundaries", s, R); return 1; }
+  }
+  // ---- 7. the seam: what the last segment left open + the leads received from the right ----
+  const int64_t open_n = (lead >= last.n && n_segs == 1) ? 0 : last.n - consumed_last;
+  if (open_n + tail_n > 0 && !(open_n == 0 && tail_n == 0)) {
+    if (open_n > 0 && tail_n == 0) {   // cannot happen: the stream leaves a tail only when told that something follows
+      ctx->set_error("tc_shard_coverage: open tail without a continuation (internal error)"); return 1;
+    }
+    const int64_t sn = open_n + tail_n;
+    uint32_t oc[2] = {0, 0};
+    if (open_n > 0) {
+      TB_CUDA(cudaMemcpyAsync(&oc[0], last.cig_off + consumed_last, 4, cudaMemcpyDeviceToHost, st));
+      TB_CUDA(cudaMemcpyAsync(&oc[1], last.cig_off + last.n, 4, cudaMemcpyDeviceToHost, st));
+      TB_CUDA(cudaStreamSynchronize(st));
+    }
+    const int64_t ow = (int64_t)(oc[1] - oc[0]), sw = ow + tail_words;
+    TB_CUDA(SB[SB_SEAM_TID].ensure(sizeof(int32_t) * sn)); TB_CUDA(SB[SB_SEAM_POS].ensure(sizeof(int32_t) * sn)); TB_CUDA(SB[SB_SEAM_YC].ensure(sizeof(float) * sn));
+    TB_CUDA(SB[SB_SEAM_STRAND].ensure((size_t)sn)); TB_CUDA(SB[SB_SEAM_OFF].ensure(sizeof(uint32_t) * (sn + 1))); TB_CUDA(SB[SB_SEAM_CIG].ensure(sizeof(uint32_t) * (sw + 4)));
+    auto d2d = [&](void* dst, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st) : cudaSuccess; };
+    TB_CUDA(d2d(SB[SB_SEAM_TID].p, last.tid + consumed_last, sizeof(int32_t) * open_n));
+    TB_CUDA(d2d(SB[SB_SEAM_POS].p, last.pos + consumed_last, sizeof(int32_t) * open_n));
+    TB_CUDA(d2d(SB[SB_SEAM_YC].p, last.yc + consumed_last, sizeof(float) * open_n));
+    TB_CUDA(d2d(SB[SB_SEAM_STRAND].p, last.strand + consumed_last, (size_t)open_n));
+    TB_CUDA(d2d(SB[SB_SEAM_CIG].p, last.cigar + oc[0], sizeof(uint32_t) * ow));
+    TB_CUDA(d2d(SB[SB_SEAM_TID].as<int32_t>() + open_n, SB[SB_TAIL_TID].p, sizeof(int32_t) * tail_n));
+    TB_CUDA(d2d(SB[SB_SEAM_POS].as<int32_t>() + open_n, SB[SB_TAIL_POS].p, sizeof(int32_t) * tail_n));
+    TB_CUDA(d2d(SB[SB_SEAM_YC].as<float>() + open_n, SB[SB_TAIL_YC].p, sizeof(float) * tail_n));
+    TB_CUDA(d2d(SB[SB_SEAM_STRAND].as<uint8_t>() + open_n, SB[SB_TAIL_STRAND].p, (size_t)tail_n));
+    TB_CUDA(d2d(SB[SB_SEAM_CIG].as<uint32_t>() + ow, SB[SB_TAIL_CIG].p, sizeof(uint32_t) * tail_words));
+    if (open_n > 0) { shard_copy_off_kernel<<<grid_for(open_n, 256), 256, 0, st>>>(last.cig_off + consumed_last, open_n, 0u, SB[SB_SEAM_OFF].as<uint32_t>()); ctx->launches++; }
+    shard_copy_off_kernel<<<grid_for(tail_n + 1, 256), 256, 0, st>>>(SB[SB_TAIL_OFF].as<uint32_t>(), tail_n + 1, (uint32_t)ow, SB[SB_SEAM_OFF].as<uint32_t>() + open_n);
+    ctx->launches++;
+    tc_soa_in seam; memset(&seam, 0, sizeof(seam));
+    seam.n = sn; seam.tid = SB[SB_SEAM_TID].as<int32_t>(); seam.pos = SB[SB_SEAM_POS].as<int32_t>(); seam.yc = SB[SB_SEAM_YC].as<float>();
+    seam.strand = SB[SB_SEAM_STRAND].as<uint8_t>(); seam.cig_off = SB[SB_SEAM_OFF].as<uint32_t>(); seam.cigar = SB[SB_SEAM_CIG].as<uint32_t>();
+    seam.on_device = 1; seam.n_cig = sw;
+    int64_t consumed = 0;
+    const float keep[3] = {ctx->last_ms[6], ctx->last_ms[1], ctx->last_ms[7]};
+    const int rc = tc_stream_impl(ctx, &seam, 0, std::max<int64_t>(window, sn), nullptr, runs, juncs, &consumed);
+    if (rc) return rc;
+    ctx->last_ms[6] += keep[0]; ctx->last_ms[1] += keep[1]; ctx->last_ms[7] += keep[2];
+    ctx->shard_stat[4] = sn;
+  }
+  if (ctx->profiling) {
+    TB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) ctx->last_ms[9] = ms;
+    (void)cudaGetLastError();
+  }
+  return 0;
+}
+
+int64_t tc_shard_stat(tb_ctx* ctx, int which) { return (ctx && which >= 0 && which < 8) ? ctx->shard_stat[which] : -1; }
+
+// ordered gather on rank 0. all_runs / all_juncs (rank 0 only; device arrays) receive the rows of rank 0, 1, ... in that
+// order; junc_base[r] (host, [world+1], every rank) = junctions of the ranks before r.
+int tc_shard_gather(tb_ctx* ctx, const tc_runs_out* runs, const tc_juncs_out* juncs, tc_runs_out* all_runs, tc_juncs_out* all_juncs, int64_t* junc_base) {
+  if (!ctx) return 1;
+  ctx->err.clear();
+  TB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int W = ctx->comm ? ctx->world : 1, R = ctx->comm ? ctx->rank : 0;
+  const int64_t nr = runs ? runs->n_runs : 0, nj = juncs ? juncs->n_juncs : 0;
+  std::vector<int64_t> cr(W, 0), cj(W, 0);
+  cr[R] = nr; cj[R] = nj;
+  ncclComm_t comm = (ncclComm_t)ctx->comm;
+  DevBuf* SB = ctx->shard_buf;
+  if (W > 1) {
+    TB_CUDA(SB[SB_GATHER].ensure(sizeof(unsigned long long) * 8 * (size_t)(W + 1)));
+    TB_CUDA(ctx->pinned[1].ensure(sizeof(unsigned long long) * 8 * (size_t)(W + 1)));
+    unsigned long long* d_mine = SB[SB_GATHER].as<unsigned long long>();
+    unsigned long long* d_all = d_mine + 8;
+    unsigned long long* h_all = ctx->pinned[1].as<unsigned long long>();
+    unsigned long long h2[2] = {(unsigned long long)nr, (unsigned long long)nj};
+    TB_CUDA(cudaMemcpyAsync(d_mine, h2, sizeof(h2), cudaMemcpyHostToDevice, st));
+    TB_NCCL(g_nccl.AllGather(d_mine, d_all, 2, ncclUint64, comm, st));
+    TB_CUDA(cudaMemcpyAsync(h_all, d_all, sizeof(unsigned long long) * 2 * W, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < W; ++r) { cr[r] = (int64_t)h_all[2 * r]; cj[r] = (int64_t)h_all[2 * r + 1]; }
+  }
+  if (junc_base) { junc_base[0] = 0; for (int r = 0; r < W; ++r) junc_base[r + 1] = junc_base[r] + cj[r]; }
+  int64_t tr = 0, tj = 0;
+  for (int r = 0; r < W; ++r) { tr += cr[r]; tj += cj[r]; }
+  if (R == 0) {
+    if (all_runs) { if (all_runs->capacity < tr) { ctx->set_error("tc_shard_gather: runs capacity %lld < %lld", (long long)all_runs->capacity, (long long)tr); return 1; } all_runs->n_runs = tr; }
+    if (all_juncs) { if (all_juncs->capacity < tj) { ctx->set_error("tc_shard_gather: junction capacity %lld < %lld", (long long)all_juncs->capacity, (long long)tj); return 1; } all_juncs->n_juncs = tj; }
+  }
+  auto d2d = [&](void* dst, const void* src, size_t bytes) { return (bytes && dst != src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st) : cudaSuccess; };
+  if (R == 0) {
+    if (all_runs && runs) {
+      TB_CUDA(d2d(all_runs->tid, runs->tid, sizeof(int32_t) * nr)); TB_CUDA(d2d(all_runs->start0, runs->start0, sizeof(int32_t) * nr));
+      TB_CUDA(d2d(all_runs->end0, runs->end0, sizeof(int32_t) * nr)); TB_CUDA(d2d(all_runs->value, runs->value, sizeof(double) * nr));
+    }
+    if (all_juncs && juncs) {
+      TB_CUDA(d2d(all_juncs->tid, juncs->tid, sizeof(int32_t) * nj)); TB_CUDA(d2d(all_juncs->start, juncs->start, sizeof(int32_t) * nj));
+      TB_CUDA(d2d(all_juncs->end, juncs->end, sizeof(int32_t) * nj)); TB_CUDA(d2d(all_juncs->strand, juncs->strand, (size_t)nj));
+      TB_CUDA(d2d(all_juncs->value, juncs->value, sizeof(double) * nj));
+    }
+  }
+  if (W > 1) {
+    TB_NCCL(g_nccl.GroupStart());
+    if (R == 0) {
+      int64_t ro = cr[0], jo = cj[0];
+      for (int r = 1; r < W; ++r) {
+        if (all_runs && cr[r] > 0) {
+          TB_NCCL(g_nccl.Recv(all_runs->tid + ro, (size_t)cr[r] * 4, ncclUint8, r, comm, st)); TB_NCCL(g_nccl.Recv(all_runs->start0 + ro, (size_t)cr[r] * 4, ncclUint8, r, comm, st));
+          TB_NCCL(g_nccl.Recv(all_runs->end0 + ro, (size_t)cr[r] * 4, ncclUint8, r, comm, st)); TB_NCCL(g_nccl.Recv(all_runs->value + ro, (size_t)cr[r] * 8, ncclUint8, r, comm, st));
+        }
+        if (all_juncs && cj[r] > 0) {
+          TB_NCCL(g_nccl.Recv(all_juncs->tid + jo, (size_t)cj[r] * 4, ncclUint8, r, comm, st)); TB_NCCL(g_nccl.Recv(all_juncs->start + jo, (size_t)cj[r] * 4, ncclUint8, r, comm, st));
+          TB_NCCL(g_nccl.Recv(all_juncs->end + jo, (size_t)cj[r] * 4, ncclUint8, r, comm, st)); TB_NCCL(g_nccl.Recv(all_juncs->strand + jo, (size_t)cj[r], ncclUint8, r, comm, st));
+          TB_NCCL(g_nccl.Recv(all_juncs->value + jo, (size_t)cj[r] * 8, ncclUint8, r, comm, st));
+        }
+        ro += cr[r]; jo += cj[r];
+      }
+    } else {
+      if (runs && nr > 0) {
+        TB_NCCL(g_nccl.Send(runs->tid, (size_t)nr * 4, ncclUint8, 0, comm, st)); TB_NCCL(g_nccl.Send(runs->start0, (size_t)nr * 4, ncclUint8, 0, comm, st));
+        TB_NCCL(g_nccl.Send(runs->end0, (size_t)nr * 4, ncclUint8, 0, comm, st)); TB_NCCL(g_nccl.Send(runs->value, (size_t)nr * 8, ncclUint8, 0, comm, st));
+      }
+      if (juncs && nj > 0) {
+        TB_NCCL(g_nccl.Send(juncs->tid, (size_t)nj * 4, ncclUint8, 0, comm, st)); TB_NCCL(g_nccl.Send(juncs->start, (size_t)nj * 4, ncclUint8, 0, comm, st));
+        TB_NCCL(g_nccl.Send(juncs->end, (size_t)nj * 4, ncclUint8, 0, comm, st)); TB_NCCL(g_nccl.Send(juncs->strand, (size_t)nj, ncclUint8, 0, comm, st));
+        TB_NCCL(g_nccl.Send(juncs->value, (size_t)nj * 8, ncclUint8, 0, comm, st));
+      }
+    }
+    TB_NCCL(g_nccl.GroupEnd());
+    ctx->shard_stat[5] = R == 0 ? (tr - cr[0]) * 20 + (tj - cj[0]) * 21 : nr * 20 + nj * 21;   // bytes over NVLink in the gather
+  }
+  TB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

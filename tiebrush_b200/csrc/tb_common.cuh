@@ -73,6 +73,7 @@ struct tb_ctx {
   int64_t last_heavy = 0;   // slots redone by the full-size tile launch in the last collapse call
   int last_yd_path = 0;     // YD stage of the last collapse call: 0 parallel (frontier + link bitmaps), 1 sequential lists
   int last_path = 0;        // front end of the last collapse call: 0 tile, 1 ordered (by options), 2 ordered (table overflow fallback)
+  int last_cov_exact = 0;   // last coverage call took the exact ordered-double path (weights that are not multiples of 2^-20)
   int last_tile_gen = 0;    // tile kernel generation of the last collapse call: 2 = TMA-staged slices (col_tile2_kernel), 1 = col_tile_kernel
   int64_t last_tile_stat[4] = {};   // generation 2, last call: slots done in several passes | deferred (staging area) | deferred (table / pile-up) | slots
   int tile2_off = 0;        // sticky: a call deferred more than a quarter of its slots (few duplicates) -> later calls use generation 1
@@ -81,10 +82,19 @@ struct tb_ctx {
   DevBuf in_stage[20];   // device copies of host input arrays
   DevBuf out_stage[8];   // device output arrays when the caller wants host results
   HostBuf pinned[2];     // small pinned readback areas
+  // multi-GPU (shard.cu): NCCL communicator of this context's rank, workspace, statistics of the last sharded call
+  void* comm = nullptr; int rank = 0; int world = 1;
+  DevBuf shard_buf[16];
+  int64_t shard_stat[8] = {};   // lead records received | sent | ranks received from | bytes sent (halo) | seam records | bytes moved by the gather
+  int64_t stream_windows = 0;   // windows of the last tc_coverage_stream / tc_shard_coverage call
   void set_error(const char* fmt, ...);
 };
 
 extern std::string g_tb_global_error;
+
+// tc_coverage_stream's view of one window (coverage.cu): the record that follows the window in the stream, and how many
+// records of the window were processed (all but the last bundle when that record continues it)
+struct CovExt { int has_next; int32_t next_tid, next_pos; int64_t consumed; };
 
 // -------------------------------------------------------------------------------------------------
 // small device helpers
