@@ -37,9 +37,15 @@ def parse_args():
     ap.add_argument("--max-nh", type=int, default=0x7fffffff, help="-N (C3 filters)")
     ap.add_argument("--min-qual", type=int, default=-1, help="-Q")
     ap.add_argument("--flag-mask", type=int, default=0, help="-F (uses the paired-end cohort so the mask has bits to bite on)")
-    ap.add_argument("--cov-records", type=int, default=int(os.environ.get("TB_BENCH_COV", 100_000_000)),
-                    help="records of the secondary tiecov leg (0 = skip)")
-    ap.add_argument("--cov-chroms", type=int, default=1, help="chromosomes of the tiecov leg's stream (C4 whole genome: 24)")
+    ap.add_argument("--cov-records", type=int, default=int(os.environ.get("TB_BENCH_COV", 2_000_000_000)),
+                    help="records of the tiecov leg = BASELINE config C4: ONE whole-genome collapsed stream of this many records, "
+                         "split in stream order over the GPUs (strong scaling; 0 = skip)")
+    ap.add_argument("--cov-window", type=int, default=int(os.environ.get("TB_BENCH_COV_WINDOW", 62_500_000)),
+                    help="records per tiecov window (cut at bundle heads): 2e9 records = 32 windows on 1 GPU, 4 per GPU on 8")
+    ap.add_argument("--cov-e2e-records", type=int, default=int(os.environ.get("TB_BENCH_COV_E2E", 250_000_000)),
+                    help="records per rank of the tiecov end-to-end leg (host buffers; a prefix of the rank's slice)")
+    ap.add_argument("--cov-cpu-sample", type=int, default=int(os.environ.get("TB_BENCH_COV_CPU", 2_000_000)),
+                    help="records of the stream written as SAM for the reference tiecov binary (CPU baseline of the tiecov leg)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--wire", default="compact", choices=["compact", "wide"],
                     help="host column format of the e2e leg: compact = n_cigar8 + cigar16 (+cigar_ext), wide = cig_off + cigar (u32)")
@@ -214,6 +220,159 @@ def run_host_cli(args):
     return out
 
 
+def write_cov_sam(cols, path, n_contigs):
+    """A prefix of the collapsed stream as SAM text (YC:i tags) for the reference tiecov binary."""
+    from tiebrush_b200 import sam, synth
+    lens, _, _ = synth.genome_layout(1000)
+    hdr = "@HD\tVN:1.0\tSO:coordinate\n" + "".join(f"@SQ\tSN:ctg{c}\tLN:{int(lens[c])}\n" for c in range(n_contigs))
+    off, cig = cols["cig_off"], cols["cigar"]
+    with open(path, "w") as fh:
+        fh.write(hdr)
+        buf = []
+        for i in range(len(cols["pos"])):
+            c = sam.cigar_str(cig[off[i]:off[i + 1]])
+            s = chr(int(cols["strand"][i]))
+            tags = f"YC:i:{int(cols['yc'][i])}" + (f"\tXS:A:{s}" if s != "." else "")
+            buf.append(f"r{i}\t0\tctg{int(cols['tid'][i])}\t{int(cols['pos'][i]) + 1}\t60\t{c}\t*\t0\t0\t*\t*\t{tags}\n")
+            if len(buf) >= 100000:
+                fh.write("".join(buf)); buf = []
+        fh.write("".join(buf))
+
+
+def run_tiecov_leg(args, rank, world, local, dev, stream, peak, barrier, dist):
+    import torch
+    from tiebrush_b200 import api, synth
+    R = args.cov_records
+    a, b = rank * R // world, (rank + 1) * R // world
+    t_gen = time.perf_counter()
+    segs, mbases = synth.genome_slice(R, a, b, seed=0, device=dev)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    n_local = b - a
+    ncig_local = sum(int(s["n_cig"]) for s in segs)
+    cctx = api.Context(device=local, n_samples=1)
+    cctx.set_stream(stream.cuda_stream); cctx.set_profiling(True)
+    if world > 1:   # one NCCL communicator of the library's own per rank; the id travels over torch.distributed
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        cctx.comm_init(rank, world, idt.cpu().numpy().tobytes())
+    # rows: a run needs a covered base of its own, so deep streams have few per record (0.15 at 2e9), shallow ones up to ~0.5
+    capr, capj = int(1.0 * n_local) + (1 << 22), int(0.05 * n_local) + (1 << 22)
+    out_local = api.cov_out_buffers(capr, capj, device=dev)
+    if world > 1 and rank == 0:
+        all_out = api.cov_out_buffers(int(1.0 * R) + (1 << 22), int(0.05 * R) + (1 << 22), device=dev)
+    else:
+        all_out = out_local if rank == 0 else None
+
+    def step():
+        loc = cctx.shard_coverage(segs, args.cov_window, out_local)
+        ms = [cctx.last_kernel_ms(i) for i in (6, 1, 7, 9)]
+        g = cctx.shard_gather(loc, all_out, world)
+        return loc, g, ms
+
+    for _ in range(max(1, args.warmup)):
+        loc, g, ms = step()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = cctx.launch_count()
+    barrier()
+    with torch.cuda.stream(stream):
+        c0.record(stream)
+        for _ in range(args.steps):
+            loc, g, ms = step()
+        c1.record(stream)
+    barrier()
+    launches = cctx.launch_count() - l0
+    cov_ms = c0.elapsed_time(c1) / args.steps
+    tot = torch.tensor([float(mbases), float(loc["n_runs"]), float(loc["n_juncs"]), float(loc["stats"]["halo_bytes_sent"]),
+                        float(loc["stats"]["lead_sent"]), float(g["gather_bytes"]) if rank else 0.0], device=dev, dtype=torch.float64)
+    tmax = torch.tensor([cov_ms, ms[3]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    cov_ms = float(tmax[0].item())
+    mb_tot, runs_tot, juncs_tot = float(tot[0].item()), int(tot[1].item()), int(tot[2].item())
+    a_cov = n_local * (19 + 4 * ncig_local / max(n_local, 1)) + 16 * loc["n_runs"] + 16 * loc["n_juncs"]   # this rank's algorithmic bytes (SURVEY §8d)
+    acc_ms = max(ms[1], 1e-6)
+    line = {"metric": "coverage_bases_per_sec", "value": mb_tot / (cov_ms / 1000.0), "unit": "bases/s", "records_per_sec": R / (cov_ms / 1000.0),
+            "ms_per_step": cov_ms, "n_gpus": world, "scaling": "strong", "steps": args.steps,
+            "config": {"workload": f"C4: tiecov -c -j on ONE synthetic collapsed whole-genome stream of {R} records (96 contigs, Zipf YC), split in stream order over {world} GPU(s), windows of <= {args.cov_window} records cut at bundle heads",
+                       "records": R, "records_per_gpu": n_local, "windows_per_gpu": loc["windows"], "gen_seconds": t_gen,
+                       "l2": "inputs (27 B/record, GBs per GPU) exceed the 126 MB L2; no flush needed"},
+            "runs": runs_tot, "juncs": juncs_tot, "gpu_launches": int(launches),
+            "exchange": {"halo_ms_max": float(tmax[1].item()), "lead_records_moved": int(tot[4].item()), "halo_bytes": int(tot[3].item()),
+                         "gather_bytes": int(tot[5].item()), "collectives": "ncclAllGather x2 (open-bundle state, lead sizes) + grouped ncclSend/ncclRecv (lead records) + ncclAllGather (row counts) + grouped ncclSend/ncclRecv (ordered gather on rank 0)" if world > 1 else "none (1 GPU)"},
+            "roofline": {"bound": "hbm", "kernel": "cov_accumulate_kernel", "achieved": a_cov / (acc_ms / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": a_cov / (acc_ms / 1000.0) / 1e9 / peak, "kernel_ms": float(acc_ms), "algorithmic_bytes": float(a_cov),
+                         "traffic": (lambda t: None if t is None else t * n_local)(traffic_per_record("cov_accumulate_kernel")),
+                         "traffic_source": "ncu dram bytes per record (profiles/traffic.json) x records of rank 0",
+                         "note": "rank 0: sum of the kernel's launches over its windows"},
+            "stage_ms": dict(zip(("bundles", "accumulate", "runs", "halo_exchange"), [float(x) for x in ms]))}
+    # ---- end to end: the same call with HOST (pinned) buffers, H2D per window and D2H of the rows inside the timed region ----
+    if not args.no_e2e and args.cov_e2e_records > 0 and segs:
+        ne = min(args.cov_e2e_records, int(segs[0]["pos"].shape[0]))
+        seg = segs[0]
+        w1 = int(seg["cig_off"][ne].item()) & 0xFFFFFFFF
+        host, h2d = {}, 0
+        for name, cnt in (("tid", ne), ("pos", ne), ("yc", ne), ("strand", ne), ("cig_off", ne + 1), ("cigar", w1)):
+            ht = torch.empty(cnt, dtype=seg[name].dtype, pin_memory=True)
+            ht.copy_(seg[name][:cnt])
+            host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32}.get(name, ht.numpy().dtype))
+            h2d += ht.numel() * ht.element_size()
+        host["n_cig"] = w1
+        mb_e = float(synth.m_bases(dict(cigar=seg["cigar"][:w1])))
+        ecap_r, ecap_j = int(1.0 * ne) + (1 << 22), int(0.05 * ne) + (1 << 22)
+        pin = lambda m, dt: torch.empty(m, dtype=dt, pin_memory=True).numpy()
+        hout = dict(r_tid=pin(ecap_r, torch.int32), r_start=pin(ecap_r, torch.int32), r_end=pin(ecap_r, torch.int32), r_val=pin(ecap_r, torch.float64),
+                    j_tid=pin(ecap_j, torch.int32), j_start=pin(ecap_j, torch.int32), j_end=pin(ecap_j, torch.int32), j_strand=pin(ecap_j, torch.uint8),
+                    j_val=pin(ecap_j, torch.float64))
+        del out_local, all_out
+        torch.cuda.empty_cache()
+        r2 = cctx.coverage_stream(host, args.cov_window, hout)
+        es = max(1, min(args.steps, 3))
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            g0.record(stream)
+            for _ in range(es):
+                r2 = cctx.coverage_stream(host, args.cov_window, hout)
+            g1.record(stream)
+        barrier()
+        e_ms = g0.elapsed_time(g1) / es
+        et = torch.tensor([e_ms], device=dev, dtype=torch.float64); eb = torch.tensor([mb_e, float(h2d), float(20 * r2["n_runs"] + 21 * r2["n_juncs"])], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX); dist.all_reduce(eb, op=dist.ReduceOp.SUM)
+        line["e2e"] = {"value": float(eb[0].item()) / (float(et[0].item()) / 1000.0), "unit": "bases/s", "ms_per_step": float(et[0].item()),
+                       "h2d_bytes_per_step": int(eb[1].item()), "d2h_bytes_per_step": int(eb[2].item()), "steps": es,
+                       "sample": f"the first {ne} records of every rank's slice through tc_coverage_stream with pinned host arrays ({r2['windows']} windows; H2D per window and D2H of the rows inside the timed region)"}
+        del host, hout
+    # ---- CPU baseline of this leg: the UNMODIFIED reference tiecov binary on a bounded prefix of the same stream (rank 0, N = 1) ----
+    ref = os.path.join(ROOT, "oracle", "_ref", "tiecov")
+    if rank == 0 and world == 1 and args.cov_cpu_sample > 0 and segs and os.path.exists(ref):
+        ns = min(args.cov_cpu_sample, int(segs[0]["pos"].shape[0]))
+        w1 = int(segs[0]["cig_off"][ns].item()) & 0xFFFFFFFF
+        sub = {k: segs[0][k][:ns].cpu().numpy() for k in ("tid", "pos", "yc", "strand")}
+        sub["cig_off"] = segs[0]["cig_off"][:ns + 1].cpu().numpy().view(np.uint32); sub["cigar"] = segs[0]["cigar"][:w1].cpu().numpy().view(np.uint32)
+        mb_s = float(synth.m_bases(dict(cigar=segs[0]["cigar"][:w1])))
+        with tempfile.TemporaryDirectory() as tmp:
+            sp = os.path.join(tmp, "c.sam")
+            write_cov_sam(sub, sp, 96)
+            best = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                r = subprocess.run([ref, "-c", os.path.join(tmp, "o.cov"), "-j", os.path.join(tmp, "o.j"), sp], capture_output=True, text=True)
+                dt = time.perf_counter() - t0
+                if r.returncode == 0 and (best is None or dt < best):
+                    best = dt
+        if best:
+            line["cpu_baseline"] = {"value": mb_s / best, "unit": "bases/s", "records_per_sec": ns / best, "cores": 1, "kind": "reference",
+                                    "sample": f"the first {ns} records of the same stream as SAM text, reference tiecov -c -j (-O2, single-threaded as shipped), best of 2, process start to exit ({best:.2f} s)"}
+    cctx.close()
+    del segs
+    return line
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
@@ -249,44 +408,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- tiecov leg (secondary): coverage + junctions + bedgraph runs on a collapsed-like stream ----
+    # ---- tiecov leg = BASELINE config C4: coverage + junctions + bedGraph runs of ONE collapsed whole-genome stream, split in
+    #      stream order over the ranks (strong scaling). Timed region per step: halo exchange over NCCL (open-bundle state
+    #      allgather, lead records to the owner of the bundle), per-rank windows cut at bundle heads, ordered gather on rank 0.
     tiecov_line = None
     if args.cov_records > 0:
-        cctx = api.Context(device=local, n_samples=1)
-        cctx.set_stream(stream.cuda_stream); cctx.set_profiling(True)
-        cov = synth.coverage_stream(args.cov_records, seed=rank, chroms=args.cov_chroms, device=dev)
-        ncov = args.cov_records
-        capr, capj = 2 * int(cov["n_cig"]) + 16, int(cov["n_cig"]) + 16
-        i32 = lambda m: torch.empty(m, dtype=torch.int32, device=dev)
-        ocov = dict(r_tid=i32(capr), r_start=i32(capr), r_end=i32(capr), r_val=torch.empty(capr, dtype=torch.float64, device=dev),
-                    j_tid=i32(capj), j_start=i32(capj), j_end=i32(capj), j_strand=torch.empty(capj, dtype=torch.uint8, device=dev),
-                    j_val=torch.empty(capj, dtype=torch.float64, device=dev))
-        for _ in range(max(1, args.warmup)):
-            r = cctx.coverage_window(cov, out=ocov)
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        cms = []
-        barrier()
-        with torch.cuda.stream(stream):
-            c0.record(stream)
-            for _ in range(args.steps):
-                r = cctx.coverage_window(cov, out=ocov)
-                cms.append(cctx.last_kernel_ms(1))
-                cstages = [cctx.last_kernel_ms(i) for i in (6, 1, 7)]
-            c1.record(stream)
-        barrier()
-        cov_ms = c0.elapsed_time(c1) / args.steps
-        host_cov = None
-        mbases = float(synth.m_bases(cov))
-        a_cov = ncov * (19 + 4 * cov["n_cig"] / ncov) + 16 * r["n_runs"] + 16 * r["n_juncs"]
-        tiecov_line = {"metric": "coverage_bases_per_sec", "value": world * mbases / (cov_ms / 1000.0), "unit": "bases/s",
-                          "records_per_sec": world * ncov / (cov_ms / 1000.0), "ms_per_step": cov_ms, "records": ncov, "runs": r["n_runs"], "juncs": r["n_juncs"],
-                          "roofline": {"bound": "hbm", "kernel": "cov_accumulate_kernel", "achieved": a_cov / (np.mean(cms) / 1000.0) / 1e9, "peak": peak,
-                                       "unit": "GB/s", "frac": a_cov / (np.mean(cms) / 1000.0) / 1e9 / peak, "kernel_ms": float(np.mean(cms)),
-                                       "traffic": (lambda t: None if t is None else t * ncov)(traffic_per_record("cov_accumulate_kernel")),
-                                       "traffic_source": "ncu dram bytes per record (profiles/traffic.json) x records of this launch"},
-                          "stage_ms": dict(zip(("bundles", "accumulate", "runs"), [float(x) for x in cstages]))}
-        del cov, ocov, r
-        cctx.close()
+        tiecov_line = run_tiecov_leg(args, rank, world, local, dev, stream, peak, barrier, dist)
         torch.cuda.empty_cache()
 
     k, reads = args.samples, args.reads

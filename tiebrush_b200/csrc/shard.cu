@@ -64,11 +64,19 @@ enum { SB_GATHER = 0, SB_SEND, SB_TAIL_TID, SB_TAIL_POS, SB_TAIL_YC, SB_TAIL_STR
        SB_SEAM_STRAND, SB_SEAM_OFF, SB_SEAM_CIG, SB_COUNT_ };
 static_assert(SB_COUNT_ <= 16, "raise tb_ctx::shard_buf");
 
-// ---- open-bundle state of a slice: maximum (tid << 32 | end) key over its records ----
-__global__ void __launch_bounds__(256) shard_maxkey_kernel(int64_t n, const int32_t* __restrict__ tid, const int32_t* __restrict__ pos,
+// ---- open-bundle state of a slice: maximum (tid << 32 | end) key over its records. Only the records of the LAST reference
+// id can hold it (tids never decrease), so a one-thread binary search finds where they start and the reduction reads
+// that part only. ----
+__global__ void shard_last_tid_kernel(int64_t n, const int32_t* __restrict__ tid, long long* __restrict__ start) {
+  const int32_t t = tid[n - 1];
+  int64_t lo = 0, hi = n - 1;   // first i with tid[i] == t
+  while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if (tid[mid] >= t) hi = mid; else lo = mid + 1; }
+  *start = lo;
+}
+__global__ void __launch_bounds__(256) shard_maxkey_kernel(int64_t n, const long long* __restrict__ start, const int32_t* __restrict__ tid, const int32_t* __restrict__ pos,
                                                            const uint32_t* __restrict__ cig_off, const uint32_t* __restrict__ cigar, unsigned long long* __restrict__ out) {
   unsigned long long m = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = *start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int l = 0;
     for (uint32_t c = cig_off[i]; c < cig_off[i + 1]; ++c) { const uint32_t w = cigar[c]; if ((0x18Du >> (w & 0xf)) & 1u) l += (int)(w >> 4); }
     const unsigned long long key = ((unsigned long long)(uint32_t)tid[i] << 32) | (uint32_t)(pos[i] + l);
@@ -80,35 +88,51 @@ __global__ void __launch_bounds__(256) shard_maxkey_kernel(int64_t n, const int3
 }
 
 // ---- lead of a slice: the records before its first bundle head, given the open-bundle state `ein` of everything left of
-// it (0 = nothing). One block walks the slice 1024 records at a time until a head shows up. out[0] = lead. ----
-__global__ void __launch_bounds__(1024) shard_lead_kernel(int64_t n, const int32_t* __restrict__ tid, const int32_t* __restrict__ pos,
-                                                          const uint32_t* __restrict__ cig_off, const uint32_t* __restrict__ cigar, unsigned long long ein,
-                                                          long long* __restrict__ out) {
-  __shared__ unsigned long long s_scan[33];
-  __shared__ long long s_first;
-  unsigned long long carry = ein;
-  for (int64_t base = 0; base < n; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    unsigned long long key = 0;
-    if (i < n) {
-      int l = 0;
-      for (uint32_t c = cig_off[i]; c < cig_off[i + 1]; ++c) { const uint32_t w = cigar[c]; if ((0x18Du >> (w & 0xf)) & 1u) l += (int)(w >> 4); }
-      key = ((unsigned long long)(uint32_t)tid[i] << 32) | (uint32_t)(pos[i] + l);
-    }
-    if (threadIdx.x == 0) s_first = -1;
+// it. Chunks of LEAD_BLOCKS x 1024 records, three small kernels per chunk (a lead can be 10^6 records in a deep stream:
+// one block walking it would take milliseconds): block maxima of the keys -> their exclusive prefix maximum (one block,
+// seeded with the carry of the chunks before) -> every block rescans its records against that carry and the first head of
+// the chunk wins an atomicMin. state[0] = carry (in/out), state[1] = first head (or -1). ----
+constexpr int LEAD_BLOCKS = 4096;
+__device__ __forceinline__ unsigned long long shard_key(int64_t i, const int32_t* tid, const int32_t* pos, const uint32_t* cig_off, const uint32_t* cigar) {
+  int l = 0;
+  for (uint32_t c = cig_off[i]; c < cig_off[i + 1]; ++c) { const uint32_t w = cigar[c]; if ((0x18Du >> (w & 0xf)) & 1u) l += (int)(w >> 4); }
+  return ((unsigned long long)(uint32_t)tid[i] << 32) | (uint32_t)(pos[i] + l);
+}
+__global__ void __launch_bounds__(1024) shard_lead_max_kernel(int64_t base, int64_t n, const int32_t* __restrict__ tid, const int32_t* __restrict__ pos,
+                                                              const uint32_t* __restrict__ cig_off, const uint32_t* __restrict__ cigar, unsigned long long* __restrict__ bmax) {
+  __shared__ unsigned long long s_w[33];
+  const int64_t i = base + (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  const unsigned long long key = i < n ? shard_key(i, tid, pos, cig_off, cigar) : 0ULL;
+  const unsigned long long tot = tb_block_reduce<OpMaxU64>(key, s_w);
+  if (threadIdx.x == 0) bmax[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(1024) shard_lead_scan_kernel(unsigned long long* __restrict__ bmax, int nblocks, unsigned long long* __restrict__ state) {
+  __shared__ unsigned long long s_w[33];
+  unsigned long long carry = state[0];
+  for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+    const int b = b0 + (int)threadIdx.x;
+    const unsigned long long v = b < nblocks ? bmax[b] : 0ULL;
     unsigned long long tot;
-    const unsigned long long exc = tb_block_exscan<OpMaxU64>(key, s_scan, &tot);   // barriers inside: s_first is visible
-    const unsigned long long run = exc > carry ? exc : carry;                       // maximum key of everything before record i
-    if (i < n) {
-      const bool head = run == 0 || tid[i] != (int)(run >> 32) || (pos[i] + 1) > (int)(uint32_t)run;   // tiecov.cpp:443
-      if (head) atomicMin((unsigned long long*)&s_first, (unsigned long long)i);
-    }
-    __syncthreads();
-    if (s_first >= 0) { if (threadIdx.x == 0) out[0] = s_first; return; }
+    const unsigned long long exc = tb_block_exscan<OpMaxU64>(v, s_w, &tot);
+    if (b < nblocks) bmax[b] = exc > carry ? exc : carry;   // maximum key of everything before block b
     carry = tot > carry ? tot : carry;
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[0] = n;   // no head at all: the whole slice continues a bundle opened further left
+  if (threadIdx.x == 0) state[0] = carry;
+}
+__global__ void __launch_bounds__(1024) shard_lead_head_kernel(int64_t base, int64_t n, const int32_t* __restrict__ tid, const int32_t* __restrict__ pos,
+                                                               const uint32_t* __restrict__ cig_off, const uint32_t* __restrict__ cigar,
+                                                               const unsigned long long* __restrict__ bpre, unsigned long long* __restrict__ state) {
+  __shared__ unsigned long long s_w[33];
+  const int64_t i = base + (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  const unsigned long long key = i < n ? shard_key(i, tid, pos, cig_off, cigar) : 0ULL;
+  const unsigned long long exc = tb_block_exscan<OpMaxU64>(key, s_w, (unsigned long long*)nullptr);
+  const unsigned long long carry = bpre[blockIdx.x];
+  const unsigned long long run = exc > carry ? exc : carry;
+  if (i < n) {
+    const bool head = run == 0 || tid[i] != (int)(run >> 32) || (pos[i] + 1) > (int)(uint32_t)run;   // tiecov.cpp:443
+    if (head) atomicMin(&state[1], (unsigned long long)i);
+  }
 }
 
 // offsets src[0..count) of a piece (absolute offsets of whoever filled it) -> dst[i] = src[i] - src[0] + dst0
@@ -270,8 +294,10 @@ int tc_shard_coverage(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t wi
     unsigned long long* h_all = ctx->pinned[1].as<unsigned long long>();
     TB_CUDA(cudaMemsetAsync(d_mine, 0, sizeof(unsigned long long) * 8, st));
     if (last.n > 0) {
-      shard_maxkey_kernel<<<std::min<unsigned>(grid_for(last.n, 256), 148u * 8u), 256, 0, st>>>(last.n, last.tid, last.pos, last.cig_off, last.cigar, d_mine);
-      ctx->launches++;
+      long long* d_start = (long long*)(d_mine + 5);
+      shard_last_tid_kernel<<<1, 1, 0, st>>>(last.n, last.tid, d_start);
+      shard_maxkey_kernel<<<148u * 8u, 256, 0, st>>>(last.n, d_start, last.tid, last.pos, last.cig_off, last.cigar, d_mine);
+      ctx->launches += 2;
     }
     {
       unsigned long long h_mine[3] = {0, 0, (unsigned long long)n_local};
@@ -292,13 +318,24 @@ int tc_shard_coverage(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t wi
     std::vector<unsigned long long> firstkey(W), nrec(W);
     for (int r = 0; r < W; ++r) { firstkey[r] = h_all[4 * r + 1]; nrec[r] = h_all[4 * r + 2]; }
     // ---- 2. my lead; allgather of {lead, lead CIGAR words, has a head, records of the first segment} ----
-    long long* d_lead = (long long*)(d_mine + 4);
     uint32_t lead_c[2] = {0, 0};
     if (first.n > 0 && ein != 0) {
-      shard_lead_kernel<<<1, 1024, 0, st>>>(first.n, first.tid, first.pos, first.cig_off, first.cigar, ein, d_lead);
-      ctx->launches++;
-      TB_CUDA(cudaMemcpyAsync(&lead, d_lead, sizeof(long long), cudaMemcpyDeviceToHost, st));
-      TB_CUDA(cudaStreamSynchronize(st));
+      TB_CUDA(SB[SB_SEND].ensure(sizeof(unsigned long long) * (LEAD_BLOCKS + 8)));
+      unsigned long long* d_bmax = SB[SB_SEND].as<unsigned long long>();
+      unsigned long long* d_state = d_mine + 6;   // [carry, first head]
+      unsigned long long h_state[2] = {ein, ~0ULL};
+      TB_CUDA(cudaMemcpyAsync(d_state, h_state, sizeof(h_state), cudaMemcpyHostToDevice, st));
+      lead = first.n;   // no head at all: the whole slice continues a bundle opened further left
+      for (int64_t base = 0; base < first.n; base += (int64_t)LEAD_BLOCKS * 1024) {
+        const int nb = (int)std::min<int64_t>(LEAD_BLOCKS, (first.n - base + 1023) / 1024);
+        shard_lead_max_kernel<<<nb, 1024, 0, st>>>(base, first.n, first.tid, first.pos, first.cig_off, first.cigar, d_bmax);
+        shard_lead_scan_kernel<<<1, 1024, 0, st>>>(d_bmax, nb, d_state);
+        shard_lead_head_kernel<<<nb, 1024, 0, st>>>(base, first.n, first.tid, first.pos, first.cig_off, first.cigar, d_bmax, d_state);
+        ctx->launches += 3;
+        TB_CUDA(cudaMemcpyAsync(h_state, d_state, sizeof(h_state), cudaMemcpyDeviceToHost, st));
+        TB_CUDA(cudaStreamSynchronize(st));
+        if (h_state[1] != ~0ULL) { lead = (int64_t)h_state[1]; break; }
+      }
       if (lead == first.n && n_segs > 1) { ctx->set_error("tc_shard_coverage: the first segment of rank %d lies inside one bundle; segments of a rank must end at reference-id boundaries", R); return 1; }
       if (lead > 0) {
         TB_CUDA(cudaMemcpyAsync(&lead_c[0], first.cig_off, 4, cudaMemcpyDeviceToHost, st));
@@ -375,6 +412,7 @@ int tc_shard_coverage(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t wi
   if (ctx->profiling) TB_CUDA(cudaEventRecord(e1, st));
   // ---- 6. this rank's whole bundles, segment by segment ----
   int64_t consumed_last = last.n;
+  float ms_sum[3] = {0.f, 0.f, 0.f};   // K6 / K7 / K8 device time over every window of the call
   for (int s = 0; s < n_segs; ++s) {
     const bool is_last = s == n_segs - 1;
     int64_t consumed = 0;
@@ -382,6 +420,7 @@ int tc_shard_coverage(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t wi
     if (skip >= segs[s].n) { if (is_last) consumed_last = segs[s].n; continue; }
     const int rc = tc_stream_impl(ctx, &segs[s], skip, window, (is_last && tail_n > 0) ? tail_next : nullptr, runs, juncs, &consumed);
     if (rc) return rc;
+    ms_sum[0] += ctx->last_ms[6]; ms_sum[1] += ctx->last_ms[1]; ms_sum[2] += ctx->last_ms[7];
     if (is_last) consumed_last = consumed;
     else if (consumed < segs[s].n) { ctx->set_error("tc_shard_coverage: segment %d of rank %d ends inside a bundle; segments of a rank must end at reference-id boundaries", s, R); return 1; }
   }
@@ -420,12 +459,12 @@ int tc_shard_coverage(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t wi
     seam.strand = SB[SB_SEAM_STRAND].as<uint8_t>(); seam.cig_off = SB[SB_SEAM_OFF].as<uint32_t>(); seam.cigar = SB[SB_SEAM_CIG].as<uint32_t>();
     seam.on_device = 1; seam.n_cig = sw;
     int64_t consumed = 0;
-    const float keep[3] = {ctx->last_ms[6], ctx->last_ms[1], ctx->last_ms[7]};
     const int rc = tc_stream_impl(ctx, &seam, 0, std::max<int64_t>(window, sn), nullptr, runs, juncs, &consumed);
     if (rc) return rc;
-    ctx->last_ms[6] += keep[0]; ctx->last_ms[1] += keep[1]; ctx->last_ms[7] += keep[2];
+    ms_sum[0] += ctx->last_ms[6]; ms_sum[1] += ctx->last_ms[1]; ms_sum[2] += ctx->last_ms[7];
     ctx->shard_stat[4] = sn;
   }
+  ctx->last_ms[6] = ms_sum[0]; ctx->last_ms[1] = ms_sum[1]; ctx->last_ms[7] = ms_sum[2];
   if (ctx->profiling) {
     TB_CUDA(cudaStreamSynchronize(st));
     float ms = 0;

@@ -325,3 +325,53 @@ def m_bases(cols):
     """Sum of CIGAR M-op lengths ("coverage bases") of a torch column dict."""
     cig = cols["cigar"].to(torch.int64) & 0xFFFFFFFF
     return int(((cig >> 4) * ((cig & 0xF) == 0)).sum())
+
+
+# ---- whole-genome collapsed stream for BASELINE config C4 (tiecov on 2e9 records), shardable by record index -------------
+def genome_layout(n_total, split=4):
+    """Contigs of the synthetic genome: every GRCh38 chromosome cut into `split` references (generation stays chunked:
+    the largest holds 2 % of the records), records per contig proportional to its length. Returns (lengths, counts, starts)."""
+    lens = np.repeat(np.asarray(GRCH38, np.int64) // split, split)
+    w = lens / lens.sum()
+    cnt = np.floor(w * n_total).astype(np.int64)
+    cnt[: int(n_total - cnt.sum())] += 1
+    start = np.concatenate([[0], np.cumsum(cnt)])
+    return lens, cnt, start
+
+
+def genome_slice(n_total, a, b, seed=0, n_tx=200000, device="cpu", seg_max=1_000_000_000, split=4):
+    """Records [a, b) (global stream order) of the synthetic whole-genome collapsed stream of `n_total` records, as a list
+    of device-resident segments (own CIGAR arena each, cut only at contig boundaries). The stream is the same whatever the
+    slicing: contig c holds sample_reads(TranscriptModel(seed 42+c), counts[c], seed 5000+7919*seed+c) with Zipf YC."""
+    lens, cnt, start = genome_layout(n_total, split)
+    parts, segs, mb = [], [], 0
+
+    def flush():
+        if not parts:
+            return
+        cols = {k: torch.cat([p[k] for p in parts]) for k in ("tid", "pos", "yc", "strand")}
+        cols["cig_off"], cols["cigar"] = _cat_csr(parts)
+        cols["n_cig"] = int(sum(p["n_cig"] for p in parts))
+        segs.append(cols)
+        parts.clear()
+
+    have = 0
+    for c in range(len(cnt)):
+        lo, hi = max(a, int(start[c])), min(b, int(start[c + 1]))
+        if lo >= hi:
+            continue
+        tm = TranscriptModel(n_tx=max(64, int(n_tx * lens[c] / lens.sum())), chrom_len=int(lens[c]), seed=42 + c, device=device)
+        p = sample_reads(tm, int(cnt[c]), 5000 + seed * 7919 + c, yc_zipf=True)
+        i0, i1 = lo - int(start[c]), hi - int(start[c])
+        off = p["cig_off"].to(torch.int64)
+        c0, c1 = int(off[i0]), int(off[i1])
+        q = dict(tid=torch.full((i1 - i0,), c, dtype=torch.int32, device=device), pos=p["pos"][i0:i1].clone(), yc=p["yc"][i0:i1].clone(),
+                 strand=p["strand"][i0:i1].clone(), cig_off=(off[i0:i1 + 1] - c0).to(torch.int32), cigar=p["cigar"][c0:c1].clone(), n_cig=c1 - c0)
+        del p, tm, off
+        if have + (i1 - i0) > seg_max:
+            flush(); have = 0
+        parts.append(q); have += i1 - i0
+    flush()
+    for s in segs:
+        mb += m_bases(s)
+    return segs, mb
