@@ -153,11 +153,29 @@ def write_sam_files(host, run_off, tmpdir):
     return paths
 
 
+def to_bam_files(sam_paths):
+    """SAM text -> BAM with oracle/_ref/hts_tool (the reference's vendored htslib); None when the tool is not built."""
+    tool = os.path.join(ROOT, "oracle", "_ref", "hts_tool")
+    if not os.path.exists(tool):
+        return None
+    out = []
+    for p in sam_paths:
+        b = p[:-4] + ".bam"
+        if subprocess.run([tool, "tobam", p, b], capture_output=True).returncode != 0:
+            return None
+        os.remove(p)
+        out.append(b)
+    return out
+
+
 def run_reference_arm(args):
     """Times the UNMODIFIED reference binary (single-threaded, as shipped) on a bounded sample: K steps of
-    `tiebrush -o out.bam s0.sam ... s{k-1}.sam`, wall clock around the process."""
+    `tiebrush -o out.bam s0.bam ... s{k-1}.bam`, wall clock around the process. Beside the headline (-O2, 1 thread, BAM in /
+    BAM out) SURVEY §8d's other baselines are taken once each: the -O0 -g build that the reference's CMakeLists.txt:49
+    produces, the reference's own parallel driver tiewrap.py on all host cores, and a decode-only pass over the inputs."""
     from tiebrush_b200 import synth
-    ref = os.path.join(ROOT, "oracle", "_ref", "tiebrush")
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    ref = os.path.join(refdir, "tiebrush")
     line = {"impl": "reference", "metric": "alignments_collapsed_per_sec", "unit": "alignments/s", "higher_is_better": True,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "dtype": "u32", "data": "synthetic", "scaling": "weak",
             "vs_baseline": None}
@@ -167,25 +185,57 @@ def run_reference_arm(args):
     cols, run_off, _ = synth.cohort_window(args.samples, args.ref_reads, seed=0, device="cpu")
     host = synth.to_host(cols)
     n = len(host["pos"])
+    nproc = len(os.sched_getaffinity(0))
+    extra = {}
     with tempfile.TemporaryDirectory() as tmp:
         paths = write_sam_files(host, run_off, tmp)
+        bams = to_bam_files(paths)
+        fmt = "BAM"
+        if bams is None:
+            bams, fmt = write_sam_files(host, run_off, tmp), "SAM text (oracle/_ref/hts_tool missing)"
         times = []
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            r = subprocess.run([ref, "-o", os.path.join(tmp, "o.bam")] + paths, capture_output=True, text=True)
+            r = subprocess.run([ref, "-o", os.path.join(tmp, "o.bam")] + bams, capture_output=True, text=True)
             dt = time.perf_counter() - t0
             if r.returncode != 0:
                 line["unavailable"] = "reference binary failed: " + r.stderr[:200]
                 print(json.dumps(line)); return
             if it >= args.warmup:
                 times.append(dt)
+
+        def once(cmd, **kw):
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, capture_output=True, text=True, **kw)
+            return (time.perf_counter() - t0) if r.returncode == 0 else None, r
+
+        o0 = os.path.join(refdir, "tiebrush_O0")
+        if os.path.exists(o0):
+            dt, _ = once([o0, "-o", os.path.join(tmp, "o0.bam")] + bams)
+            if dt:
+                extra["O0_build"] = {"value": n / dt, "unit": "alignments/s", "cores": 1, "seconds": dt,
+                                     "what": "-O0 -g build of the same sources (what the reference's CMakeLists.txt:49 produces), 1 run"}
+        tw = os.path.join(refdir, "tiewrap.py")
+        if os.path.exists(tw):
+            bsz = max(2, -(-len(bams) // nproc))
+            dt, r = once([sys.executable, tw, "-t", str(nproc), "-b", str(bsz), "-o", os.path.join(tmp, "tw.bam")] + bams)
+            if dt:
+                extra["tiewrap_all_cores"] = {"value": n / dt, "unit": "alignments/s", "cores": nproc, "batch_size": bsz, "seconds": dt,
+                                              "what": f"the reference's own parallel mode: tiewrap.py -t {nproc} -b {bsz} (batch tree of tiebrush -O2 processes), 1 run"}
+        tool = os.path.join(refdir, "hts_tool")
+        if os.path.exists(tool) and fmt == "BAM":
+            dt, r = once([tool, "decode"] + bams)
+            if dt:
+                extra["decode_only"] = {"value": n / dt, "unit": "alignments/s", "cores": 1, "seconds": dt,
+                                        "what": "sam_read1 loop over the same BAM inputs (htslib sam.c), no collapse, no output: the host decode share"}
     ms = 1000.0 * float(np.mean(times))
     v = n / (ms / 1000.0)
     line.update({"value": v, "ms_per_step": ms,
-                 "config": {"workload": f"C2 cohort model (100 samples x 10M reads chr1, default mode); bounded sample: {args.samples} SAM files x {args.ref_reads} reads",
-                            "records_per_step": n},
+                 "config": {"workload": f"C2 cohort model (100 samples x 10M reads chr1, default mode); bounded sample: {args.samples} {fmt} files x {args.ref_reads} reads",
+                            "records_per_step": n, "host_cores_available": nproc},
                  "cpu_baseline": {"value": v, "unit": "alignments/s", "cores": 1, "kind": "reference",
-                                  "sample": f"{args.samples} files x {args.ref_reads} reads of the C2 cohort model as SAM text, reference tiebrush -O2, 1 thread (the reference is single-threaded)"},
+                                  "sample": f"{args.samples} files x {args.ref_reads} reads of the C2 cohort model as {fmt}, reference tiebrush -O2, 1 thread (the reference is single-threaded)",
+                                  **extra},
                  "e2e": {"value": v, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line))
 
@@ -202,6 +252,11 @@ def run_host_cli(args):
     n = len(host["pos"])
     with tempfile.TemporaryDirectory() as tmp:
         paths = write_sam_files(host, run_off, tmp)
+        bams = to_bam_files(paths)
+        fmt = "BAM"
+        if bams is None:
+            bams, fmt = write_sam_files(host, run_off, tmp), "SAM"
+        paths = bams
         best = None
         for _ in range(3):
             t0 = time.perf_counter()
@@ -213,7 +268,7 @@ def run_host_cli(args):
                 best = (dt, r.stderr)
     m = re.search(r"total ([0-9.]+) s \| decode\+merge ([0-9.]+) \| pack ([0-9.]+) \| device \(H2D\+kernels\+D2H\) ([0-9.]+) \| tag\+write ([0-9.]+) \| windows (\d+)", best[1])
     out = {"value": n / best[0], "unit": "alignments/s", "wall_s": best[0], "records": n,
-           "sample": f"{args.samples} SAM files x {args.cli_reads} reads of the C2 cohort model (same sample as --impl reference), best of 3, process start to exit"}
+           "sample": f"{args.samples} {fmt} files x {args.cli_reads} reads of the C2 cohort model (same sample as --impl reference), {fmt} in / BAM out, best of 3, process start to exit"}
     if m:
         out.update({"in_process_s": float(m.group(1)), "decode_merge_s": float(m.group(2)), "pack_s": float(m.group(3)),
                     "device_s": float(m.group(4)), "tag_write_s": float(m.group(5)), "windows": int(m.group(6))})

@@ -343,3 +343,23 @@ def test_collapse_compact_wire_format_equals_wide(mode):
         assert np.array_equal(np.asarray(got[key]), np.asarray(wide[key])), key
         G = dgot["n_groups"]
         assert np.array_equal(dgot[key][:G].cpu().numpy().view(np.asarray(exp[key]).dtype), exp[key]), key
+
+
+def test_compact_wire_format_is_validated():
+    """a packer whose n_cig / cigar_ext do not match the per-record op counts gets an error, not an out-of-bounds read."""
+    from tiebrush_b200 import api, synth
+    cols, run_off, pr = synth.cohort_window(6, 3000, seed=2, n_tx=20, device="cpu")
+    host = synth.to_host(cols)
+    n8, c16, ext = api.compact_cigar_columns(host["cig_off"], host["cigar"])
+    compact = {k: host[k] for k in ("pos", "flag", "mapq", "strand", "nh")}
+    with api.Context(device=0, n_samples=6) as ctx:
+        bad = dict(compact, n_cigar8=n8.copy(), cigar16=c16, cigar_ext=ext)
+        bad["n_cigar8"][5] += 1                                  # op counts no longer sum to n_cig
+        with pytest.raises(api.TieBrushError, match="n_cigar8 sums to"):
+            ctx.collapse_window(bad, run_off)
+        if len(ext):
+            bad = dict(compact, n_cigar8=n8, cigar16=c16, cigar_ext=ext[:-1].copy())   # one escaped length short
+            with pytest.raises(api.TieBrushError, match="escaped lengths"):
+                ctx.collapse_window(bad, run_off)
+        ok = ctx.collapse_window(dict(compact, n_cigar8=n8, cigar16=c16, cigar_ext=ext), run_off)
+        assert ok["n_groups"] > 0

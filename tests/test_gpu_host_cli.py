@@ -135,3 +135,62 @@ def test_recollapse_and_tiecov_cli_match_reference(sams):
         _run([os.path.join(HOST, "tiecov_gpu"), "-s", gs, "-c", gs + "_c", src], env={"TB_WINDOW_RECORDS": "700"})
         assert open(gs + ".bedgraph").read() == open(rs + ".bedgraph").read()
         assert len(open(rs + ".bedgraph").read().split("\n")) > 10
+
+
+# ---- BASELINE config C1: the reference's own 20 fixture BAMs through the GPU command lines --------------------------------
+FIX = os.path.join(ROOT, "tests", "golden", "fixtures")     # test/t1/t1s*.bam and test/t2/t2s*.bam of the reference (data, 9.3 MB)
+# record-text md5 (htsfile -c out.bam | grep -v '^@' | md5sum) and output-file md5s of the compiled reference, SURVEY §8c / BASELINE.md §3
+C1_MD5 = {"t1": "db674977026be7f2832fe9869ed40376", "t2": "27f7b93a789a9cddb06dca63449d32af", "t12": "50320443e9d380da6bc6c46b1fa90d85",
+          "cov": "8d1b0c70113a233095742cec61bb8129", "junc": "61427ff301f9ea70d48d5fbff20db7e2"}
+
+
+def _fixture_bams(which):
+    import glob
+    fs = []
+    for t in which:
+        fs += sorted(glob.glob(os.path.join(FIX, t, f"{t}s[0-9].bam")))
+    return fs
+
+
+def _md5_records(bam):
+    import hashlib
+    return hashlib.md5(("\n".join(_records(bam)) + "\n").encode()).hexdigest()
+
+
+@pytest.mark.parametrize("name,which", [("t1", ["t1"]), ("t2", ["t2"]), ("t12", ["t1", "t2"])])
+def test_c1_fixture_bams_through_tiebrush_gpu_md5(tmp_path, name, which):
+    """C1: `tiebrush -o o.bam test/t1/t1s[0-9].bam ...` on the GPU command line reproduces the record md5 of the compiled reference."""
+    _need(os.path.join(REF, "htsfile"), os.path.join(HOST, "tiebrush_gpu"))
+    files = _fixture_bams(which)
+    assert len(files) == 10 * len(which)
+    out = str(tmp_path / f"{name}.bam")
+    msg = _run([os.path.join(HOST, "tiebrush_gpu"), "-o", out] + files)
+    assert _md5_records(out) == C1_MD5[name]
+    assert {"t1": "416922 input records written as 3479", "t2": "242910 input records written as 8179", "t12": "659832 input records written as 9491"}[name] in msg
+
+
+def test_c1_tiecov_gpu_on_the_collapsed_fixtures_md5(tmp_path):
+    """C1: tiecov -c -j on the 20-file collapsed BAM: bedGraph and junction BED bytes of the compiled reference (md5)."""
+    import hashlib
+    _need(os.path.join(HOST, "tiebrush_gpu"), os.path.join(HOST, "tiecov_gpu"))
+    out = str(tmp_path / "t12.bam")
+    _run([os.path.join(HOST, "tiebrush_gpu"), "-o", out] + _fixture_bams(["t1", "t2"]))
+    c, j = str(tmp_path / "k.cov"), str(tmp_path / "k.j")
+    _run([os.path.join(HOST, "tiecov_gpu"), "-c", c, "-j", j, out], env={"TB_WINDOW_RECORDS": "2000"})
+    assert hashlib.md5(open(c + ".bedgraph", "rb").read()).hexdigest() == C1_MD5["cov"]
+    assert hashlib.md5(open(j + ".bed", "rb").read()).hexdigest() == C1_MD5["junc"]
+
+
+def test_store_frac_then_tiecov_cli_is_exact(sams):
+    """tiebrush --store-frac writes YC like 0.333333: tiecov_gpu must print the reference's bytes (ordered double sums), not
+    2^-20 fixed-point sums. VERDICT r1 item 5a."""
+    _need(os.path.join(REF, "tiecov"), os.path.join(HOST, "tiecov_gpu"))
+    tmp, paths, _ = sams
+    frac = os.path.join(tmp, "frac.bam")
+    _run([os.path.join(REF, "tiebrush"), "--store-frac", "--keep-secondary", "-o", frac] + paths)
+    assert any("YC:f:0.3" in r or "YC:f:0.1" in r or "YC:f:0.2" in r for r in _records(frac)[:5000])
+    rc, rj, gc, gj = (os.path.join(tmp, x) for x in ("ref_frac_cov", "ref_frac_j", "gpu_frac_cov", "gpu_frac_j"))
+    _run([os.path.join(REF, "tiecov"), "-c", rc, "-j", rj, frac])
+    _run([os.path.join(HOST, "tiecov_gpu"), "-c", gc, "-j", gj, frac], env={"TB_WINDOW_RECORDS": "800"})
+    assert open(gc + ".bedgraph").read() == open(rc + ".bedgraph").read()
+    assert open(gj + ".bed").read() == open(rj + ".bed").read()

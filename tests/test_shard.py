@@ -235,3 +235,30 @@ def test_sample_heatmap_shards_equal_whole_stream(seed, world, chroms):
         got = shard._stitch_sample(parts)
         for a, b in zip(got, exp):
             assert np.array_equal(a, b), (seed, world, shift)
+
+
+def _tiny_stream(recs):
+    """recs = [(pos, M length)] on tid 0, YX = 3, 7, 11 ..."""
+    n = len(recs)
+    return dict(tid=np.zeros(n, np.int32), pos=np.asarray([p for p, _ in recs], np.int32), yc=np.ones(n, np.float32),
+                strand=np.full(n, ord("."), np.uint8), cig_off=np.arange(n + 1, dtype=np.uint32),
+                cigar=np.asarray([(l << 4) | 0 for _, l in recs], np.uint32), yx=np.asarray([3 + 4 * i for i in range(n)], np.int32))
+
+
+@pytest.mark.parametrize("recs,cuts", [
+    ([(0, 100), (200, 50)], [(0, 50)]),                       # the bundle reaches past the cut, no record of it starts there
+    ([(0, 100), (200, 50)], [(0, 50), (0, 80)]),              # ... and a rank with no record of its own in between
+    ([(0, 100), (200, 50)], [(0, 150)]),                      # cut in the gap
+    ([(0, 300), (10, 20), (400, 30)], [(0, 5), (0, 100), (0, 250)]),
+    ([(0, 300), (10, 20), (400, 30)], [(0, 11), (0, 350)]),
+    ([(0, 300), (10, 20), (400, 30)], [(0, 299), (0, 300), (0, 301)]),
+])
+def test_sample_heatmap_shards_sparse_streams_and_empty_ranks(recs, cuts):
+    """a bundle open at a cut with no further record after it, ranks without records, cuts in gaps."""
+    cols = _tiny_stream(recs)
+    exp = oracle.sample_heatmap(cols)
+    bounds = [None] + cuts + [None]
+    parts = [shard.sample_shard_local(oracle.sample_heatmap, cols, bounds[g], bounds[g + 1]) for g in range(len(cuts) + 1)]
+    got = shard._stitch_sample(parts)
+    for a, b in zip(got, exp):
+        assert np.array_equal(a, b), (recs, cuts, got, exp)

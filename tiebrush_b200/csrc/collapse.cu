@@ -55,6 +55,11 @@ struct ExpandOut {
   }
 };
 
+// compact wire format: a scan total against what the packer declared (status[CS_ERR] = code on mismatch)
+__global__ void col_check_total_kernel(const uint32_t* tot, unsigned long long want, long long* status, int code) {
+  if ((unsigned long long)*tot != want) { status[CS_ERR] = code; status[CS_ERRIDX] = (long long)*tot; }
+}
+
 struct HistIn { const uint32_t* c; __device__ uint32_t operator()(int64_t i) const { return c[i]; } };
 struct HistOut { uint32_t* p; __device__ void operator()(int64_t i, uint32_t exc, uint32_t) const { p[i] = exc; } };
 
@@ -85,6 +90,12 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
   in.n = n; in.k = k; in.mode = ctx->mode; in.flag_mask = ctx->flag_mask; in.max_nh = ctx->max_nh; in.min_qual = ctx->min_qual; in.keep_bits = ctx->keep_bits;
   in.collapse_same = ctx->collapse_same;
   in.pos_lo = hin->pos_lo; in.span = (uint32_t)(hin->pos_hi - hin->pos_lo);
+  TB_CUDA(B[XB_STATUS].ensure(sizeof(int64_t) * 16));
+  TB_CUDA(ctx->pinned[0].ensure(1024));
+  long long* d_status = B[XB_STATUS].as<long long>();
+  long long* h_status = ctx->pinned[0].as<long long>();
+  memset(h_status, 0, sizeof(int64_t) * 16); h_status[CS_ERRIDX] = -1;
+  TB_CUDA(cudaMemcpyAsync(d_status, h_status, sizeof(int64_t) * 16, cudaMemcpyHostToDevice, st));
   const int dev = hin->on_device;
   if (tb_stage_in(ctx, ctx->in_stage[0], hin->pos, (size_t)n, dev, &in.pos)) return 1;
   if (tb_stage_in(ctx, ctx->in_stage[1], hin->flag, (size_t)n, dev, &in.flag)) return 1;
@@ -101,6 +112,9 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
     TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks(n) + 8) * sizeof(uint64_t)));
     TB_CUDA((tb_device_scan<OpSumU32>(ctx, Nc8In{n8}, n, B[XB_AGG].as<uint32_t>(), OffOut{ctx->in_stage[5].as<uint32_t>(), n})));
     in.cig_off = ctx->in_stage[5].as<uint32_t>();
+    // the packer's n_cig must be the sum of the per-record op counts (otherwise the arena would be read out of bounds)
+    col_check_total_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(n), (unsigned long long)hin->n_cig, d_status, 4);
+    ctx->launches++;
   }
   if (hin->cigar) { if (tb_stage_in(ctx, ctx->in_stage[6], hin->cigar, (size_t)hin->n_cig, dev, &in.cigar)) return 1; }
   else {   // 16-bit ops widened to BAM words, escaped lengths taken from cigar_ext in op order
@@ -111,6 +125,9 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
     TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks(hin->n_cig) + 8) * sizeof(uint64_t)));
     TB_CUDA((tb_device_scan<OpSumU32>(ctx, EscIn{c16}, hin->n_cig, B[XB_AGG].as<uint32_t>(), ExpandOut{c16, ext, ctx->in_stage[6].as<uint32_t>()})));
     in.cigar = ctx->in_stage[6].as<uint32_t>();
+    // every escaped length (field 0xFFF) takes one entry of cigar_ext, in op order
+    col_check_total_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(hin->n_cig), (unsigned long long)hin->n_ext, d_status, 5);
+    ctx->launches++;
   }
   if (ctx->mode == TB_MODE_FULL) {
     if (tb_stage_in(ctx, ctx->in_stage[7], hin->md_off, (size_t)n + 1, dev, &in.md_off)) return 1;
@@ -125,12 +142,6 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
 
   const uint32_t W = (uint32_t)((k + 31) / 32);
   const uint32_t S = in.span;
-  TB_CUDA(B[XB_STATUS].ensure(sizeof(int64_t) * 16));
-  TB_CUDA(ctx->pinned[0].ensure(1024));
-  long long* d_status = B[XB_STATUS].as<long long>();
-  long long* h_status = ctx->pinned[0].as<long long>();
-  memset(h_status, 0, sizeof(int64_t) * 16); h_status[CS_ERRIDX] = -1;
-  TB_CUDA(cudaMemcpyAsync(d_status, h_status, sizeof(int64_t) * 16, cudaMemcpyHostToDevice, st));
   TB_CUDA(B[XB_HIST].ensure(sizeof(uint32_t) * ((size_t)S + 2)));
   TB_CUDA(B[XB_RUNOFF].ensure(sizeof(int64_t) * (k + 1)));
   TB_CUDA(cudaMemcpyAsync(B[XB_RUNOFF].p, hin->run_off, sizeof(int64_t) * (k + 1), cudaMemcpyHostToDevice, st));
@@ -158,6 +169,8 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
   TB_CUDA(cudaStreamSynchronize(st));
   if (ctx->profiling) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ctx->last_ms[2] = ms; }
   if (h_status[CS_ERR] == ERR_POS_RANGE) { ctx->set_error("tb_collapse_window: record %lld has pos outside [pos_lo,pos_hi)", h_status[CS_ERRIDX]); return 1; }
+  if (h_status[CS_ERR] == 4) { ctx->set_error("tb_collapse_window: compact wire format: n_cigar8 sums to %lld ops but n_cig = %lld", h_status[CS_ERRIDX], (long long)hin->n_cig); return 1; }
+  if (h_status[CS_ERR] == 5) { ctx->set_error("tb_collapse_window: compact wire format: cigar16 holds %lld escaped lengths but n_ext = %lld", h_status[CS_ERRIDX], (long long)hin->n_ext); return 1; }
   if (h_status[CS_ERR] == 3) { ctx->set_error("tb_collapse_window: unmapped record %lld kept by -M: the reference aborts here (GVec invalid index)", h_status[CS_ERRIDX]); return 1; }
 
   ColGeom g; g.n = n; g.k = k; g.W = W; g.S = S; g.P = d_hist; g.d_runoff = B[XB_RUNOFF].as<long long>(); g.d_merged = d_merged; g.d_status = d_status; g.n_cig = hin->n_cig;

@@ -32,6 +32,7 @@
 #include <condition_variable>
 #include <deque>
 #include <memory>
+#include <functional>
 #include "tiebrush_b200.h"
 
 namespace {
@@ -50,6 +51,26 @@ struct TbWindow {   // what the reader thread hands to the device thread
   }
 };
 
+// background deleter of the records of finished windows
+struct Reaper {
+  std::mutex m; std::condition_variable cv; std::deque<std::vector<GSamRecord*>> q; bool done = false; std::thread th;
+  Reaper() : th([this] {
+    for (;;) {
+      std::vector<GSamRecord*> v;
+      { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return !q.empty() || done; }); if (q.empty()) return; v = std::move(q.front()); q.pop_front(); }
+      const size_t n = v.size();
+      int nt = n > 200000 ? 4 : 1;
+      if (const char* e = getenv("TB_FREE_THREADS")) nt = atoi(e) > 0 ? atoi(e) : 1;
+      if (nt == 1) { for (GSamRecord* r : v) delete r; continue; }
+      std::vector<std::thread> w;
+      for (int t = 0; t < nt; ++t) w.emplace_back([&, t] { for (size_t x = n * t / nt; x < n * (t + 1) / nt; ++x) delete v[x]; });
+      for (auto& x : w) x.join();
+    }
+  }) {}
+  void push(std::vector<GSamRecord*>&& v) { { std::lock_guard<std::mutex> lk(m); q.push_back(std::move(v)); } cv.notify_all(); }
+  void finish() { { std::lock_guard<std::mutex> lk(m); done = true; } cv.notify_all(); th.join(); }
+};
+
 struct TbWindowPacker {
   int k = 0;
   htsFile* out_fp = NULL; sam_hdr_t* out_hdr = NULL;
@@ -64,7 +85,8 @@ struct TbWindowPacker {
   std::vector<float> yc_in;
   std::vector<GSamRecord*> held;                    // window index -> record
   std::vector<uint32_t> o_rep, o_yx; std::vector<float> o_yc; std::vector<int32_t> o_yd;
-  double t_pack = 0, t_device = 0, t_write = 0;
+  double t_pack = 0, t_device = 0, t_write = 0, t_tagwrite_only = 0;
+  struct Reaper* reaper = NULL;
   int64_t n_windows = 0;
 
   void init(int nfiles) { k = nfiles; }
@@ -88,43 +110,75 @@ struct TbWindowPacker {
     for (int f = 0; f < k; ++f) any_merged |= file_merged[f] != 0;
     run_off.assign(k + 1, 0);
     pos.resize(n); flag.resize(n); mapq.resize(n); strand.resize(n); nh.resize(n); cig_off.resize(n + 1);
-    cigar.clear(); held.resize(n);
-    n_cigar8.resize(n); cigar16.clear(); cigar_ext.clear();
+    held.resize(n);
+    n_cigar8.resize(n);
     bool compact = getenv("TB_WIRE_WIDE") == NULL;   // falls back to the wide columns when a record has >= 256 ops
-    if (want_md) { md_off.resize(n + 1); md.clear(); }
+    if (want_md) md_off.resize(n + 1);
     if (want_q) qhash.resize(n);
     if (any_merged) { yc_in.resize(n); yx_in.resize(n); yd_in.resize(n); }
-    size_t i = 0;
-    int32_t pos_lo = 0x7fffffff, pos_hi = 0;
-    for (int f = 0; f < k; ++f) {
-      run_off[f] = (int64_t)i;
+    // ---- two passes over the files, both on TB_PACK_THREADS threads (a share of the files each): sizes first (records,
+    // CIGAR ops, MD bytes, escaped lengths per file), then every file fills its own slice of the columns ----
+    int nt = (int)std::thread::hardware_concurrency(); if (nt > 16) nt = 16;
+    if (const char* e = getenv("TB_PACK_THREADS")) nt = atoi(e);
+    if (nt < 1) nt = 1;
+    if (nt > k) nt = k;
+    if (n < 50000) nt = 1;
+    std::vector<size_t> f_rec(k + 1, 0), f_cig(k + 1, 0), f_md(k + 1, 0), f_ext(k + 1, 0);
+    std::vector<uint8_t> f_long(k, 0);
+    auto on_files = [&](const std::function<void(int)>& body) {
+      if (nt == 1) { for (int f = 0; f < k; ++f) body(f); return; }
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; ++t) th.emplace_back([&, t] { for (int f = t; f < k; f += nt) body(f); });
+      for (auto& x : th) x.join();
+    };
+    on_files([&](int f) {
+      size_t c = 0, m = 0, x = 0; bool lg = false;
+      for (GSamRecord* r : per_file[f]) {
+        bam1_t* b = r->get_b();
+        c += b->core.n_cigar;
+        if (b->core.n_cigar >= 256) lg = true;
+        const uint32_t* cg = bam_get_cigar(b);
+        for (uint32_t q = 0; q < b->core.n_cigar; ++q) if ((cg[q] >> 4) >= 0xFFFu) ++x;
+        if (want_md) { const char* s = r->tag_str("MD"); if (s) m += strlen(s) + 1; }
+      }
+      f_rec[f + 1] = per_file[f].size(); f_cig[f + 1] = c; f_md[f + 1] = m; f_ext[f + 1] = x; f_long[f] = lg;
+    });
+    for (int f = 0; f < k; ++f) { f_rec[f + 1] += f_rec[f]; f_cig[f + 1] += f_cig[f]; f_md[f + 1] += f_md[f]; f_ext[f + 1] += f_ext[f]; if (f_long[f]) compact = false; }
+    if (f_cig[k] >= (1ULL << 32)) GError("Error: a window of %zu CIGAR operations does not fit 32-bit offsets (lower TB_WINDOW_RECORDS)\n", f_cig[k]);
+    cigar.resize(f_cig[k]);
+    if (compact) { cigar16.resize(f_cig[k]); cigar_ext.resize(f_ext[k]); }
+    if (want_md) md.resize(f_md[k]);
+    std::vector<int32_t> f_lo(k, 0x7fffffff), f_hi(k, 0);
+    on_files([&](int f) {
+      size_t i = f_rec[f], ci = f_cig[f], mi = f_md[f], xi = f_ext[f];
       for (GSamRecord* r : per_file[f]) {
         bam1_t* b = r->get_b();
         held[i] = r;
         pos[i] = (int32_t)b->core.pos;
-        if (pos[i] < pos_lo) pos_lo = pos[i];
-        if (pos[i] >= pos_hi) pos_hi = pos[i] + 1;
+        if (pos[i] < f_lo[f]) f_lo[f] = pos[i];
+        if (pos[i] >= f_hi[f]) f_hi[f] = pos[i] + 1;
         flag[i] = b->core.flag;
         mapq[i] = b->core.qual;
         strand[i] = (uint8_t)r->spliceStrand();                      // GSam.cpp:464-475
         int64_t v = r->tag_int("NH", 0);                             // passes_options, tiebrush.cpp:537
         nh[i] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
-        cig_off[i] = (uint32_t)cigar.size();
+        cig_off[i] = (uint32_t)ci;
         const uint32_t* c = bam_get_cigar(b);
-        cigar.insert(cigar.end(), c, c + b->core.n_cigar);
-        if (b->core.n_cigar >= 256) compact = false;
+        const uint32_t nc = b->core.n_cigar;
+        memcpy(cigar.data() + ci, c, sizeof(uint32_t) * nc);
         if (compact) {
-          n_cigar8[i] = (uint8_t)b->core.n_cigar;
-          for (uint32_t q = 0; q < b->core.n_cigar; ++q) {
+          n_cigar8[i] = (uint8_t)nc;
+          for (uint32_t q = 0; q < nc; ++q) {
             const uint32_t len = c[q] >> 4;
-            if (len >= 0xFFFu) { cigar16.push_back((uint16_t)((c[q] & 0xfu) | (0xFFFu << 4))); cigar_ext.push_back(len); }
-            else cigar16.push_back((uint16_t)((c[q] & 0xfu) | (len << 4)));
+            if (len >= 0xFFFu) { cigar16[ci + q] = (uint16_t)((c[q] & 0xfu) | (0xFFFu << 4)); cigar_ext[xi++] = len; }
+            else cigar16[ci + q] = (uint16_t)((c[q] & 0xfu) | (len << 4));
           }
         }
+        ci += nc;
         if (want_md) {
-          md_off[i] = (uint32_t)md.size();
+          md_off[i] = (uint32_t)mi;
           const char* m = r->tag_str("MD");                          // cmpFull, tiebrush.cpp:285-304
-          if (m) md.insert(md.end(), (const uint8_t*)m, (const uint8_t*)m + strlen(m) + 1);
+          if (m) { const size_t l = strlen(m) + 1; memcpy(md.data() + mi, m, l); mi += l; }
         }
         if (want_q) qhash[i] = fnv1a(r->name());
         if (any_merged) {
@@ -134,7 +188,10 @@ struct TbWindowPacker {
         }
         ++i;
       }
-    }
+    });
+    int32_t pos_lo = 0x7fffffff, pos_hi = 0;
+    for (int f = 0; f < k; ++f) { run_off[f] = (int64_t)f_rec[f]; if (f_lo[f] < pos_lo) pos_lo = f_lo[f]; if (f_hi[f] > pos_hi) pos_hi = f_hi[f]; }
+    const size_t i = n;
     run_off[k] = (int64_t)i;
     cig_off[n] = (uint32_t)cigar.size();
     if (want_md) md_off[n] = (uint32_t)md.size();
@@ -159,15 +216,33 @@ struct TbWindowPacker {
     if (tb_collapse_window(ctx, &in, &out)) GError("%s\n", tb_last_error(ctx));
     auto t2 = clk::now();
     inCounter += (uint64_t)out.n_kept;                               // tiebrush.cpp:573
-    for (int64_t g = 0; g < out.n_groups; ++g) {                     // flushPData, tiebrush.cpp:506-527
-      GSamRecord* r = held[o_rep[g]];
-      r->add_double_tag("YC", (double)o_yc[g]);
-      r->add_int_tag("YX", (int64_t)o_yx[g]);
-      if (o_yd[g] > 0) r->add_int_tag("YD", o_yd[g]); else r->remove_tag("YD");
-      if (sam_write1(out_fp, out_hdr, r->get_b()) < 0) GError("Error writing SAM record!\n");   // GSamWriter::write, GSam.h:648-653
-      outCounter++;
+    {   // flushPData, tiebrush.cpp:506-527: the tags of the representatives are patched on the pack threads (records are
+        // independent), the BAM records are then written in output order (BGZF compression on the htslib worker threads)
+      const int64_t G = out.n_groups;
+      auto patch = [&](int64_t g) {
+        GSamRecord* r = held[o_rep[g]];
+        r->add_double_tag("YC", (double)o_yc[g]);
+        r->add_int_tag("YX", (int64_t)o_yx[g]);
+        if (o_yd[g] > 0) r->add_int_tag("YD", o_yd[g]); else r->remove_tag("YD");
+      };
+      if (nt == 1 || G < 20000) { for (int64_t g = 0; g < G; ++g) patch(g); }
+      else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back([&, t] { for (int64_t g = G * t / nt; g < G * (t + 1) / nt; ++g) patch(g); });
+        for (auto& x : th) x.join();
+      }
+      for (int64_t g = 0; g < G; ++g) {
+        if (sam_write1(out_fp, out_hdr, held[o_rep[g]]->get_b()) < 0) GError("Error writing SAM record!\n");   // GSamWriter::write, GSam.h:648-653
+        outCounter++;
+      }
     }
-    for (GSamRecord* r : held) delete r;
+    auto t2b = clk::now();
+    // the window's records (millions of bam1_t + exon vectors) go back to the allocator on a background thread: off the
+    // device thread's critical path, overlapping the next window
+    if (reaper) reaper->push(std::move(held));
+    else for (GSamRecord* r : held) delete r;
+    held = std::vector<GSamRecord*>();
+    t_tagwrite_only += std::chrono::duration<double>(t2b - t2).count();
     ++n_windows;
     auto t3 = clk::now();
     t_pack += std::chrono::duration<double>(t1 - t0).count();
@@ -220,8 +295,15 @@ int main(int argc, char* argv[]) {
   size_t window_min = 1u << 20;
   if (const char* e = getenv("TB_WINDOW_RECORDS")) { long v = atol(e); if (v > 0) window_min = (size_t)v; }
 
+  // The window is cut only at a coordinate no read covers; an input without such a gap (a deep locus, DNA-seq) would buffer a
+  // whole contig on the host and then overflow tb_collapse_window's n < 2^31: stop with a clear message before that
+  // (the reference streams such inputs in O(k) memory; carrying the YD segment lists across windows is not built yet).
+  size_t window_max = 400u << 20;
+  if (const char* e = getenv("TB_WINDOW_MAX_RECORDS")) { long long v = atoll(e); if (v > 0) window_max = (size_t)v; }
+  if (window_max > 2000000000u) window_max = 2000000000u;
   const bool dry_run = getenv("TB_DRYRUN") != NULL;   // reader self-check: no device, no output records, window statistics only
   TbWindowPacker packer; packer.init(numSamples); packer.out_fp = out_fp; packer.out_hdr = out_hdr;
+  Reaper reaper; packer.reaper = &reaper;
   TbQueue queue;
   double t_create = 0;
   std::thread device_thread([&] {   // owns the CUDA context: one submitting host thread per context
@@ -324,6 +406,9 @@ int main(int argc, char* argv[]) {
         for (size_t x = 0; x < m; ++x) { run += depth[x]; if (run == 0 && x > 0) cut = chunk_lo + x; }   // keeps the last one
       }
       if (cut == 0) {   // too few records or no gap inside the chunk: extend it (span follows the read density)
+        if (n_pend > window_max)
+          GError("Error: no coverage gap within %zu alignments on reference %d (coordinates %llu-%llu): the window cannot be cut. Raise TB_WINDOW_MAX_RECORDS (host memory ~400 B per alignment, at most 2e9) or split the input.\n",
+                 n_pend, cur_tid, (unsigned long long)chunk_lo, (unsigned long long)bound);
         if (n_pend > 0) {
           const double dens = (double)n_pend / (double)(bound - chunk_lo + 1);
           const double want = (double)window_min / (dens > 1e-9 ? dens : 1e-9);
@@ -358,6 +443,8 @@ int main(int argc, char* argv[]) {
   const double t_read = std::chrono::duration<double>(clk::now() - tr0).count();
   queue.finish();
   device_thread.join();
+  const double t_before_reap = std::chrono::duration<double>(clk::now() - t_begin).count();
+  reaper.finish();
   inRecords.stop();
   if (hts_close(out_fp) < 0) GError("Error closing output file %s\n", outfname.chars());
   sam_hdr_destroy(out_hdr);
@@ -365,7 +452,7 @@ int main(int argc, char* argv[]) {
   double p = 100.00 - (double)(outCounter * 100.00) / (double)inCounter;
   GMessage("%ld input records written as %ld (%.2f%% reduction)\n", inCounter, outCounter, p);
   if (getenv("TB_TIMING"))
-    fprintf(stderr, "tb_b200 timing: total %.3f s | decode+merge %.3f | pack %.3f | device (H2D+kernels+D2H) %.3f | tag+write %.3f | windows %ld | cuda init %.3f (overlapped) | reader thread includes waiting for the device thread\n",
-            std::chrono::duration<double>(clk::now() - t_begin).count(), t_read, packer.t_pack, packer.t_device, packer.t_write, (long)packer.n_windows, t_create);
+    fprintf(stderr, "tb_b200 timing: total %.3f s | decode+merge %.3f | pack %.3f | device (H2D+kernels+D2H) %.3f | tag+write %.3f | windows %ld | cuda init %.3f (overlapped) | reader thread includes waiting for the device thread | all windows written at %.3f s, records freed on a background thread\n",
+            std::chrono::duration<double>(clk::now() - t_begin).count(), t_read, packer.t_pack, packer.t_device, packer.t_write, (long)packer.n_windows, t_create, t_before_reap);
   return 0;
 }

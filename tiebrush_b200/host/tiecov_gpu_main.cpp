@@ -17,22 +17,46 @@
 
 #include <vector>
 #include <chrono>
+#include <string>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <deque>
+#include <memory>
 #include "tiebrush_b200.h"
 
 namespace {
 
-struct TcWindowPacker {
+// rows [a, b) of a text track, formatted by `fmt(i, buf)` on TB_PRINT_THREADS threads and written in order (the text is what
+// fprintf would have produced: the same format strings)
+template <class F>
+static void print_rows(FILE* f, int64_t n, F fmt) {
+  if (n <= 0) return;
+  int nt = 8;
+  if (const char* e = getenv("TB_PRINT_THREADS")) nt = atoi(e);
+  if (nt < 1) nt = 1;
+  if (n < 20000) nt = 1;
+  std::vector<std::string> parts(nt);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&, t] {
+      const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+      std::string& out = parts[t];
+      out.reserve((size_t)(b - a) * 40);
+      char buf[512];
+      for (int64_t i = a; i < b; ++i) { const int len = fmt(i, buf, sizeof(buf)); out.append(buf, (size_t)len); }
+    });
+  for (auto& x : th) x.join();
+  for (int t = 0; t < nt; ++t) fwrite(parts[t].data(), 1, parts[t].size(), f);
+}
+
+struct TcWindow {   // what the reader thread hands to the device thread: SoA columns of whole bundles
   std::vector<int32_t> tid, pos;
   std::vector<float> yc;
   std::vector<uint8_t> strand;
   std::vector<uint32_t> cig_off, cigar;
   std::vector<int32_t> yx;                                          // -s: YX tag per record
-  int n_samples = 0;                                                // -s: @CO SAMPLE lines of the header
-  std::vector<int32_t> r_tid, r_start, r_end, j_tid, j_start, j_end, s_tid, s_start, s_end; std::vector<double> r_val, j_val, s_val; std::vector<uint8_t> j_strand;
-  double t_device = 0, t_print = 0; int64_t n_windows = 0;
-
   size_t n() const { return pos.size(); }
-
   void add(GSamRecord& brec) {
     bam1_t* b = brec.get_b();
     tid.push_back(b->core.tid); pos.push_back((int32_t)b->core.pos);
@@ -45,9 +69,17 @@ struct TcWindowPacker {
     const uint32_t* c = bam_get_cigar(b);
     cigar.insert(cigar.end(), c, c + b->core.n_cigar);
   }
+};
 
-  void flush(tb_ctx* ctx, sam_hdr_t* hdr) {
-    const size_t m = n();
+struct TcWindowPacker {
+  int n_samples = 0;                                                // -s: @CO SAMPLE lines of the header
+  std::vector<int32_t> r_tid, r_start, r_end, j_tid, j_start, j_end, s_tid, s_start, s_end; std::vector<double> r_val, j_val, s_val; std::vector<uint8_t> j_strand;
+  double t_device = 0, t_print = 0; int64_t n_windows = 0;
+
+  void flush(tb_ctx* ctx, sam_hdr_t* hdr, TcWindow& w) {
+    std::vector<int32_t>& tid = w.tid; std::vector<int32_t>& pos = w.pos; std::vector<float>& yc = w.yc; std::vector<uint8_t>& strand = w.strand;
+    std::vector<uint32_t>& cig_off = w.cig_off; std::vector<uint32_t>& cigar = w.cigar; std::vector<int32_t>& yx = w.yx;
+    const size_t m = w.n();
     if (m == 0) return;
     using clk = std::chrono::steady_clock;
     auto t0 = clk::now();
@@ -79,24 +111,23 @@ struct TcWindowPacker {
       if (tc_sample_window(ctx, &in, yx.data(), &rows)) GError("%s\n", tb_last_error(ctx));
     }
     auto t1 = clk::now();
-    if (coutf)
-      for (int64_t i = 0; i < runs.n_runs; ++i)                      // flushCoverage, tiecov.cpp:237
-        fprintf(coutf, "%s\t%d\t%d\t%.3f\n", hdr->target_name[r_tid[i]], r_start[i], r_end[i], r_val[i]);
-    if (joutf)
-      for (int64_t i = 0; i < js.n_juncs; ++i) {                     // CJunc::write, tiecov.cpp:91-95
-        juncCount++;
-        fprintf(joutf, "%s\t%d\t%d\tJUNC%08d\t%.3f\t%c\n", hdr->target_name[j_tid[i]], j_start[i] - 1, j_end[i], juncCount, j_val[i], (char)j_strand[i]);
-      }
+    if (coutf)                                                        // flushCoverage, tiecov.cpp:237
+      print_rows(coutf, runs.n_runs, [&](int64_t i, char* buf, size_t cap) {
+        return snprintf(buf, cap, "%s\t%d\t%d\t%.3f\n", hdr->target_name[r_tid[i]], r_start[i], r_end[i], r_val[i]); });
+    if (joutf) {                                                      // CJunc::write, tiecov.cpp:91-95 (global counter)
+      const int base = juncCount;
+      print_rows(joutf, js.n_juncs, [&](int64_t i, char* buf, size_t cap) {
+        return snprintf(buf, cap, "%s\t%d\t%d\tJUNC%08d\t%.3f\t%c\n", hdr->target_name[j_tid[i]], j_start[i] - 1, j_end[i], base + (int)i + 1, j_val[i], (char)j_strand[i]); });
+      juncCount += (int)js.n_juncs;
+    }
     if (soutf) {   // normalize(bsam, 0.1, 1.5, n_samples) + flushCoverage of the pair vector (tiecov.cpp:293-318)
       const float mint = 0.1, maxt = 1.5;
       const float denom = n_samples, mult = (maxt - mint);
-      for (int64_t i = 0; i < rows.n_runs; ++i) {
+      print_rows(soutf, rows.n_runs, [&](int64_t i, char* buf, size_t cap) {
         const uint64_t ival = (uint64_t)s_val[i];
         const float hval = ((float)ival / denom) * mult + mint;
-        fprintf(soutf, "%s\t%d\t%d\t%ld\t%f\n", hdr->target_name[s_tid[i]], s_start[i], s_end[i], (long)ival, hval);
-      }
+        return snprintf(buf, cap, "%s\t%d\t%d\t%ld\t%f\n", hdr->target_name[s_tid[i]], s_start[i], s_end[i], (long)ival, hval); });
     }
-    tid.clear(); pos.clear(); yc.clear(); strand.clear(); cig_off.clear(); cigar.clear(); yx.clear();
     ++n_windows;
     auto t2 = clk::now();
     t_device += std::chrono::duration<double>(t1 - t0).count();
@@ -137,24 +168,51 @@ int main(int argc, char* argv[]) {
     load_sample_info(samreader.header(), sample_info);
     packer.n_samples = (int)sample_info.size();
   }
+  // host pipeline: this thread decodes and packs window w+1 while the device thread runs window w and
+  // formats / writes its rows; at most two windows wait in the queue
+  std::mutex qm; std::condition_variable qcv; std::deque<std::unique_ptr<TcWindow>> q; bool q_done = false;
+  std::thread device_thread([&] {
+    for (;;) {
+      std::unique_ptr<TcWindow> w;
+      {
+        std::unique_lock<std::mutex> lk(qm);
+        qcv.wait(lk, [&] { return !q.empty() || q_done; });
+        if (q.empty()) return;
+        w = std::move(q.front()); q.pop_front(); qcv.notify_all();
+      }
+      packer.flush(ctx, samreader.header(), *w);
+    }
+  });
+  auto hand_over = [&](std::unique_ptr<TcWindow>& w) {
+    if (w->n() == 0) return;
+    std::unique_lock<std::mutex> lk(qm);
+    qcv.wait(lk, [&] { return q.size() < 2; });
+    q.push_back(std::move(w)); qcv.notify_all();
+    w.reset(new TcWindow());
+  };
+  std::unique_ptr<TcWindow> win(new TcWindow());
   int prev_tid = -1, b_end = 0;
   GSamRecord brec;
+  auto tr0 = clk::now();
   while (samreader.next(brec)) {
     if (brec.isUnmapped()) continue;                                 // tiecov.cpp:436-438
     const bool new_bundle = brec.refId() != prev_tid || (int)brec.start > b_end;   // tiecov.cpp:443
     if (new_bundle) {
-      if (packer.n() >= window_min) packer.flush(ctx, samreader.header());
+      if (win->n() >= window_min) hand_over(win);
       b_end = brec.end; prev_tid = brec.refId();
     } else if (b_end < (int)brec.end) b_end = brec.end;
-    packer.add(brec);
+    win->add(brec);
   }
-  packer.flush(ctx, samreader.header());
+  hand_over(win);
+  const double t_read = std::chrono::duration<double>(clk::now() - tr0).count();
+  { std::lock_guard<std::mutex> lk(qm); q_done = true; qcv.notify_all(); }
+  device_thread.join();
   if (coutf && coutf != stdout) fclose(coutf);
   if (joutf) fclose(joutf);
   if (soutf) fclose(soutf);
   tb_destroy(ctx);
   if (getenv("TB_TIMING"))
-    fprintf(stderr, "tb_b200 timing: total %.3f s | device (H2D+kernels+D2H) %.3f | print %.3f | windows %ld\n",
-            std::chrono::duration<double>(clk::now() - t_begin).count(), packer.t_device, packer.t_print, (long)packer.n_windows);
+    fprintf(stderr, "tb_b200 timing: total %.3f s | decode+pack (reader thread, incl. waiting for the device thread) %.3f | device (H2D+kernels+D2H) %.3f | print %.3f | windows %ld\n",
+            std::chrono::duration<double>(clk::now() - t_begin).count(), t_read, packer.t_device, packer.t_print, (long)packer.n_windows);
   return 0;
 }

@@ -433,13 +433,26 @@ def sample_shard_local(compute, cols, lo, hi):
     a = 0 if lo is None else int(np.searchsorted(key, (lo[0] << 32) | lo[1], side="left"))
     b = n if hi is None else int(np.searchsorted(key, (hi[0] << 32) | hi[1], side="left"))
     empty = tuple(np.zeros(0, dt) for dt in (np.int32, np.int32, np.int32, np.uint64))
-    head = bundle_heads(np.asarray(cols["tid"]), np.asarray(cols["pos"]), ref_end(cols))
-    inside = bool(lo is not None and a < n and not head[a])          # the cut at lo falls inside a bundle
-    if a >= b:
+    end = ref_end(cols)
+    head = bundle_heads(np.asarray(cols["tid"]), np.asarray(cols["pos"]), end)
+    # Is a bundle open at `lo`? Decided from the running maximum end of the records BEFORE the cut (0-based exclusive end
+    # > lo's position on lo's tid), not from the first record at or after it: the bundle may reach beyond the cut without
+    # any further record of it starting there, and then its bases in [lo, bundle end) belong to this rank all the same.
+    inside = False
+    if lo is not None and a > 0:
+        pm_before = int(np.max(_key(cols["tid"], end)[:a]))      # keys grow with tid, so the maximum sits on the last tid
+        inside = (pm_before >> 32) == lo[0] and (pm_before & 0xFFFFFFFF) > lo[1]
+    if a >= b and not inside:
         return empty, inside
     a0 = a
-    while not head[a0]:
-        a0 -= 1
+    if inside:
+        a0 = a - 1
+        while not head[a0]:
+            a0 -= 1
+        # records [a0, a) open the bundle; if the first record at or after the cut starts a NEW bundle it is simply the next
+        # bundle of this rank's window
+    if a0 >= b:
+        return empty, inside
     idx = np.arange(a0, b, dtype=np.int64)
     sub = _cov_take(cols, idx)
     sub["yx"] = np.asarray(cols["yx"])[idx]
@@ -467,9 +480,10 @@ def _stitch_sample(parts):
     out = [[], [], [], []]
     for rows, inside in parts:
         t, s, e, v = rows
-        if len(t) and len(out[0]) and inside:
-            lt, ls, le, lv = out[0][-1], out[1][-1], out[2][-1], out[3][-1]
-            if len(lt) and lt[-1] == t[0] and le[-1] == s[0] and lv[-1] == v[0]:
+        last = next((i for i in range(len(out[0]) - 1, -1, -1) if len(out[0][i])), None)   # a rank may have contributed no row
+        if len(t) and last is not None and inside:
+            lt, ls, le, lv = out[0][last], out[1][last], out[2][last], out[3][last]
+            if lt[-1] == t[0] and le[-1] == s[0] and lv[-1] == v[0]:
                 le[-1] = e[0]
                 t, s, e, v = t[1:], s[1:], e[1:], v[1:]
         for q, x in zip(out, (t, s, e, v)):
