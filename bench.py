@@ -47,8 +47,9 @@ def parse_args():
     ap.add_argument("--cov-cpu-sample", type=int, default=int(os.environ.get("TB_BENCH_COV_CPU", 2_000_000)),
                     help="records of the stream written as SAM for the reference tiecov binary (CPU baseline of the tiecov leg)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--wire", default="compact", choices=["compact", "wide"],
-                    help="host column format of the e2e leg: compact = n_cigar8 + cigar16 (+cigar_ext), wide = cig_off + cigar (u32)")
+    ap.add_argument("--wire", default="packed", choices=["packed", "compact", "wide"],
+                    help="host column format of the e2e leg: packed = pos_d8 + meta8 (+ dictionary / escapes) and the compact CIGAR columns, "
+                         "compact = wide fixed columns + n_cigar8 + cigar16 (+cigar_ext), wide = cig_off + cigar (u32)")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("TB_BENCH_CPU_SAMPLE", 20_000_000)),
                     help="records of the cohort fed to the CPU baseline (bounded sample)")
     ap.add_argument("--cli-reads", type=int, default=int(os.environ.get("TB_BENCH_CLI_READS", 50_000)),
@@ -562,14 +563,20 @@ def main():
             torch.cuda.empty_cache()
             wire_cols = dict(cols)
             names = ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar")
-            if args.wire == "compact":   # what a host packer would fill directly; built here from the wide columns
+            if args.wire in ("compact", "packed"):   # what a host packer would fill directly; built here from the wide columns
                 wire_cols["n_cigar8"], wire_cols["cigar16"], wire_cols["cigar_ext"] = api.compact_cigar_columns(cols["cig_off"], cols["cigar"])
                 names = ("pos", "flag", "mapq", "strand", "nh", "n_cigar8", "cigar16", "cigar_ext")
+            meta_dict = None
+            if args.wire == "packed":
+                pk = api.pack_fixed_columns(cols, run_off)
+                meta_dict = pk.pop("meta_dict")
+                wire_cols.update(pk)
+                names = ("pos_d8", "pos_ext", "meta8", "meta_ext", "n_cigar8", "cigar16", "cigar_ext")
             for name in names + (("md_off", "md") if args.mode == 1 else ()):
                 t = wire_cols[name]
                 ht = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
                 ht.copy_(t)
-                host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32, "md_off": np.uint32, "flag": np.uint16, "nh": np.uint16, "cigar16": np.uint16, "cigar_ext": np.uint32}.get(name, ht.numpy().dtype))
+                host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32, "md_off": np.uint32, "flag": np.uint16, "nh": np.uint16, "cigar16": np.uint16, "cigar_ext": np.uint32, "meta_ext": np.uint64}.get(name, ht.numpy().dtype))
                 h2d += ht.numel() * ht.element_size()
             cap = max(G + 1024, 1)
             hout_t = dict(rep_index=torch.empty(cap, dtype=torch.int32, pin_memory=True), yc=torch.empty(cap, dtype=torch.float32, pin_memory=True),
@@ -586,6 +593,9 @@ def main():
             line["e2e"] = {"unavailable": "host buffers for the end-to-end leg could not be prepared on every rank" + (": " + e2e_err if "e2e_err" in dir() else "")}
         else:
             host["n_cig"] = n_cig
+            if meta_dict is not None:
+                host["meta_dict"] = meta_dict
+                h2d += meta_dict.nbytes
             if args.mode == 1:
                 host["n_md"] = int(cols["n_md"])
             # the device-resident copy is not needed any more: the host path stages its own (full size: 25 GB each)
@@ -610,7 +620,8 @@ def main():
                 e2e_ms = float(t.item())
             line["e2e"] = {"value": world * n / (e2e_ms / 1000.0), "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(16 * r2["n_groups"] + 128),
                            "ms_per_step": e2e_ms, "steps": es, "wall_ms_per_step": 1000.0 * (time.perf_counter() - t0) / es,
-                           "wire_format": args.wire + (" (n_cigar8 + cigar16 + cigar_ext; the device rebuilds cig_off / cigar inside the timed region)" if args.wire == "compact" else " (cig_off + cigar u32)")}
+                           "wire_format": args.wire + {"packed": " (pos_d8 + meta8 with dictionary / escapes, n_cigar8 + cigar16 + cigar_ext; the device rebuilds every wide column inside the timed region)",
+                                                       "compact": " (n_cigar8 + cigar16 + cigar_ext; the device rebuilds cig_off / cigar inside the timed region)", "wide": " (cig_off + cigar u32)"}[args.wire]}
     sampler.stop_flag.set(); sampler.join(timeout=3)
     line["clocks"] = clocks.summary()
 

@@ -363,3 +363,78 @@ def test_compact_wire_format_is_validated():
                 ctx.collapse_window(bad, run_off)
         ok = ctx.collapse_window(dict(compact, n_cigar8=n8, cigar16=c16, cigar_ext=ext), run_off)
         assert ok["n_groups"] > 0
+
+
+@pytest.mark.parametrize("mode,name", [(3, "-E"), (1, "-L")])
+def test_collapse_c3_full_size_properties_and_oracle_prefix(mode, name):
+    """BASELINE C3 at its configured size: the C2 cohort (100 x 10M reads, chr1) in -E and -L modes with -N 5 -Q 1
+    (TB_TEST_FULL=0 shrinks it to 100 x 2M). Size-independent properties over the whole output (sum YC == records that pass the
+    filters, counted independently on the device; YX bounds; representatives pass the filters and come in position order) and
+    bit-exact equality with the oracle on a coordinate prefix. VERDICT r1 item 5c."""
+    import os
+    import torch
+    from oracle import oracle
+    from tiebrush_b200 import api, synth
+    k = 100
+    reads = 2_000_000 if os.environ.get("TB_TEST_FULL") == "0" else 10_000_000
+    cols, run_off, pr = synth.cohort_window(k, reads, seed=0, device="cuda", with_md=(mode == 1))
+    if mode == 1:
+        cols["md_off"], cols["md"], cols["n_md"] = synth.md_columns_torch(cols)
+        del cols["md_mm"], cols["md_a"]
+    n = k * reads
+    out = dict(rep_index=torch.empty(n, dtype=torch.int32, device="cuda"), yc=torch.empty(n, dtype=torch.float32, device="cuda"),
+               yx=torch.empty(n, dtype=torch.int32, device="cuda"), yd=torch.empty(n, dtype=torch.int32, device="cuda"))
+    with api.Context(device=0, n_samples=k, mode=mode, max_nh=5, min_qual=1) as ctx:
+        got = ctx.collapse_window(cols, run_off, pos_range=pr, out=out)
+        assert ctx.last_path() == 0
+    G = got["n_groups"]
+    passes = ((cols["nh"].to(torch.int32) & 0xffff) <= 5) & (cols["mapq"].to(torch.int32) >= 1)
+    kept = int(passes.sum().item())
+    assert 0 < kept < n and got["n_kept"] == kept
+    rep = out["rep_index"][:G].long() & 0xffffffff
+    yc, yx, yd = out["yc"][:G], out["yx"][:G], out["yd"][:G]
+    assert int(yc.to(torch.float64).sum().item()) == kept
+    assert bool((yx >= 1).all()) and bool((yx.to(torch.float32) <= torch.clamp(yc, max=float(k))).all()) and bool((yd >= 0).all())
+    assert bool(passes[rep].all())
+    rpos = cols["pos"][rep]
+    assert bool((rpos[1:] >= rpos[:-1]).all())
+    sub, sub_off = synth.prefix_slice(cols, run_off, 1_500_000)
+    hi = int(sub["pos"].max()) + 1
+    exp = oracle.collapse(sub, sub_off, mode=mode, max_nh=5, min_qual=1)
+    Gs = len(exp["rep_index"])
+    assert Gs > 1000 and bool((rpos[:Gs] < hi).all()) and (G == Gs or int(rpos[Gs].item()) >= hi)
+    # representatives compared through (file, index in file): the prefix keeps every file's order
+    sub_file = np.searchsorted(sub_off, exp["rep_index"].astype(np.int64), side="right") - 1
+    glob = np.asarray(run_off)[sub_file] + (exp["rep_index"].astype(np.int64) - sub_off[sub_file])
+    assert np.array_equal(glob, rep[:Gs].cpu().numpy())
+    assert np.array_equal(yc[:Gs].cpu().numpy(), exp["yc"]) and np.array_equal(yx[:Gs].cpu().numpy().view(np.uint32), exp["yx"])
+    assert np.array_equal(yd[:Gs].cpu().numpy(), exp["yd"])
+
+
+@pytest.mark.parametrize("mode,max_dict", [(0, 255), (3, 255), (0, 3)])
+def test_collapse_packed_wire_format_equals_wide(mode, max_dict):
+    """pos_d8 (+ pos_ext: run starts, large gaps) and meta8 (+ dictionary, escapes when the dictionary is too small) with the
+    compact CIGAR columns must give exactly the wide-format result, from host buffers and from device-resident tensors."""
+    import torch
+    from oracle import oracle
+    from tiebrush_b200 import api, synth
+    k = 12
+    cols, run_off, pr = synth.cohort_window(k, 15000, seed=23, n_tx=200, device="cpu")
+    host = synth.to_host(cols)
+    n8, c16, ext = api.compact_cigar_columns(host["cig_off"], host["cigar"])
+    pk = api.pack_fixed_columns(host, run_off, max_dict=max_dict)
+    assert len(pk["pos_ext"]) >= k and (len(pk["meta_ext"]) > 0) == (max_dict < 10)
+    packed = dict(pk, n_cigar8=n8, cigar16=c16, cigar_ext=ext)
+    exp = oracle.collapse(host, run_off, mode=mode)
+    with api.Context(device=0, n_samples=k, mode=mode) as ctx:
+        got = ctx.collapse_window(packed, run_off, pos_range=pr)
+        tpk = api.pack_fixed_columns({kk: (v.cuda() if hasattr(v, "cuda") else v) for kk, v in cols.items()}, run_off, max_dict=max_dict)
+        dcols = dict(tpk, n_cigar8=torch.as_tensor(n8).cuda(), cigar16=torch.as_tensor(c16.view(np.int16)).cuda(), cigar_ext=torch.as_tensor(ext.view(np.int32)).cuda())
+        dgot = ctx.collapse_window(dcols, run_off, pos_range=pr)
+        bad = dict(packed, pos_ext=pk["pos_ext"][:-1].copy())
+        with pytest.raises(api.TieBrushError, match="pos_d8 holds"):
+            ctx.collapse_window(bad, run_off, pos_range=pr)
+    for key in ("rep_index", "yc", "yx", "yd"):
+        assert np.array_equal(np.asarray(got[key]), exp[key]), key
+        G = dgot["n_groups"]
+        assert np.array_equal(dgot[key][:G].cpu().numpy().view(np.asarray(exp[key]).dtype), exp[key]), key

@@ -24,7 +24,9 @@ class SoaIn(C.Structure):
                 ("md_off", C.c_void_p), ("md", C.c_void_p), ("qhash", C.c_void_p), ("yc_in", C.c_void_p),
                 ("yx_in", C.c_void_p), ("yd_in", C.c_void_p), ("on_device", C.c_int32),
                 ("n_cig", C.c_int64), ("n_md", C.c_int64), ("pos_lo", C.c_int32), ("pos_hi", C.c_int32),
-                ("n_cigar8", C.c_void_p), ("cigar16", C.c_void_p), ("cigar_ext", C.c_void_p), ("n_ext", C.c_int64)]
+                ("n_cigar8", C.c_void_p), ("cigar16", C.c_void_p), ("cigar_ext", C.c_void_p), ("n_ext", C.c_int64),
+                ("pos_d8", C.c_void_p), ("pos_ext", C.c_void_p), ("n_pos_ext", C.c_int64), ("meta8", C.c_void_p), ("meta_dict", C.c_void_p),
+                ("n_meta_dict", C.c_int32), ("meta_ext", C.c_void_p), ("n_meta_ext", C.c_int64)]
 
 
 class GroupsOut(C.Structure):

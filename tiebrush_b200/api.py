@@ -70,6 +70,59 @@ def _host(a, dt):
     return np.ascontiguousarray(a, dtype=dt)
 
 
+def pack_fixed_columns(cols, run_off, max_dict=255):
+    """Host packer of the packed wire format of the fixed columns (include/tiebrush_b200.h): pos -> pos_d8 (+ pos_ext),
+    (flag, mapq, strand, nh) -> meta8 (+ meta_dict, meta_ext). numpy or torch columns in, same kind out (meta_dict always
+    numpy). What a host packer would fill directly; here built from the wide columns."""
+    pos = cols["pos"]
+    tor = _is_torch(pos)
+    n = int(pos.shape[0])
+    starts = np.asarray(run_off[:-1], np.int64)
+    starts = starts[starts < n]
+    if tor:
+        import torch
+        dev = pos.device
+        d = torch.empty(n, dtype=torch.int64, device=dev)
+        d[0:1] = 0
+        d[1:] = pos[1:].to(torch.int64) - pos[:-1].to(torch.int64)
+        is_start = torch.zeros(n, dtype=torch.bool, device=dev)
+        is_start[torch.as_tensor(starts, device=dev)] = True
+        esc = is_start | (d >= 254) | (d < 0)
+        absolute = is_start | (d < 0)
+        d8 = torch.where(absolute, 255, torch.where(esc, 254, d)).to(torch.uint8)
+        ext = torch.where(absolute, pos.to(torch.int64), d)[esc].to(torch.int32)
+        del d, is_start, esc, absolute
+        tup = (cols["flag"].to(torch.int64) & 0xffff) | ((cols["mapq"].to(torch.int64) & 0xff) << 16) | ((cols["strand"].to(torch.int64) & 0xff) << 24) | ((cols["nh"].to(torch.int64) & 0xffff) << 32)
+        samp = tup[:: max(1, n // 4_000_000)]
+        vals, cnts = torch.unique(samp, return_counts=True)
+        order = torch.argsort(cnts, descending=True)[:max_dict]
+        dict_sorted = torch.sort(vals[order]).values
+        idx = torch.searchsorted(dict_sorted, tup).clamp(max=max(len(dict_sorted) - 1, 0))
+        hit = dict_sorted[idx] == tup if len(dict_sorted) else torch.zeros(n, dtype=torch.bool, device=dev)
+        m8 = torch.where(hit, idx, 255).to(torch.uint8)
+        mext = tup[~hit]
+        return dict(pos_d8=d8, pos_ext=ext, meta8=m8, meta_ext=mext, meta_dict=dict_sorted.cpu().numpy().astype(np.uint64))
+    pos64 = np.asarray(pos).astype(np.int64)
+    d = np.zeros(n, np.int64)
+    d[1:] = pos64[1:] - pos64[:-1]
+    is_start = np.zeros(n, bool); is_start[starts] = True
+    absolute = is_start | (d < 0)
+    esc = absolute | (d >= 254)
+    d8 = np.where(absolute, 255, np.where(esc, 254, d)).astype(np.uint8)
+    ext = np.where(absolute, pos64, d)[esc].astype(np.int32)
+    tup = (np.asarray(cols["flag"]).astype(np.uint64) & 0xffff) | ((np.asarray(cols["mapq"]).astype(np.uint64) & 0xff) << np.uint64(16)) | \
+          ((np.asarray(cols["strand"]).astype(np.uint64) & 0xff) << np.uint64(24)) | ((np.asarray(cols["nh"]).astype(np.uint64) & 0xffff) << np.uint64(32))
+    vals, cnts = np.unique(tup, return_counts=True)
+    dict_sorted = np.sort(vals[np.argsort(-cnts, kind="stable")[:max_dict]])
+    if len(dict_sorted):
+        idx = np.minimum(np.searchsorted(dict_sorted, tup), len(dict_sorted) - 1)
+        hit = dict_sorted[idx] == tup
+    else:
+        idx, hit = np.zeros(n, np.int64), np.zeros(n, bool)
+    m8 = np.where(hit, idx, 255).astype(np.uint8)
+    return dict(pos_d8=d8, pos_ext=ext, meta8=m8, meta_ext=tup[~hit].astype(np.uint64), meta_dict=dict_sorted.astype(np.uint64))
+
+
 class Context:
     def __init__(self, device=0, n_samples=1, mode=0, flag_mask=0, max_nh=NO_MAX_NH, min_qual=-1, keep_bits=0, collapse_same=0):
         self.lib = _lib.load()
@@ -128,8 +181,9 @@ class Context:
     # ------------------------------------------------------------------------------------------
     def collapse_window(self, cols, run_off, tid=0, file_merged=None, pos_range=None, out=None):
         """One window of tiebrush. Returns dict(rep_index, yc, yx, yd, n_kept, n_groups)."""
-        dev = _is_torch(cols["pos"])
-        n = int(cols["pos"].shape[0])
+        first = cols["pos"] if cols.get("pos") is not None else cols["pos_d8"]
+        dev = _is_torch(first)
+        n = int(first.shape[0])
         run_off = _host(run_off, np.int64)
         k = len(run_off) - 1
         keep = []  # keep converted arrays alive
@@ -148,6 +202,11 @@ class Context:
         cig_off, cigar = col("cig_off", np.uint32), col("cigar", np.uint32)
         # compact wire format of the CIGAR columns (see include/tiebrush_b200.h); used when the wide column is absent
         n8, c16, cext = col("n_cigar8", np.uint8), col("cigar16", np.uint16), col("cigar_ext", np.uint32)
+        # packed wire format of the fixed columns (pos_d8 / meta8, see include/tiebrush_b200.h); used when the wide column is absent
+        pd8, pext = col("pos_d8", np.uint8), col("pos_ext", np.int32)
+        m8, mext = col("meta8", np.uint8), col("meta_ext", np.uint64)
+        mdict = _host(cols["meta_dict"], np.uint64) if cols.get("meta_dict") is not None else None   # always host memory
+        keep.append(mdict)
         md_off, md = col("md_off", np.uint32), col("md", np.uint8)
         qh = col("qhash", np.uint64)
         fm = _host(file_merged, np.uint8) if file_merged is not None else None
@@ -160,15 +219,19 @@ class Context:
         if pos_range is None:
             if dev:
                 raise ValueError("pos_range=(lo,hi) is required for device-resident windows")
+            if pos is None:
+                raise ValueError("pos_range=(lo,hi) is required with the packed wire format")
             pos_range = (int(pos.min()), int(pos.max()) + 1) if n else (0, 0)
         sin = _lib.SoaIn(n, k, tid, _ptr(run_off), _ptr(fm), _ptr(pos), _ptr(flag), _ptr(mapq), _ptr(strand), _ptr(nh),
                          _ptr(cig_off), _ptr(cigar), _ptr(md_off), _ptr(md), _ptr(qh), _ptr(yc_in), _ptr(yx_in), _ptr(yd_in),
-                         1 if dev else 0, n_cig, n_md, pos_range[0], pos_range[1], _ptr(n8), _ptr(c16), _ptr(cext), n_ext)
+                         1 if dev else 0, n_cig, n_md, pos_range[0], pos_range[1], _ptr(n8), _ptr(c16), _ptr(cext), n_ext,
+                         _ptr(pd8), _ptr(pext), int(pext.shape[0]) if pext is not None else 0, _ptr(m8), _ptr(mdict),
+                         int(mdict.shape[0]) if mdict is not None else 0, _ptr(mext), int(mext.shape[0]) if mext is not None else 0)
         cap = max(n, 1)
         if out is None:
             if dev:
                 import torch
-                d = cols["pos"].device
+                d = first.device
                 out = dict(rep_index=torch.empty(cap, dtype=torch.int32, device=d), yc=torch.empty(cap, dtype=torch.float32, device=d),
                            yx=torch.empty(cap, dtype=torch.int32, device=d), yd=torch.empty(cap, dtype=torch.int32, device=d))
             else:

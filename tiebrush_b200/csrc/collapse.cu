@@ -60,6 +60,30 @@ __global__ void col_check_total_kernel(const uint32_t* tot, unsigned long long w
   if ((unsigned long long)*tot != want) { status[CS_ERR] = code; status[CS_ERRIDX] = (long long)*tot; }
 }
 
+// packed wire format of the fixed columns (tb_soa_in.pos_d8 / meta8): rebuilt on the device by scans
+struct PosEscIn { const uint8_t* d; __device__ uint32_t operator()(int64_t i) const { return d[i] >= 254 ? 1u : 0u; } };
+struct PosValOut {   // delta (or absolute position) of every record; escaped ones take the next entry of pos_ext
+  const uint8_t* d; const int32_t* ext; int32_t* val;
+  __device__ void operator()(int64_t i, uint32_t exc, uint32_t) const { val[i] = d[i] >= 254 ? ext[exc] : (int32_t)d[i]; }
+};
+struct SegT { int32_t v; int32_t abs; };
+struct OpSegSum {   // running sum that restarts at absolute entries (non-commutative, associative)
+  typedef SegT T;
+  __host__ __device__ static T identity() { return SegT{0, 0}; }
+  __host__ __device__ static T combine(T a, T b) { return b.abs ? b : SegT{a.v + b.v, a.abs}; }
+};
+struct SegIn { const uint8_t* d; const int32_t* val; __device__ SegT operator()(int64_t i) const { return SegT{val[i], d[i] == 255 ? 1 : 0}; } };
+struct SegOut { int32_t* pos; __device__ void operator()(int64_t i, SegT, SegT inc) const { pos[i] = inc.v; } };
+struct MetaEscIn { const uint8_t* m; __device__ uint32_t operator()(int64_t i) const { return m[i] == 255 ? 1u : 0u; } };
+struct MetaOut {
+  const uint8_t* m; const unsigned long long* dict; const unsigned long long* ext;
+  uint16_t* flag; uint8_t* mapq; uint8_t* strand; uint16_t* nh;
+  __device__ void operator()(int64_t i, uint32_t exc, uint32_t) const {
+    const unsigned long long t = m[i] == 255 ? ext[exc] : dict[m[i]];
+    flag[i] = (uint16_t)t; mapq[i] = (uint8_t)(t >> 16); strand[i] = (uint8_t)(t >> 24); nh[i] = (uint16_t)(t >> 32);
+  }
+};
+
 struct HistIn { const uint32_t* c; __device__ uint32_t operator()(int64_t i) const { return c[i]; } };
 struct HistOut { uint32_t* p; __device__ void operator()(int64_t i, uint32_t exc, uint32_t) const { p[i] = exc; } };
 
@@ -97,11 +121,48 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
   memset(h_status, 0, sizeof(int64_t) * 16); h_status[CS_ERRIDX] = -1;
   TB_CUDA(cudaMemcpyAsync(d_status, h_status, sizeof(int64_t) * 16, cudaMemcpyHostToDevice, st));
   const int dev = hin->on_device;
-  if (tb_stage_in(ctx, ctx->in_stage[0], hin->pos, (size_t)n, dev, &in.pos)) return 1;
-  if (tb_stage_in(ctx, ctx->in_stage[1], hin->flag, (size_t)n, dev, &in.flag)) return 1;
-  if (tb_stage_in(ctx, ctx->in_stage[2], hin->mapq, (size_t)n, dev, &in.mapq)) return 1;
-  if (tb_stage_in(ctx, ctx->in_stage[3], hin->strand, (size_t)n, dev, &in.strand)) return 1;
-  if (tb_stage_in(ctx, ctx->in_stage[4], hin->nh, (size_t)n, dev, &in.nh)) return 1;
+  if (!hin->pos && !hin->pos_d8) { ctx->set_error("tb_collapse_window: neither pos nor pos_d8 given"); return 1; }
+  if (!(hin->flag && hin->mapq && hin->strand && hin->nh) && !(hin->meta8 && (hin->meta_dict || hin->n_meta_dict == 0) && (hin->meta_ext || hin->n_meta_ext == 0))) {
+    ctx->set_error("tb_collapse_window: neither flag / mapq / strand / nh nor meta8 (+ meta_dict, meta_ext) given"); return 1;
+  }
+  if (hin->pos) { if (tb_stage_in(ctx, ctx->in_stage[0], hin->pos, (size_t)n, dev, &in.pos)) return 1; }
+  else {   // positions = running sum of the per-record differences, restarted at absolute entries
+    const uint8_t* d8 = nullptr; const int32_t* pext = nullptr;
+    if (tb_stage_in(ctx, ctx->in_stage[16], hin->pos_d8, (size_t)n, dev, &d8)) return 1;
+    if (hin->n_pos_ext > 0) { if (tb_stage_in(ctx, ctx->in_stage[17], hin->pos_ext, (size_t)hin->n_pos_ext, dev, &pext)) return 1; }
+    TB_CUDA(ctx->in_stage[0].ensure(sizeof(int32_t) * (size_t)n + 16));
+    TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks(n) + 8) * sizeof(uint64_t)));
+    int32_t* dpos = ctx->in_stage[0].as<int32_t>();
+    TB_CUDA((tb_device_scan<OpSumU32>(ctx, PosEscIn{d8}, n, B[XB_AGG].as<uint32_t>(), PosValOut{d8, pext, dpos})));
+    col_check_total_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(n), (unsigned long long)hin->n_pos_ext, d_status, 6);
+    TB_CUDA((tb_device_scan<OpSegSum>(ctx, SegIn{d8, dpos}, n, B[XB_AGG].as<SegT>(), SegOut{dpos})));
+    ctx->launches++;
+    in.pos = dpos;
+  }
+  if (hin->flag && hin->mapq && hin->strand && hin->nh) {
+    if (tb_stage_in(ctx, ctx->in_stage[1], hin->flag, (size_t)n, dev, &in.flag)) return 1;
+    if (tb_stage_in(ctx, ctx->in_stage[2], hin->mapq, (size_t)n, dev, &in.mapq)) return 1;
+    if (tb_stage_in(ctx, ctx->in_stage[3], hin->strand, (size_t)n, dev, &in.strand)) return 1;
+    if (tb_stage_in(ctx, ctx->in_stage[4], hin->nh, (size_t)n, dev, &in.nh)) return 1;
+  } else {   // dictionary-coded (flag, mapq, strand, nh)
+    if (hin->n_meta_dict < 0 || hin->n_meta_dict > 255) { ctx->set_error("tb_collapse_window: n_meta_dict %d out of range (0..255)", hin->n_meta_dict); return 1; }
+    const uint8_t* m8 = nullptr; const uint64_t* mext = nullptr;
+    if (tb_stage_in(ctx, ctx->in_stage[18], hin->meta8, (size_t)n, dev, &m8)) return 1;
+    if (hin->n_meta_ext > 0) { if (tb_stage_in(ctx, ctx->in_stage[19], hin->meta_ext, (size_t)hin->n_meta_ext, dev, &mext)) return 1; }
+    TB_CUDA(ctx->in_stage[1].ensure(sizeof(uint16_t) * (size_t)n + 16)); TB_CUDA(ctx->in_stage[2].ensure((size_t)n + 16));
+    TB_CUDA(ctx->in_stage[3].ensure((size_t)n + 16)); TB_CUDA(ctx->in_stage[4].ensure(sizeof(uint16_t) * (size_t)n + 16));
+    TB_CUDA(B[XB_META_DICT].ensure(sizeof(uint64_t) * 256));
+    uint64_t dict_h[256]; memset(dict_h, 0, sizeof(dict_h));
+    if (hin->n_meta_dict > 0) memcpy(dict_h, hin->meta_dict, sizeof(uint64_t) * (size_t)hin->n_meta_dict);
+    TB_CUDA(cudaMemcpyAsync(B[XB_META_DICT].p, dict_h, sizeof(dict_h), cudaMemcpyHostToDevice, st));
+    TB_CUDA(B[XB_AGG].ensure((size_t)(tb_scan_blocks(n) + 8) * sizeof(uint64_t)));
+    TB_CUDA((tb_device_scan<OpSumU32>(ctx, MetaEscIn{m8}, n, B[XB_AGG].as<uint32_t>(),
+                                      MetaOut{m8, B[XB_META_DICT].as<unsigned long long>(), (const unsigned long long*)mext, ctx->in_stage[1].as<uint16_t>(),
+                                              ctx->in_stage[2].as<uint8_t>(), ctx->in_stage[3].as<uint8_t>(), ctx->in_stage[4].as<uint16_t>()})));
+    col_check_total_kernel<<<1, 1, 0, st>>>(B[XB_AGG].as<uint32_t>() + tb_scan_blocks(n), (unsigned long long)hin->n_meta_ext, d_status, 7);
+    ctx->launches++;
+    in.flag = ctx->in_stage[1].as<uint16_t>(); in.mapq = ctx->in_stage[2].as<uint8_t>(); in.strand = ctx->in_stage[3].as<uint8_t>(); in.nh = ctx->in_stage[4].as<uint16_t>();
+  }
   if (!hin->cig_off && !hin->n_cigar8) { ctx->set_error("tb_collapse_window: neither cig_off nor n_cigar8 given"); return 1; }
   if (!hin->cigar && !(hin->cigar16 && (hin->cigar_ext || hin->n_ext == 0))) { ctx->set_error("tb_collapse_window: neither cigar nor cigar16 (+cigar_ext) given"); return 1; }
   if (hin->cig_off) { if (tb_stage_in(ctx, ctx->in_stage[5], hin->cig_off, (size_t)n + 1, dev, &in.cig_off)) return 1; }
@@ -171,6 +232,8 @@ int tb_collapse_impl(tb_ctx* ctx, const tb_soa_in* hin, tb_groups_out* out) {
   if (h_status[CS_ERR] == ERR_POS_RANGE) { ctx->set_error("tb_collapse_window: record %lld has pos outside [pos_lo,pos_hi)", h_status[CS_ERRIDX]); return 1; }
   if (h_status[CS_ERR] == 4) { ctx->set_error("tb_collapse_window: compact wire format: n_cigar8 sums to %lld ops but n_cig = %lld", h_status[CS_ERRIDX], (long long)hin->n_cig); return 1; }
   if (h_status[CS_ERR] == 5) { ctx->set_error("tb_collapse_window: compact wire format: cigar16 holds %lld escaped lengths but n_ext = %lld", h_status[CS_ERRIDX], (long long)hin->n_ext); return 1; }
+  if (h_status[CS_ERR] == 6) { ctx->set_error("tb_collapse_window: packed wire format: pos_d8 holds %lld escaped entries but n_pos_ext = %lld", h_status[CS_ERRIDX], (long long)hin->n_pos_ext); return 1; }
+  if (h_status[CS_ERR] == 7) { ctx->set_error("tb_collapse_window: packed wire format: meta8 holds %lld escaped entries but n_meta_ext = %lld", h_status[CS_ERRIDX], (long long)hin->n_meta_ext); return 1; }
   if (h_status[CS_ERR] == 3) { ctx->set_error("tb_collapse_window: unmapped record %lld kept by -M: the reference aborts here (GVec invalid index)", h_status[CS_ERRIDX]); return 1; }
 
   ColGeom g; g.n = n; g.k = k; g.W = W; g.S = S; g.P = d_hist; g.d_runoff = B[XB_RUNOFF].as<long long>(); g.d_merged = d_merged; g.d_status = d_status; g.n_cig = hin->n_cig;
