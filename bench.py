@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--wire", default="packed", choices=["packed", "compact", "wide"],
                     help="host column format of the e2e leg: packed = pos_d8 + meta8 (+ dictionary / escapes) and the compact CIGAR columns, "
                          "compact = wide fixed columns + n_cigar8 + cigar16 (+cigar_ext), wide = cig_off + cigar (u32)")
+    ap.add_argument("--e2e-windows", type=int, default=int(os.environ.get("TB_BENCH_E2E_WINDOWS", 8)),
+                    help="end-to-end leg: the window is handed over as this many coordinate sub-windows cut at coverage gaps (as the host tool "
+                         "cuts them), two in flight on two contexts so that the copies of one overlap the kernels of the other (1 = one call)")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("TB_BENCH_CPU_SAMPLE", 20_000_000)),
                     help="records of the cohort fed to the CPU baseline (bounded sample)")
     ap.add_argument("--cli-reads", type=int, default=int(os.environ.get("TB_BENCH_CLI_READS", 50_000)),
@@ -293,6 +296,97 @@ def write_cov_sam(cols, path, n_contigs):
             if len(buf) >= 100000:
                 fh.write("".join(buf)); buf = []
         fh.write("".join(buf))
+
+
+def gap_cut_subwindows(cols, run_off, pr, S, dev):
+    """The file-major window as S coordinate sub-windows cut where NO read of any sample covers the cut coordinate (the rule of
+    the host tool, tiebrush_gpu_main.cpp: groups never span a start position and the YD segment lists are empty after a gap,
+    so the sub-windows are independent and their outputs concatenate to the window's). Returns [(cols_s, run_off_s, (lo, hi))]."""
+    import torch
+    k = len(run_off) - 1
+    lo = int(pr[0])
+    span = int(pr[1]) - lo + 400000
+    cover = torch.zeros(span + 2, dtype=torch.int32, device=dev)
+    offs = []
+    for f in range(k):
+        a, b = int(run_off[f]), int(run_off[f + 1])
+        o = cols["cig_off"][a:b + 1].to(torch.int64) & 0xFFFFFFFF
+        offs.append(o)
+        c0, c1 = int(o[0]), int(o[-1])
+        cig = cols["cigar"][c0:c1].to(torch.int64) & 0xFFFFFFFF
+        op = cig & 0xF
+        ref = torch.where((op == 0) | (op == 2) | (op == 3) | (op == 7) | (op == 8), cig >> 4, torch.zeros_like(cig))
+        cs = torch.zeros(c1 - c0 + 1, dtype=torch.int64, device=dev)
+        cs[1:] = torch.cumsum(ref, 0)
+        rl = cs[o[1:] - c0] - cs[o[:-1] - c0]
+        p = cols["pos"][a:b].to(torch.int64) - lo
+        ones = torch.ones(b - a, dtype=torch.int32, device=dev)
+        cover.index_add_(0, p, ones)
+        cover.index_add_(0, (p + rl).clamp(max=span), -ones)
+        del cig, op, ref, cs, rl, p, ones
+    depth = torch.cumsum(cover, 0, dtype=torch.int32)
+    del cover
+    pos0 = cols["pos"][int(run_off[0]):int(run_off[1])]
+    cuts = []
+    for s_ in range(1, S):
+        x = int(pos0[len(pos0) * s_ // S].item()) - lo
+        z = (depth[x:x + 20_000_000] == 0).nonzero()
+        if len(z) == 0:
+            continue
+        c = lo + x + int(z[0].item())
+        if (not cuts or c > cuts[-1]) and c < int(pr[1]):
+            cuts.append(c)
+    del depth
+    bounds = [lo] + cuts + [int(pr[1])]
+    subs = []
+    for s_ in range(len(bounds) - 1):
+        b0 = torch.tensor([bounds[s_], bounds[s_ + 1]], device=dev, dtype=cols["pos"].dtype)
+        parts = {kk: [] for kk in ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar")}
+        ro, base = [0], 0
+        for f in range(k):
+            a, b = int(run_off[f]), int(run_off[f + 1])
+            i0, i1 = (int(v) for v in torch.searchsorted(cols["pos"][a:b], b0))
+            for kk in ("pos", "flag", "mapq", "strand", "nh"):
+                parts[kk].append(cols[kk][a + i0:a + i1])
+            o = offs[f]
+            c0, c1 = int(o[i0]), int(o[i1])
+            parts["cig_off"].append(o[i0:i1] - c0 + base)
+            parts["cigar"].append(cols["cigar"][c0:c1])
+            base += c1 - c0
+            ro.append(ro[-1] + (i1 - i0))
+        sub = {kk: torch.cat(v) for kk, v in parts.items() if kk != "cig_off"}
+        sub["cig_off"] = torch.cat(parts["cig_off"] + [torch.tensor([base], device=dev, dtype=torch.int64)]).to(torch.int32)
+        sub["n_cig"] = base
+        subs.append((sub, np.asarray(ro, np.int64), (bounds[s_], bounds[s_ + 1])))
+    return subs
+
+
+def pin_wire(api, sub, run_off, wire):
+    """Pinned host arrays of one (sub-)window in the wire format; returns (host dict, bytes)."""
+    import torch
+    wc = dict(sub)
+    names = ("pos", "flag", "mapq", "strand", "nh", "cig_off", "cigar")
+    if wire in ("compact", "packed"):
+        wc["n_cigar8"], wc["cigar16"], wc["cigar_ext"] = api.compact_cigar_columns(sub["cig_off"], sub["cigar"])
+        names = ("pos", "flag", "mapq", "strand", "nh", "n_cigar8", "cigar16", "cigar_ext")
+    meta_dict = None
+    if wire == "packed":
+        pk = api.pack_fixed_columns(sub, run_off)
+        meta_dict = pk.pop("meta_dict")
+        wc.update(pk)
+        names = ("pos_d8", "pos_ext", "meta8", "meta_ext", "n_cigar8", "cigar16", "cigar_ext")
+    host, nbytes = {}, 0
+    for name in names:
+        t = wc[name]
+        ht = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        ht.copy_(t)
+        host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32, "flag": np.uint16, "nh": np.uint16, "cigar16": np.uint16, "cigar_ext": np.uint32, "meta_ext": np.uint64}.get(name, ht.numpy().dtype))
+        nbytes += ht.numel() * ht.element_size()
+    host["n_cig"] = int(sub["n_cig"])
+    if meta_dict is not None:
+        host["meta_dict"] = meta_dict
+        nbytes += meta_dict.nbytes
+    return host, nbytes
 
 
 def run_tiecov_leg(args, rank, world, local, dev, stream, peak, barrier, dist):
@@ -581,6 +675,18 @@ def main():
             cap = max(G + 1024, 1)
             hout_t = dict(rep_index=torch.empty(cap, dtype=torch.int32, pin_memory=True), yc=torch.empty(cap, dtype=torch.float32, pin_memory=True),
                           yx=torch.empty(cap, dtype=torch.int32, pin_memory=True), yd=torch.empty(cap, dtype=torch.int32, pin_memory=True))
+            # the same window as coordinate sub-windows cut at coverage gaps (what the host tool hands over), packed and pinned
+            subs_host = []
+            if args.e2e_windows > 1 and args.mode != 1:
+                for sub, ro_s, pr_s in gap_cut_subwindows(cols, run_off, pr, args.e2e_windows, dev):
+                    hs, nb = pin_wire(api, sub, ro_s, args.wire)
+                    ns = int(ro_s[-1])
+                    capg = int(0.5 * ns) + (1 << 20)
+                    ho = dict(rep_index=torch.empty(capg, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32), yc=torch.empty(capg, dtype=torch.float32, pin_memory=True).numpy(),
+                              yx=torch.empty(capg, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32), yd=torch.empty(capg, dtype=torch.int32, pin_memory=True).numpy())
+                    subs_host.append((hs, ro_s, pr_s, ho, nb, ns))
+                    del sub
+                torch.cuda.empty_cache()
         except (RuntimeError, MemoryError) as ex:
             ok = 0
             e2e_err = str(ex)[:200]
@@ -618,8 +724,60 @@ def main():
                 t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 e2e_ms = float(t.item())
-            line["e2e"] = {"value": world * n / (e2e_ms / 1000.0), "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(16 * r2["n_groups"] + 128),
+            single = {"ms_per_step": e2e_ms, "value": world * n / (e2e_ms / 1000.0), "h2d_bytes_per_step": int(h2d), "what": "ONE tb_collapse_window call on the whole 1e9-alignment window: every copy before the first kernel"}
+            g_tot = r2["n_groups"]
+            n_sw = 1
+            if subs_host:
+                # ---- pipelined hand-over: sub-windows alternate between two contexts (two host threads, two streams): the
+                # host->device copies of one sub-window overlap the kernels of the other ----
+                import threading
+                host = None
+                stream2 = torch.cuda.Stream(device=dev)
+                ctx2 = api.Context(device=local, n_samples=k, mode=args.mode, flag_mask=args.flag_mask, max_nh=args.max_nh, min_qual=args.min_qual)
+                ctx2.set_stream(stream2.cuda_stream)
+                pair = ((ctx, stream), (ctx2, stream2))
+                n_sw = len(subs_host)
+                res_sw = [None] * n_sw
+
+                def work(ci, e_end):
+                    c, st_ = pair[ci]
+                    for i in range(ci, n_sw, 2):
+                        hs, ro_s, pr_s, ho, _, _ = subs_host[i]
+                        res_sw[i] = c.collapse_window(hs, ro_s, pos_range=pr_s, out=ho)
+                    if e_end is not None:
+                        e_end.record(st_)
+
+                def one_step(e_ends):
+                    th = [threading.Thread(target=work, args=(ci, e_ends[ci] if e_ends else None)) for ci in range(2)]
+                    for t_ in th: t_.start()
+                    for t_ in th: t_.join()
+
+                one_step(None)   # warm both contexts' staging buffers
+                barrier()
+                t0 = time.perf_counter()
+                ms_steps = []
+                for _ in range(es):
+                    ea, eb, e0 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    torch.cuda.synchronize()
+                    e0.record(stream)
+                    stream2.wait_event(e0)
+                    one_step((ea, eb))
+                    torch.cuda.synchronize()
+                    ms_steps.append(max(e0.elapsed_time(ea), e0.elapsed_time(eb)))
+                barrier()
+                e2e_ms = float(np.mean(ms_steps))
+                if world > 1:
+                    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    e2e_ms = float(t.item())
+                h2d = sum(x[4] for x in subs_host)
+                g_tot = sum(r_["n_groups"] for r_ in res_sw)
+                assert g_tot == r2["n_groups"], f"sub-windows gave {g_tot} groups, the one window {r2['n_groups']}"
+                ctx2.close()
+            line["e2e"] = {"value": world * n / (e2e_ms / 1000.0), "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(16 * g_tot + 128 * n_sw),
                            "ms_per_step": e2e_ms, "steps": es, "wall_ms_per_step": 1000.0 * (time.perf_counter() - t0) / es,
+                           "windows": n_sw, "hand_over": ("%d coordinate sub-windows cut at coverage gaps, two in flight on two contexts / streams (copies of one overlap the kernels of the other)" % n_sw) if n_sw > 1 else "one call",
+                           "single_call": single,
                            "wire_format": args.wire + {"packed": " (pos_d8 + meta8 with dictionary / escapes, n_cigar8 + cigar16 + cigar_ext; the device rebuilds every wide column inside the timed region)",
                                                        "compact": " (n_cigar8 + cigar16 + cigar_ext; the device rebuilds cig_off / cigar inside the timed region)", "wide": " (cig_off + cigar u32)"}[args.wire]}
     sampler.stop_flag.set(); sampler.join(timeout=3)
