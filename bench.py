@@ -412,14 +412,18 @@ def run_tiecov_leg(args, rank, world, local, dev, stream, peak, barrier, dist):
     capr, capj = int(1.0 * n_local) + (1 << 22), int(0.05 * n_local) + (1 << 22)
     out_local = api.cov_out_buffers(capr, capj, device=dev)
     if world > 1 and rank == 0:
-        all_out = api.cov_out_buffers(int(1.0 * R) + (1 << 22), int(0.05 * R) + (1 << 22), device=dev)
+        all_out = api.cov_out_buffers(world * capr, world * capj, device=dev)
     else:
         all_out = out_local if rank == 0 else None
 
+    cap_all_r, cap_all_j = world * capr, world * capj   # rank 0: one region per rank (the same capacities on every rank)
+
     def step():
-        loc = cctx.shard_coverage(segs, args.cov_window, out_local)
+        # this rank's windows with the ordered gather folded in: after every window the new rows travel to rank 0's region
+        # of this rank on a second stream while the next window computes
+        loc = cctx.shard_coverage_gather(segs, args.cov_window, out_local, all_out, cap_all_r, cap_all_j, world)
         ms = [cctx.last_kernel_ms(i) for i in (6, 1, 7, 9)]
-        g = cctx.shard_gather(loc, all_out, world)
+        g = {"gather_bytes": loc["stats"]["gather_bytes"], "rounds": loc["stats"]["gather_rounds"]}
         return loc, g, ms
 
     for _ in range(max(1, args.warmup)):
@@ -443,6 +447,8 @@ def run_tiecov_leg(args, rank, world, local, dev, stream, peak, barrier, dist):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     cov_ms = float(tmax[0].item())
     mb_tot, runs_tot, juncs_tot = float(tot[0].item()), int(tot[1].item()), int(tot[2].item())
+    if rank == 0:
+        assert loc["total_runs"] == runs_tot and loc["total_juncs"] == juncs_tot, "gathered rows != rows produced"
     a_cov = n_local * (19 + 4 * ncig_local / max(n_local, 1)) + 16 * loc["n_runs"] + 16 * loc["n_juncs"]   # this rank's algorithmic bytes
     acc_ms = max(ms[1], 1e-6)
     line = {"metric": "coverage_bases_per_sec", "value": mb_tot / (cov_ms / 1000.0), "unit": "bases/s", "records_per_sec": R / (cov_ms / 1000.0),
@@ -452,7 +458,8 @@ def run_tiecov_leg(args, rank, world, local, dev, stream, peak, barrier, dist):
                        "l2": "inputs (27 B/record, GBs per GPU) exceed the 126 MB L2; no flush needed"},
             "runs": runs_tot, "juncs": juncs_tot, "gpu_launches": int(launches),
             "exchange": {"halo_ms_max": float(tmax[1].item()), "lead_records_moved": int(tot[4].item()), "halo_bytes": int(tot[3].item()),
-                         "gather_bytes": int(tot[5].item()), "collectives": "ncclAllGather x2 (open-bundle state, lead sizes) + grouped ncclSend/ncclRecv (lead records) + ncclAllGather (row counts) + grouped ncclSend/ncclRecv (ordered gather on rank 0)" if world > 1 else "none (1 GPU)"},
+                         "gather_bytes": int(tot[5].item()), "gather_rounds": int(g["rounds"]),
+                         "collectives": "ncclAllGather x2 (open-bundle state, lead sizes) + grouped ncclSend/ncclRecv (lead records); per window, on a second stream: ncclAllGather (new row counts) + grouped ncclSend/ncclRecv (the window's rows into this rank's region on rank 0), overlapped with the next window" if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "kernel": "cov_accumulate_kernel", "achieved": a_cov / (acc_ms / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": a_cov / (acc_ms / 1000.0) / 1e9 / peak, "kernel_ms": float(acc_ms), "algorithmic_bytes": float(a_cov),
                          "traffic": (lambda t: None if t is None else t * n_local)(traffic_per_record("cov_accumulate_kernel")),

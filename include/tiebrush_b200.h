@@ -225,8 +225,16 @@ int tc_shard_coverage(tb_ctx*, const tc_soa_in* segs, int n_segs, int64_t window
  * the global JUNC%08d counter (tiecov.cpp:92-94). */
 int tc_shard_gather(tb_ctx*, const tc_runs_out* runs, const tc_juncs_out* juncs, tc_runs_out* all_runs, tc_juncs_out* all_juncs,
                     int64_t* junc_base);
+/* tc_shard_coverage with the ordered gather OVERLAPPED with the windows: rank 0's arrays are cut into `world` regions of
+ * equal capacity (all_runs->capacity / world rows each), the rows of rank r arrive in region r while rank r is still
+ * computing its later windows (one ncclAllGather of the new row counts and one grouped ncclSend / ncclRecv per window, on a
+ * second stream). Every rank passes all_runs / all_juncs with the SAME capacities (their arrays may be NULL except on rank
+ * 0). region (host, [4 * world], every rank) = for rank r: offset and count of its runs, offset and count of its junction
+ * rows; the ordered result is region 0, region 1, ... (not contiguous). Collective. */
+int tc_shard_coverage_gather(tb_ctx*, const tc_soa_in* segs, int n_segs, int64_t window, tc_runs_out* runs, tc_juncs_out* juncs,
+                             tc_runs_out* all_runs, tc_juncs_out* all_juncs, int64_t* region);
 /* Statistics of the last tc_shard_coverage / tc_shard_gather call: 0 lead records received, 1 lead records sent, 2 ranks
- * received from, 3 bytes sent in the halo exchange, 4 records of the seam window, 5 bytes this rank moved in the gather. */
+ * received from, 3 bytes sent in the halo exchange, 4 records of the seam window, 5 bytes this rank moved in the gather, 6 gather rounds (tc_shard_coverage_gather). */
 int64_t tc_shard_stat(tb_ctx*, int which);
 /* Windows the last tc_coverage_stream / tc_shard_coverage call processed. */
 int64_t tc_stream_windows(tb_ctx*);

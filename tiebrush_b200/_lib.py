@@ -14,7 +14,7 @@ SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_set_stream", "tb_get_
            "tb_collapse_window", "tc_coverage_window", "tc_sample_window", "tb_launch_count", "tb_set_profiling",
            "tb_last_kernel_ms", "tb_version", "tb_last_path", "tb_last_yd_path", "tb_last_heavy_slots", "tb_last_tile_gen", "tb_last_tile_stat",
            "tc_coverage_stream", "tb_comm_unique_id", "tb_comm_init", "tb_comm_destroy", "tb_comm_rank", "tb_comm_world",
-           "tc_shard_coverage", "tc_shard_gather", "tc_shard_stat", "tc_stream_windows", "tc_last_exact"]
+           "tc_shard_coverage", "tc_shard_coverage_gather", "tc_shard_gather", "tc_shard_stat", "tc_stream_windows", "tc_last_exact"]
 
 
 class SoaIn(C.Structure):
@@ -97,6 +97,7 @@ def load():
     lib.tb_comm_rank.argtypes = [C.c_void_p]
     lib.tb_comm_world.argtypes = [C.c_void_p]
     lib.tc_shard_coverage.argtypes = [C.c_void_p, C.POINTER(CovIn), C.c_int, C.c_int64, C.POINTER(RunsOut), C.POINTER(JuncsOut)]
+    lib.tc_shard_coverage_gather.argtypes = [C.c_void_p, C.POINTER(CovIn), C.c_int, C.c_int64, C.POINTER(RunsOut), C.POINTER(JuncsOut), C.POINTER(RunsOut), C.POINTER(JuncsOut), C.POINTER(C.c_int64)]
     lib.tc_shard_gather.argtypes = [C.c_void_p, C.POINTER(RunsOut), C.POINTER(JuncsOut), C.POINTER(RunsOut), C.POINTER(JuncsOut), C.POINTER(C.c_int64)]
     lib.tc_shard_stat.argtypes = [C.c_void_p, C.c_int]
     lib.tc_shard_stat.restype = C.c_int64

@@ -423,7 +423,47 @@ def _shard_gather(self, local, all_out, world):
     return res
 
 
+def _shard_coverage_gather(self, segs, window, out, all_out, cap_runs_all, cap_juncs_all, world):
+    """tc_shard_coverage_gather: this rank's windows with the ordered gather on rank 0 overlapped (one round per window on a
+    second stream). `all_out` = rank 0's arrays (capacity cap_*_all, cut into `world` regions), None elsewhere; every rank
+    passes the same capacities. Returns the local rows, the regions [(runs offset, runs, juncs offset, juncs)] and, on rank 0,
+    the gathered rows per region."""
+    keep = []
+    arr = (_lib.CovIn * len(segs))(*[_cov_in(s, keep) for s in segs])
+    runs, juncs = _out_structs(out)
+    if all_out is not None:
+        ar, aj = _out_structs(all_out)
+        ar.capacity, aj.capacity = int(cap_runs_all), int(cap_juncs_all)
+    else:
+        ar = _lib.RunsOut(int(cap_runs_all), 0, None, None, None, None, 1)
+        aj = _lib.JuncsOut(int(cap_juncs_all), 0, None, None, None, None, None, 1)
+    region = (C.c_int64 * (4 * world))()
+    rc = self.lib.tc_shard_coverage_gather(self.h, arr, len(segs), int(window), C.byref(runs), C.byref(juncs), C.byref(ar), C.byref(aj), region)
+    if rc == 2:
+        raise ValueError(self._err())
+    if rc != 0:
+        raise TieBrushError(self._err())
+    res = _rows(out, int(runs.n_runs), int(juncs.n_juncs))
+    res["windows"] = int(self.lib.tc_stream_windows(self.h))
+    res["stats"] = dict(zip(("lead_received", "lead_sent", "ranks_received_from", "halo_bytes_sent", "seam_records", "gather_bytes", "gather_rounds"),
+                            (int(self.lib.tc_shard_stat(self.h, i)) for i in range(7))))
+    res["regions"] = [tuple(int(region[4 * r + q]) for q in range(4)) for r in range(world)]
+    res["total_runs"] = sum(x[1] for x in res["regions"]); res["total_juncs"] = sum(x[3] for x in res["regions"])
+    if all_out is not None:
+        cat = lambda keys, oi, ci: tuple((torch_cat if _is_torch(all_out[keys[0]]) else np.concatenate)([all_out[kk][x[oi]:x[oi] + x[ci]] for x in res["regions"]]) for kk in keys)
+        import functools
+        try:
+            import torch
+            torch_cat = torch.cat
+        except Exception:   # pragma: no cover
+            torch_cat = None
+        res["gathered_runs"] = lambda: cat(("r_tid", "r_start", "r_end", "r_val"), 0, 1)
+        res["gathered_juncs"] = lambda: cat(("j_tid", "j_start", "j_end", "j_strand", "j_val"), 2, 3)
+    return res
+
+
 Context.coverage_stream = _coverage_stream
+Context.shard_coverage_gather = _shard_coverage_gather
 Context.comm_init = _comm_init
 Context.shard_coverage = _shard_coverage
 Context.shard_gather = _shard_gather

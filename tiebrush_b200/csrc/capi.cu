@@ -67,6 +67,7 @@ void tb_destroy(tb_ctx* ctx) {
   for (auto& b : ctx->pinned) b.release();
   for (auto& b : ctx->shard_buf) b.release();
   tb_comm_destroy(ctx);
+  if (ctx->gather_stream) cudaStreamDestroy(ctx->gather_stream);
   for (int i = 0; i < 16; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;

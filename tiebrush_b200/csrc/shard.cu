@@ -20,6 +20,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <algorithm>
+#include <functional>
 #include "tb_common.cuh"
 
 int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* in, tc_runs_out* runs, tc_juncs_out* juncs, const int32_t* yx, CovExt* ext);
@@ -61,7 +62,7 @@ NcclApi g_nccl;
 
 // workspace slots of this file in ctx->shard_buf
 enum { SB_GATHER = 0, SB_SEND, SB_TAIL_TID, SB_TAIL_POS, SB_TAIL_YC, SB_TAIL_STRAND, SB_TAIL_OFF, SB_TAIL_CIG, SB_SEAM_TID, SB_SEAM_POS, SB_SEAM_YC,
-       SB_SEAM_STRAND, SB_SEAM_OFF, SB_SEAM_CIG, SB_COUNT_ };
+       SB_SEAM_STRAND, SB_SEAM_OFF, SB_SEAM_CIG, SB_GROUND, SB_COUNT_ };
 static_assert(SB_COUNT_ <= 16, "raise tb_ctx::shard_buf");
 
 // ---- open-bundle state of a slice: maximum (tid << 32 | end) key over its records. Only the records of the LAST reference
@@ -152,12 +153,112 @@ static tc_soa_in sub_window(const tc_soa_in& in, int64_t w0, int64_t len, int64_
   return s;
 }
 
+// ---- ordered gather overlapped with the windows (tc_shard_coverage_gather) ------------------------------------------------
+// Rank 0's output arrays are cut into `world` regions of equal capacity; the rows of rank r arrive in region r in the order
+// they are produced. After every window a rank takes part in one ROUND on a second stream: ncclAllGather of {new runs, new
+// junction rows, done} (the only host wait of the round: the previous round's transfers have long finished), then one
+// grouped ncclSend / ncclRecv of the new rows, which travels while the next window computes. Ranks that run out of windows
+// keep answering rounds with zero rows until every rank is done.
+struct GatherState {
+  tc_runs_out* all_runs = nullptr; tc_juncs_out* all_juncs = nullptr;   // rank 0 only
+  int64_t cap_r = 0, cap_j = 0;            // region capacity per rank
+  int64_t sent_r = 0, sent_j = 0;          // rows of this rank already handed over
+  std::vector<int64_t> got_r, got_j;       // rows per rank so far (every rank tracks them: they come with the allgather)
+  bool all_done = false;
+  int rounds = 0;
+  int64_t bytes = 0;
+};
+
+static int gather_round(tb_ctx* ctx, GatherState& gs, const tc_runs_out* runs, const tc_juncs_out* juncs, bool done) {
+  const int W = ctx->comm ? ctx->world : 1, R = ctx->comm ? ctx->rank : 0;
+  cudaStream_t gst = ctx->gather_stream;
+  const int64_t new_r = (runs ? runs->n_runs : 0) - gs.sent_r, new_j = (juncs ? juncs->n_juncs : 0) - gs.sent_j;
+  std::vector<unsigned long long> h(4 * (size_t)W, 0ULL);
+  if (W > 1) {
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    DevBuf* SB = ctx->shard_buf;
+    TB_CUDA(SB[SB_GROUND].ensure(sizeof(unsigned long long) * 4 * (size_t)(W + 1)));
+    TB_CUDA(ctx->pinned[1].ensure(sizeof(unsigned long long) * 8 * (size_t)(W + 1)));
+    unsigned long long* d_mine = SB[SB_GROUND].as<unsigned long long>();
+    unsigned long long* d_all = d_mine + 4;
+    unsigned long long* h_all = ctx->pinned[1].as<unsigned long long>();
+    h_all[0] = (unsigned long long)new_r; h_all[1] = (unsigned long long)new_j; h_all[2] = done ? 1ULL : 0ULL; h_all[3] = 0;
+    TB_CUDA(cudaMemcpyAsync(d_mine, h_all, sizeof(unsigned long long) * 4, cudaMemcpyHostToDevice, gst));
+    TB_NCCL(g_nccl.AllGather(d_mine, d_all, 4, ncclUint64, comm, gst));
+    TB_CUDA(cudaMemcpyAsync(h_all + 4, d_all, sizeof(unsigned long long) * 4 * W, cudaMemcpyDeviceToHost, gst));
+    TB_CUDA(cudaStreamSynchronize(gst));
+    for (int i = 0; i < 4 * W; ++i) h[i] = h_all[4 + i];
+  } else {
+    h[0] = (unsigned long long)new_r; h[1] = (unsigned long long)new_j; h[2] = done ? 1ULL : 0ULL;
+  }
+  bool all = true;
+  for (int r = 0; r < W; ++r) {
+    if (!h[4 * r + 2]) all = false;
+    if (gs.got_r[r] + (int64_t)h[4 * r] > gs.cap_r || gs.got_j[r] + (int64_t)h[4 * r + 1] > gs.cap_j) {
+      ctx->set_error("tc_shard_coverage_gather: region of rank %d too small (%lld runs / %lld junction rows per rank)", r, (long long)gs.cap_r, (long long)gs.cap_j);
+      return 1;
+    }
+  }
+  auto d2d = [&](void* dst, const void* src, size_t bytes) { return (bytes && dst != src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, gst) : cudaSuccess; };
+  if (R == 0 && gs.all_runs && runs && new_r > 0) {
+    const int64_t o = gs.got_r[0];
+    TB_CUDA(d2d(gs.all_runs->tid + o, runs->tid + gs.sent_r, sizeof(int32_t) * new_r)); TB_CUDA(d2d(gs.all_runs->start0 + o, runs->start0 + gs.sent_r, sizeof(int32_t) * new_r));
+    TB_CUDA(d2d(gs.all_runs->end0 + o, runs->end0 + gs.sent_r, sizeof(int32_t) * new_r)); TB_CUDA(d2d(gs.all_runs->value + o, runs->value + gs.sent_r, sizeof(double) * new_r));
+  }
+  if (R == 0 && gs.all_juncs && juncs && new_j > 0) {
+    const int64_t o = gs.got_j[0];
+    TB_CUDA(d2d(gs.all_juncs->tid + o, juncs->tid + gs.sent_j, sizeof(int32_t) * new_j)); TB_CUDA(d2d(gs.all_juncs->start + o, juncs->start + gs.sent_j, sizeof(int32_t) * new_j));
+    TB_CUDA(d2d(gs.all_juncs->end + o, juncs->end + gs.sent_j, sizeof(int32_t) * new_j)); TB_CUDA(d2d(gs.all_juncs->strand + o, juncs->strand + gs.sent_j, (size_t)new_j));
+    TB_CUDA(d2d(gs.all_juncs->value + o, juncs->value + gs.sent_j, sizeof(double) * new_j));
+  }
+  if (W > 1) {
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    TB_NCCL(g_nccl.GroupStart());
+    if (R == 0) {
+      for (int r = 1; r < W; ++r) {
+        const int64_t cr = (int64_t)h[4 * r], cj = (int64_t)h[4 * r + 1];
+        const int64_t ro = r * gs.cap_r + gs.got_r[r], jo = r * gs.cap_j + gs.got_j[r];
+        if (gs.all_runs && cr > 0) {
+          TB_NCCL(g_nccl.Recv(gs.all_runs->tid + ro, (size_t)cr * 4, ncclUint8, r, comm, gst)); TB_NCCL(g_nccl.Recv(gs.all_runs->start0 + ro, (size_t)cr * 4, ncclUint8, r, comm, gst));
+          TB_NCCL(g_nccl.Recv(gs.all_runs->end0 + ro, (size_t)cr * 4, ncclUint8, r, comm, gst)); TB_NCCL(g_nccl.Recv(gs.all_runs->value + ro, (size_t)cr * 8, ncclUint8, r, comm, gst));
+          gs.bytes += cr * 20;
+        }
+        if (gs.all_juncs && cj > 0) {
+          TB_NCCL(g_nccl.Recv(gs.all_juncs->tid + jo, (size_t)cj * 4, ncclUint8, r, comm, gst)); TB_NCCL(g_nccl.Recv(gs.all_juncs->start + jo, (size_t)cj * 4, ncclUint8, r, comm, gst));
+          TB_NCCL(g_nccl.Recv(gs.all_juncs->end + jo, (size_t)cj * 4, ncclUint8, r, comm, gst)); TB_NCCL(g_nccl.Recv(gs.all_juncs->strand + jo, (size_t)cj, ncclUint8, r, comm, gst));
+          TB_NCCL(g_nccl.Recv(gs.all_juncs->value + jo, (size_t)cj * 8, ncclUint8, r, comm, gst));
+          gs.bytes += cj * 21;
+        }
+      }
+    } else {
+      if (runs && new_r > 0) {
+        TB_NCCL(g_nccl.Send(runs->tid + gs.sent_r, (size_t)new_r * 4, ncclUint8, 0, comm, gst)); TB_NCCL(g_nccl.Send(runs->start0 + gs.sent_r, (size_t)new_r * 4, ncclUint8, 0, comm, gst));
+        TB_NCCL(g_nccl.Send(runs->end0 + gs.sent_r, (size_t)new_r * 4, ncclUint8, 0, comm, gst)); TB_NCCL(g_nccl.Send(runs->value + gs.sent_r, (size_t)new_r * 8, ncclUint8, 0, comm, gst));
+        gs.bytes += new_r * 20;
+      }
+      if (juncs && new_j > 0) {
+        TB_NCCL(g_nccl.Send(juncs->tid + gs.sent_j, (size_t)new_j * 4, ncclUint8, 0, comm, gst)); TB_NCCL(g_nccl.Send(juncs->start + gs.sent_j, (size_t)new_j * 4, ncclUint8, 0, comm, gst));
+        TB_NCCL(g_nccl.Send(juncs->end + gs.sent_j, (size_t)new_j * 4, ncclUint8, 0, comm, gst)); TB_NCCL(g_nccl.Send(juncs->strand + gs.sent_j, (size_t)new_j, ncclUint8, 0, comm, gst));
+        TB_NCCL(g_nccl.Send(juncs->value + gs.sent_j, (size_t)new_j * 8, ncclUint8, 0, comm, gst));
+        gs.bytes += new_j * 21;
+      }
+    }
+    TB_NCCL(g_nccl.GroupEnd());
+  }
+  for (int r = 0; r < W; ++r) { gs.got_r[r] += (int64_t)h[4 * r]; gs.got_j[r] += (int64_t)h[4 * r + 1]; }
+  gs.sent_r += new_r; gs.sent_j += new_j;
+  gs.all_done = all;
+  gs.rounds++;
+  return 0;
+}
+
 }  // namespace
 
 // One stream slice in windows cut at bundle heads. `skip` leading records are not processed (they belong to a bundle that
 // another rank owns). next = {tid, pos} of the record that follows the slice in the stream (host values), or NULL.
 // Outputs are appended to runs / juncs (n_runs / n_juncs on entry = rows already there). *consumed = records processed.
-int tc_stream_impl(tb_ctx* ctx, const tc_soa_in* in, int64_t skip, int64_t window, const int32_t* next, tc_runs_out* runs, tc_juncs_out* juncs, int64_t* consumed) {
+int tc_stream_impl(tb_ctx* ctx, const tc_soa_in* in, int64_t skip, int64_t window, const int32_t* next, tc_runs_out* runs, tc_juncs_out* juncs, int64_t* consumed,
+                   const std::function<int()>* after_window = nullptr) {
   TB_CUDA(cudaSetDevice(ctx->device));
   const int64_t n = in->n;
   if (window < 1024) window = 1024;
@@ -207,6 +308,7 @@ int tc_stream_impl(tb_ctx* ctx, const tc_soa_in* in, int64_t skip, int64_t windo
       if (juncs) juncs->n_juncs += j.n_juncs;
       ms_acc[0] += ctx->last_ms[6]; ms_acc[1] += ctx->last_ms[1]; ms_acc[2] += ctx->last_ms[7];
       ctx->stream_windows++;
+      if (after_window) { const int rc2 = (*after_window)(); if (rc2) return rc2; }
       if (ext.consumed < wlen && w1 >= n) { *consumed = w0 + ext.consumed; goto done; }   // the open tail belongs with the records behind the slice
       w0 += ext.consumed;
       break;
@@ -263,7 +365,7 @@ int tc_coverage_stream(tb_ctx* ctx, const tc_soa_in* in, int64_t window, const i
   return tc_stream_impl(ctx, in, 0, window, next_tid_pos, runs, juncs, consumed);
 }
 
-int tc_shard_coverage(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t window, tc_runs_out* runs, tc_juncs_out* juncs) {
+static int shard_coverage_impl(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t window, tc_runs_out* runs, tc_juncs_out* juncs, GatherState* gs) {
   if (!ctx) return 1;
   if (!segs || n_segs < 1 || (!runs && !juncs)) { ctx->set_error("tc_shard_coverage: segments and one of runs / juncs are required"); return 1; }
   for (int s = 0; s < n_segs; ++s) if (!segs[s].on_device) { ctx->set_error("tc_shard_coverage: segments must be device resident"); return 1; }
@@ -413,12 +515,14 @@ int tc_shard_coverage(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t wi
   // ---- 6. this rank's whole bundles, segment by segment ----
   int64_t consumed_last = last.n;
   float ms_sum[3] = {0.f, 0.f, 0.f};   // K6 / K7 / K8 device time over every window of the call
+  std::function<int()> round_cb = [&]() -> int { return gather_round(ctx, *gs, runs, juncs, false); };
+  const std::function<int()>* cb = gs ? &round_cb : nullptr;
   for (int s = 0; s < n_segs; ++s) {
     const bool is_last = s == n_segs - 1;
     int64_t consumed = 0;
     const int64_t skip = s == 0 ? lead : 0;
     if (skip >= segs[s].n) { if (is_last) consumed_last = segs[s].n; continue; }
-    const int rc = tc_stream_impl(ctx, &segs[s], skip, window, (is_last && tail_n > 0) ? tail_next : nullptr, runs, juncs, &consumed);
+    const int rc = tc_stream_impl(ctx, &segs[s], skip, window, (is_last && tail_n > 0) ? tail_next : nullptr, runs, juncs, &consumed, cb);
     if (rc) return rc;
     ms_sum[0] += ctx->last_ms[6]; ms_sum[1] += ctx->last_ms[1]; ms_sum[2] += ctx->last_ms[7];
     if (is_last) consumed_last = consumed;
@@ -459,18 +563,59 @@ int tc_shard_coverage(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t wi
     seam.strand = SB[SB_SEAM_STRAND].as<uint8_t>(); seam.cig_off = SB[SB_SEAM_OFF].as<uint32_t>(); seam.cigar = SB[SB_SEAM_CIG].as<uint32_t>();
     seam.on_device = 1; seam.n_cig = sw;
     int64_t consumed = 0;
-    const int rc = tc_stream_impl(ctx, &seam, 0, std::max<int64_t>(window, sn), nullptr, runs, juncs, &consumed);
+    const int rc = tc_stream_impl(ctx, &seam, 0, std::max<int64_t>(window, sn), nullptr, runs, juncs, &consumed, cb);
     if (rc) return rc;
     ms_sum[0] += ctx->last_ms[6]; ms_sum[1] += ctx->last_ms[1]; ms_sum[2] += ctx->last_ms[7];
     ctx->shard_stat[4] = sn;
   }
   ctx->last_ms[6] = ms_sum[0]; ctx->last_ms[1] = ms_sum[1]; ctx->last_ms[7] = ms_sum[2];
+  if (gs) {   // hand over what is left and answer rounds until every rank is done
+    for (int guard = 0; !gs->all_done; ++guard) {
+      if (guard > (1 << 20)) { ctx->set_error("tc_shard_coverage_gather: the ranks did not agree on the end of the gather (internal error)"); return 1; }
+      if (gather_round(ctx, *gs, runs, juncs, true)) return 1;
+    }
+    TB_CUDA(cudaStreamSynchronize(ctx->gather_stream));
+  }
   if (ctx->profiling) {
     TB_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) ctx->last_ms[9] = ms;
     (void)cudaGetLastError();
   }
+  return 0;
+}
+
+int tc_shard_coverage(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t window, tc_runs_out* runs, tc_juncs_out* juncs) {
+  return shard_coverage_impl(ctx, segs, n_segs, window, runs, juncs, nullptr);
+}
+
+// tc_shard_coverage with the ordered gather folded into the window loop (see GatherState). region (host, [4 * world], every
+// rank): for rank r the offset and count of its runs, then of its junction rows, inside all_runs / all_juncs on rank 0; the
+// ordered result is region 0, region 1, ... The junction numbering base of rank r is the sum of the junction counts before it.
+int tc_shard_coverage_gather(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t window, tc_runs_out* runs, tc_juncs_out* juncs,
+                             tc_runs_out* all_runs, tc_juncs_out* all_juncs, int64_t* region) {
+  if (!ctx) return 1;
+  if (!runs || !juncs || !region) { ctx->set_error("tc_shard_coverage_gather: runs, juncs and region are required"); return 1; }
+  const int W = ctx->comm ? ctx->world : 1, R = ctx->comm ? ctx->rank : 0;
+  if (R == 0 && (!all_runs || !all_juncs)) { ctx->set_error("tc_shard_coverage_gather: rank 0 needs all_runs and all_juncs"); return 1; }
+  TB_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->gather_stream) TB_CUDA(cudaStreamCreateWithFlags(&ctx->gather_stream, cudaStreamNonBlocking));
+  GatherState gs;
+  gs.all_runs = R == 0 ? all_runs : nullptr; gs.all_juncs = R == 0 ? all_juncs : nullptr;
+  // every rank must use the same region sizes: rank 0's capacities travel with the first allgather of the halo exchange?
+  // simpler: the caller passes the SAME capacities on every rank (all_* structs with NULL arrays elsewhere)
+  if (!all_runs || !all_juncs) { ctx->set_error("tc_shard_coverage_gather: every rank passes all_runs / all_juncs (capacities; arrays may be NULL except on rank 0)"); return 1; }
+  gs.cap_r = all_runs->capacity / W; gs.cap_j = all_juncs->capacity / W;
+  gs.got_r.assign(W, 0); gs.got_j.assign(W, 0);
+  const int rc = shard_coverage_impl(ctx, segs, n_segs, window, runs, juncs, &gs);
+  if (rc) return rc;
+  int64_t tr = 0, tj = 0;
+  for (int r = 0; r < W; ++r) {
+    region[4 * r] = r * gs.cap_r; region[4 * r + 1] = gs.got_r[r]; region[4 * r + 2] = r * gs.cap_j; region[4 * r + 3] = gs.got_j[r];
+    tr += gs.got_r[r]; tj += gs.got_j[r];
+  }
+  if (R == 0) { all_runs->n_runs = tr; all_juncs->n_juncs = tj; }
+  ctx->shard_stat[5] = gs.bytes; ctx->shard_stat[6] = gs.rounds;
   return 0;
 }
 

@@ -84,6 +84,7 @@ struct tb_ctx {
   HostBuf pinned[2];     // small pinned readback areas
   // multi-GPU (shard.cu): NCCL communicator of this context's rank, workspace, statistics of the last sharded call
   void* comm = nullptr; int rank = 0; int world = 1;
+  cudaStream_t gather_stream = nullptr;   // second stream: ordered gather overlapped with the windows
   DevBuf shard_buf[16];
   int64_t shard_stat[8] = {};   // lead records received | sent | ranks received from | bytes sent (halo) | seam records | bytes moved by the gather
   int64_t stream_windows = 0;   // windows of the last tc_coverage_stream / tc_shard_coverage call

@@ -50,8 +50,17 @@ def main():
             g = ctx.shard_gather(loc, api.cov_out_buffers(cap, cap, device=dev) if rank == 0 else None, world)
             stats = loc["stats"]
             print(f"case {case} rank {rank}: records [{a},{b}) runs {loc['n_runs']} juncs {loc['n_juncs']} windows {loc['windows']} {stats} gather_bytes {g['gather_bytes']}", flush=True)
+            # the same with the gather folded into the window loop (regions on rank 0)
+            ov = ctx.shard_coverage_gather([seg], 50000, api.cov_out_buffers(cap, cap, device=dev), api.cov_out_buffers(cap * world, cap * world, device=dev) if rank == 0 else None,
+                                           cap * world, cap * world, world)
+            print(f"case {case} rank {rank}: overlapped gather: rounds {ov['stats']['gather_rounds']} bytes {ov['stats']['gather_bytes']} regions {ov['regions']}", flush=True)
             if rank == 0:
                 one = ctx.coverage_stream(cols, 50000, api.cov_out_buffers(cap, cap, device=dev))
+                for name, x, y in zip(("r_tid", "r_start", "r_end", "r_val", "j_tid", "j_start", "j_end", "j_strand", "j_val"),
+                                      ov["gathered_runs"]() + ov["gathered_juncs"](), one["runs"] + one["juncs"]):
+                    if not np.array_equal(x.cpu().numpy(), y.cpu().numpy()):
+                        ok = False
+                        print(f"case {case}: overlapped gather: {name} differs: {len(x)} vs {len(y)}", flush=True)
                 from oracle import oracle
                 exp = oracle.coverage(host)
                 for name, x, y, z in zip(("r_tid", "r_start", "r_end", "r_val", "j_tid", "j_start", "j_end", "j_strand", "j_val"),
