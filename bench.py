@@ -40,8 +40,10 @@ def parse_args():
     ap.add_argument("--cov-records", type=int, default=int(os.environ.get("TB_BENCH_COV", 2_000_000_000)),
                     help="records of the tiecov leg = BASELINE config C4: ONE whole-genome collapsed stream of this many records, "
                          "split in stream order over the GPUs (strong scaling; 0 = skip)")
-    ap.add_argument("--cov-window", type=int, default=int(os.environ.get("TB_BENCH_COV_WINDOW", 62_500_000)),
-                    help="records per tiecov window (cut at bundle heads): 2e9 records = 32 windows on 1 GPU, 4 per GPU on 8")
+    ap.add_argument("--cov-window", type=int, default=int(os.environ.get("TB_BENCH_COV_WINDOW", 0)),
+                    help="records per tiecov window (cut at bundle heads); 0 = a quarter of the rank's slice (>= 4 windows per GPU: 5e8 records "
+                         "each on 1 GPU, 6.25e7 on 8), at most 5e8")
+    ap.add_argument("--cov-no-end", action="store_true", help="tiecov leg without the optional `end` column (the bundle kernel walks the CIGARs)")
     ap.add_argument("--cov-e2e-records", type=int, default=int(os.environ.get("TB_BENCH_COV_E2E", 250_000_000)),
                     help="records per rank of the tiecov end-to-end leg (host buffers; a prefix of the rank's slice)")
     ap.add_argument("--cov-cpu-sample", type=int, default=int(os.environ.get("TB_BENCH_COV_CPU", 2_000_000)),
@@ -395,10 +397,13 @@ def run_tiecov_leg(args, rank, world, local, dev, stream, peak, barrier, dist):
     R = args.cov_records
     a, b = rank * R // world, (rank + 1) * R // world
     t_gen = time.perf_counter()
-    segs, mbases = synth.genome_slice(R, a, b, seed=0, device=dev)
+    # the segments carry the `end` column a host packer has for free (GSamRecord::end): the bundle kernel then reads 16 B per record
+    segs, mbases = synth.genome_slice(R, a, b, seed=0, device=dev, with_end=not args.cov_no_end)
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
     n_local = b - a
+    if args.cov_window <= 0:
+        args.cov_window = int(min(500_000_000, max(1 << 20, -(-n_local // 4))))
     ncig_local = sum(int(s["n_cig"]) for s in segs)
     cctx = api.Context(device=local, n_samples=1)
     cctx.set_stream(stream.cuda_stream); cctx.set_profiling(True)
@@ -454,7 +459,7 @@ def run_tiecov_leg(args, rank, world, local, dev, stream, peak, barrier, dist):
     line = {"metric": "coverage_bases_per_sec", "value": mb_tot / (cov_ms / 1000.0), "unit": "bases/s", "records_per_sec": R / (cov_ms / 1000.0),
             "ms_per_step": cov_ms, "n_gpus": world, "scaling": "strong", "steps": args.steps,
             "config": {"workload": f"C4: tiecov -c -j on ONE synthetic collapsed whole-genome stream of {R} records (96 contigs, Zipf YC), split in stream order over {world} GPU(s), windows of <= {args.cov_window} records cut at bundle heads",
-                       "records": R, "records_per_gpu": n_local, "windows_per_gpu": loc["windows"], "gen_seconds": t_gen,
+                       "records": R, "records_per_gpu": n_local, "end_column": not args.cov_no_end, "windows_per_gpu": loc["windows"], "gen_seconds": t_gen,
                        "l2": "inputs (27 B/record, GBs per GPU) exceed the 126 MB L2; no flush needed"},
             "runs": runs_tot, "juncs": juncs_tot, "gpu_launches": int(launches),
             "exchange": {"halo_ms_max": float(tmax[1].item()), "lead_records_moved": int(tot[4].item()), "halo_bytes": int(tot[3].item()),
@@ -472,7 +477,7 @@ def run_tiecov_leg(args, rank, world, local, dev, stream, peak, barrier, dist):
         seg = segs[0]
         w1 = int(seg["cig_off"][ne].item()) & 0xFFFFFFFF
         host, h2d = {}, 0
-        for name, cnt in (("tid", ne), ("pos", ne), ("yc", ne), ("strand", ne), ("cig_off", ne + 1), ("cigar", w1)):
+        for name, cnt in (("tid", ne), ("pos", ne), ("yc", ne), ("strand", ne), ("cig_off", ne + 1), ("cigar", w1)):   # no `end` over PCIe: the device derives it
             ht = torch.empty(cnt, dtype=seg[name].dtype, pin_memory=True)
             ht.copy_(seg[name][:cnt])
             host[name] = ht.numpy().view({"cig_off": np.uint32, "cigar": np.uint32}.get(name, ht.numpy().dtype))

@@ -135,6 +135,9 @@ typedef struct {
   const uint32_t* cigar;
   int32_t  on_device;
   int64_t  n_cig;          /* words in `cigar` (== cig_off[n]) */
+  const int32_t*  end;     /* OPTIONAL, may be NULL: 0-based exclusive end of every record = GSamRecord::end as the host computed
+                              it (GSam.cpp:351-417; the north star lists `end` among the packed fields). With it the bundle
+                              kernel reads 16 instead of 27 bytes per record and never walks a CIGAR                     */
 } tc_soa_in;
 
 /* bedGraph runs, in file order: "chr\tstart0\tend0\t%.3f" (tiecov.cpp:226-241) */

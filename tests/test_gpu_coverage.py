@@ -233,3 +233,31 @@ def test_coverage_fractional_yc_takes_the_exact_path(ctx, seed):
     host["yc"] = np.ones_like(host["yc"])
     ctx.coverage_window(host)
     assert ctx.last_cov_exact() == 0
+
+
+# ---- the optional `end` column (GSamRecord::end from the host packer): K6 never walks a CIGAR ------------------------------
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_coverage_with_end_column_equals_without(ctx, where):
+    import torch
+    from oracle import oracle
+    from tiebrush_b200 import api, synth
+    cols = synth.coverage_stream(50000, seed=8, n_tx=40, chroms=3, device="cuda" if where == "device" else "cpu")
+    cols["end"] = synth.end_column(cols)
+    host = synth.to_host(cols)
+    exp = oracle.coverage(host)
+    src = cols if where == "device" else host
+    got = ctx.coverage_window(src)
+    for a, b in zip(got["runs"] + got["juncs"], exp["runs"] + exp["juncs"]):
+        assert np.array_equal(a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a), b)
+    cap = 2 * int(host["cig_off"][-1]) + 16
+    st = ctx.coverage_stream(src, 3000, api.cov_out_buffers(cap, cap, device="cuda" if where == "device" else None))
+    _same_rows(st, dict(runs=exp["runs"], juncs=exp["juncs"], n_runs=len(exp["runs"][0]), n_juncs=len(exp["juncs"][0])))
+
+
+def test_coverage_with_end_column_still_rejects_unsupported_ops(ctx):
+    cols = dict(tid=np.zeros(2, np.int32), pos=np.asarray([10, 12], np.int32), yc=np.ones(2, np.float32),
+                strand=np.asarray([ord(".")] * 2, np.uint8), cig_off=np.asarray([0, 1, 2], np.uint32),
+                cigar=np.asarray([(5 << 4) | 0, (5 << 4) | 7], np.uint32), end=np.asarray([15, 17], np.int32))
+    with pytest.raises(ValueError):
+        ctx.coverage_window(cols)
+    assert ctx.coverage_window(cols, want_runs=False)["n_juncs"] == 0

@@ -36,7 +36,7 @@ class GroupsOut(C.Structure):
 
 class CovIn(C.Structure):
     _fields_ = [("n", C.c_int64), ("tid", C.c_void_p), ("pos", C.c_void_p), ("yc", C.c_void_p), ("strand", C.c_void_p),
-                ("cig_off", C.c_void_p), ("cigar", C.c_void_p), ("on_device", C.c_int32), ("n_cig", C.c_int64)]
+                ("cig_off", C.c_void_p), ("cigar", C.c_void_p), ("on_device", C.c_int32), ("n_cig", C.c_int64), ("end", C.c_void_p)]
 
 
 class RunsOut(C.Structure):

@@ -281,7 +281,11 @@ class Context:
         tid, pos, yc = col("tid", np.int32), col("pos", np.int32), col("yc", np.float32)
         strand, cig_off, cigar = col("strand", np.uint8), col("cig_off", np.uint32), col("cigar", np.uint32)
         n_cig = int(cols["n_cig"]) if "n_cig" in cols else (int(cig_off[-1]) if n else 0)
-        cin = _lib.CovIn(n, _ptr(tid), _ptr(pos), _ptr(yc), _ptr(strand), _ptr(cig_off), _ptr(cigar), 1 if dev else 0, n_cig)
+        end = cols.get("end")
+        if end is not None:
+            end = end if dev else _host(end, np.int32)
+            keep.append(end)
+        cin = _lib.CovIn(n, _ptr(tid), _ptr(pos), _ptr(yc), _ptr(strand), _ptr(cig_off), _ptr(cigar), 1 if dev else 0, n_cig, _ptr(end))
         capr = cap_runs if cap_runs is not None else 2 * n_cig + 16
         capj = cap_juncs if cap_juncs is not None else n_cig + 16
         if out is None:
@@ -326,7 +330,12 @@ def _cov_in(cols, keep):
         keep.append(a)
         arrs.append(a)
     n_cig = int(cols["n_cig"]) if "n_cig" in cols else (int(arrs[4][-1]) - int(arrs[4][0]) if n else 0)
-    return _lib.CovIn(n, *[_ptr(a) for a in arrs], 1 if dev else 0, n_cig)
+    end = cols.get("end")
+    if end is not None:
+        if not dev:
+            end = _host(end, np.int32)
+        keep.append(end)
+    return _lib.CovIn(n, *[_ptr(a) for a in arrs], 1 if dev else 0, n_cig, _ptr(end))
 
 
 def cov_out_buffers(cap_runs, cap_juncs, device=None):

@@ -63,6 +63,7 @@ struct CovIn {
   int64_t n;
   const int32_t* tid; const int32_t* pos; const float* yc; const uint8_t* strand;
   const uint32_t* cig_off; const uint32_t* cigar;
+  const int32_t* end;   // optional (tc_soa_in.end): 0-based exclusive end of every record; K6 then never touches the CIGARs
 };
 
 // ---- K6: bundles in ONE pass over the records (decoupled look-back) -----------------------------------------------
@@ -84,7 +85,7 @@ struct CovIn {
 constexpr int CBK_THREADS = 256, CBK_ITEMS = TB_CBK_ITEMS, CBK_TILE = CBK_THREADS * CBK_ITEMS;
 // VEC: the per-record columns are 16-byte aligned, so a thread fetches its 8 consecutive records with 128-bit loads
 // (a warp request then covers 512 contiguous bytes instead of 32 scattered sectors)
-template <bool VEC>
+template <bool VEC, bool HAS_END>
 __global__ void __launch_bounds__(CBK_THREADS, TB_CBK_MINB) cov_bundle_kernel(CovIn in, int check_ops, unsigned long long* __restrict__ st_max,
                                                                  unsigned long long* __restrict__ st_cnt, unsigned long long* __restrict__ ticket,
                                                                  uint32_t* __restrict__ bid, int32_t* __restrict__ bstart, int32_t* __restrict__ bend,
@@ -98,31 +99,33 @@ __global__ void __launch_bounds__(CBK_THREADS, TB_CBK_MINB) cov_bundle_kernel(Co
   const long long tile = (long long)s_tile;
   const int64_t base = tile * CBK_TILE + (int64_t)threadIdx.x * CBK_ITEMS;
   unsigned long long key[CBK_ITEMS]; int pos[CBK_ITEMS], tidv[CBK_ITEMS];
-  uint32_t coff[CBK_ITEMS + 1]; float ycv[CBK_ITEMS];
+  uint32_t coff[CBK_ITEMS + 1]; float ycv[CBK_ITEMS];   // coff: CIGAR offsets, or (HAS_END) the record ends
   const bool full = base + CBK_ITEMS <= in.n;
   if (VEC && full) {
     static_assert(CBK_ITEMS % 4 == 0, "128-bit loads");
 #pragma unroll
     for (int q = 0; q < CBK_ITEMS / 4; ++q) {
       const int4 p = *reinterpret_cast<const int4*>(in.pos + base + 4 * q), t = *reinterpret_cast<const int4*>(in.tid + base + 4 * q);
-      const uint4 c = *reinterpret_cast<const uint4*>(in.cig_off + base + 4 * q);
+      const uint4 c = HAS_END ? *reinterpret_cast<const uint4*>(in.end + base + 4 * q) : *reinterpret_cast<const uint4*>(in.cig_off + base + 4 * q);
       const float4 y = *reinterpret_cast<const float4*>(in.yc + base + 4 * q);
       pos[4 * q] = p.x; pos[4 * q + 1] = p.y; pos[4 * q + 2] = p.z; pos[4 * q + 3] = p.w;
       tidv[4 * q] = t.x; tidv[4 * q + 1] = t.y; tidv[4 * q + 2] = t.z; tidv[4 * q + 3] = t.w;
       coff[4 * q] = c.x; coff[4 * q + 1] = c.y; coff[4 * q + 2] = c.z; coff[4 * q + 3] = c.w;
       ycv[4 * q] = y.x; ycv[4 * q + 1] = y.y; ycv[4 * q + 2] = y.z; ycv[4 * q + 3] = y.w;
     }
-    coff[CBK_ITEMS] = in.cig_off[base + CBK_ITEMS];
+    coff[CBK_ITEMS] = HAS_END ? 0u : in.cig_off[base + CBK_ITEMS];
   } else {
 #pragma unroll
     for (int k = 0; k < CBK_ITEMS; ++k) {
       const int64_t i = base + k;
       pos[k] = 0; tidv[k] = 0; coff[k] = 0; ycv[k] = 0.f;
-      if (i < in.n) { pos[k] = in.pos[i]; tidv[k] = in.tid[i]; coff[k] = in.cig_off[i]; ycv[k] = in.yc[i]; }
+      if (i < in.n) { pos[k] = in.pos[i]; tidv[k] = in.tid[i]; coff[k] = HAS_END ? (uint32_t)in.end[i] : in.cig_off[i]; ycv[k] = in.yc[i]; }
     }
     coff[CBK_ITEMS] = 0;
+    if (!HAS_END) {
 #pragma unroll
-    for (int k = 0; k < CBK_ITEMS; ++k) if (base + k < in.n) coff[k + 1] = in.cig_off[base + k + 1];
+      for (int k = 0; k < CBK_ITEMS; ++k) if (base + k < in.n) coff[k + 1] = in.cig_off[base + k + 1];
+    }
   }
   unsigned long long tm = 0;
 #pragma unroll
@@ -130,17 +133,21 @@ __global__ void __launch_bounds__(CBK_THREADS, TB_CBK_MINB) cov_bundle_kernel(Co
     const int64_t i = base + k;
     key[k] = 0;
     if (i < in.n) {
-      const uint32_t c0 = coff[k], c1 = coff[k + 1];
-      int l = 0;
-      bool bad = check_ops && (c1 - c0 >= 256u);  // tiecov.cpp:198 uint8_t loop counter never terminates
-      for (uint32_t c = c0; c < c1; ++c) {
-        const uint32_t w = in.cigar[c];
-        const uint32_t op = w & 0xf, len = w >> 4;
-        if (op == TB_OP_M || op == TB_OP_D || op == TB_OP_N || op == TB_OP_EQ || op == TB_OP_X) l += (int)len;
-        if (check_ops && !(op == TB_OP_M || op == TB_OP_I || op == TB_OP_D || op == TB_OP_N || op == TB_OP_S)) bad = true;
+      if (HAS_END) {   // the packer supplied GSamRecord::end (GSam.cpp:351-417 ran on the host): no CIGAR walk here; K7 checks the ops
+        key[k] = ((unsigned long long)(uint32_t)tidv[k] << 32) | coff[k];
+      } else {
+        const uint32_t c0 = coff[k], c1 = coff[k + 1];
+        int l = 0;
+        bool bad = check_ops && (c1 - c0 >= 256u);  // tiecov.cpp:198 uint8_t loop counter never terminates
+        for (uint32_t c = c0; c < c1; ++c) {
+          const uint32_t w = in.cigar[c];
+          const uint32_t op = w & 0xf, len = w >> 4;
+          if (op == TB_OP_M || op == TB_OP_D || op == TB_OP_N || op == TB_OP_EQ || op == TB_OP_X) l += (int)len;
+          if (check_ops && !(op == TB_OP_M || op == TB_OP_I || op == TB_OP_D || op == TB_OP_N || op == TB_OP_S)) bad = true;
+        }
+        if (bad) atomicMin((unsigned long long*)&status[ST_ERRIDX], (unsigned long long)i);
+        key[k] = ((unsigned long long)(uint32_t)tidv[k] << 32) | (uint32_t)(pos[k] + l);
       }
-      if (bad) atomicMin((unsigned long long*)&status[ST_ERRIDX], (unsigned long long)i);
-      key[k] = ((unsigned long long)(uint32_t)tidv[k] << 32) | (uint32_t)(pos[k] + l);
       const float sc = ycv[k] * (float)COV_FX_SCALE;
       if (sc != truncf(sc)) status[ST_INEXACT] = 1;  // benign race: any writer stores 1
       tm = key[k] > tm ? key[k] : tm;
@@ -297,7 +304,7 @@ struct CovSmem {
 // input); and the -w closing an M block cancels against the +w opening the next when the blocks touch (M I M).
 __global__ void __launch_bounds__(COV_THREADS) cov_accumulate_kernel(CovIn in, const uint32_t* __restrict__ bid, const int32_t* __restrict__ bstart,
                                                                      const long long* __restrict__ bbase, long long* __restrict__ diff,
-                                                                     int do_cov, int do_junc, JTable jt, long long* __restrict__ status) {
+                                                                     int do_cov, int do_junc, JTable jt, long long* __restrict__ status, int check_ops) {
   __shared__ CovSmem sm;
   const int64_t rec0 = (int64_t)blockIdx.x * (COV_THREADS * COV_RPT);
   for (int c = threadIdx.x; c < COV_TILE; c += COV_THREADS) { sm.lo[c] = 0; sm.hi[c] = 0; }
@@ -357,9 +364,11 @@ __global__ void __launch_bounds__(COV_THREADS) cov_accumulate_kernel(CovIn in, c
     int l = 0, exstart = pos, nclosed = 0, last_end = 0;
     bool intron = false, ins = false;
     long long pend = -1;   // difference cell of the pending -w (one past the last M block), -1 = none
+    if (check_ops && nc >= 256u) atomicMin((unsigned long long*)&status[ST_ERRIDX], (unsigned long long)i);   // tiecov.cpp:198
     for (uint32_t q = 0; q < nc; ++q) {
       const uint32_t cw = in.cigar[c0 + q];
       const uint32_t op = cw & 0xf; const int len = (int)(cw >> 4);
+      if (check_ops && !((0x1Fu >> op) & 1u)) atomicMin((unsigned long long*)&status[ST_ERRIDX], (unsigned long long)i);   // M I D N S only (tiecov.cpp:219-220)
       // the switch of setupCoordinates / addCov as predicated arithmetic (lanes of a warp sit on different ops):
       //   M,=,X,D : l += len, intron = ins = false      N : close the exon (unless ins && intron), l += len, intron = true
       //   S,H     : intron = ins = false                I : ins = true                  M alone adds coverage
@@ -680,6 +689,8 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     if (stage_in(ctx, ctx->in_stage[5], hin->cigar ? hin->cigar + cbase : nullptr, (size_t)ncig, hin->on_device, &staged)) return 1;
     in.cigar = staged - cbase;
   }
+  in.end = nullptr;
+  if (hin->end) { if (stage_in(ctx, ctx->in_stage[7], hin->end, (size_t)n, hin->on_device, &in.end)) return 1; }
   const int32_t* d_yx = nullptr;
   if (sample) { if (stage_in(ctx, ctx->in_stage[6], yx_in, (size_t)n, hin->on_device, &d_yx)) return 1; }
 
@@ -706,23 +717,23 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
   }
   // ---- K6 ----
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[8], st));
-  auto launch_k6 = [&]() -> int {
+  auto launch_k6 = [&](bool use_end) -> int {
     const int64_t ntiles = (n + CBK_TILE - 1) / CBK_TILE;
     unsigned long long* st_max = B[CB_KEY].as<unsigned long long>();
     unsigned long long* st_cnt = st_max + ntiles;
     unsigned long long* ticket = st_cnt + ntiles;
     TB_CUDA(cudaMemsetAsync(st_max, 0, sizeof(uint64_t) * (2 * (size_t)ntiles + 8), st));
-    const bool vec = (((uintptr_t)in.pos | (uintptr_t)in.tid | (uintptr_t)in.cig_off | (uintptr_t)in.yc) & 15u) == 0 && !getenv("TB_COV_NOVEC");
-    if (vec)
-      cov_bundle_kernel<true><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, do_cov, st_max, st_cnt, ticket, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(),
-                                                                       B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_pmend, d_rfirst, d_status);
-    else
-      cov_bundle_kernel<false><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, do_cov, st_max, st_cnt, ticket, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(),
-                                                                        B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_pmend, d_rfirst, d_status);
+    const bool vec = (((uintptr_t)in.pos | (uintptr_t)in.tid | (uintptr_t)in.cig_off | (uintptr_t)in.yc | (uintptr_t)in.end) & 15u) == 0 && !getenv("TB_COV_NOVEC");
+#define TB_K6(V, E) cov_bundle_kernel<V, E><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, do_cov, st_max, st_cnt, ticket, B[CB_BID].as<uint32_t>(), \
+      B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_pmend, d_rfirst, d_status)
+    if (use_end) { if (vec) TB_K6(true, true); else TB_K6(false, true); }
+    else { if (vec) TB_K6(true, false); else TB_K6(false, false); }
+#undef TB_K6
     ctx->launches++;
     return 0;
   };
-  if (launch_k6()) return 1;
+  const bool has_end = in.end != nullptr && !sample;
+  if (launch_k6(has_end)) return 1;
   if (ext) { cov_tail_kernel<<<1, 1, 0, st>>>(B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_rfirst, d_status); ctx->launches++; }
   // the bundle count decides the size of the next scan
   TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
@@ -753,7 +764,7 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     const int64_t nb_keep = h_status[ST_NBUNDLES];
     const int64_t n_eff = n;
     in.n = n_full; n = n_full;
-    if (launch_k6()) return 1;          // second run: also the running maximum of the ends (pmend) for the ordered walks
+    if (launch_k6(false)) return 1;     // second run: also the running maximum of the ends (pmend) for the ordered walks (walks the CIGARs: op check)
     in.n = n_eff; n = n_eff;
     cov_set_nbundles_kernel<<<1, 1, 0, st>>>(d_status, nb_keep);
     ctx->launches++;
@@ -818,7 +829,7 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     // ---- K7 (+K9 insert): the dominant kernel ----
     if (ctx->profiling && !cells) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
     cov_accumulate_kernel<<<grid_for(n, COV_THREADS * COV_RPT), COV_THREADS, 0, st>>>(in, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(), B[CB_BBASE].as<long long>(),
-                                                           B[CB_DIFF].as<long long>(), acc_cov, do_junc, jt, d_status);
+                                                           B[CB_DIFF].as<long long>(), acc_cov, do_junc, jt, d_status, (has_end && do_cov) ? 1 : 0);
     ctx->launches++;
     if (ctx->profiling && !cells) TB_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (!do_junc) break;
@@ -854,6 +865,10 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
     // the number of change points is only known on the device
     TB_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, st));
     TB_CUDA(cudaStreamSynchronize(st));
+    if (h_status[ST_ERRIDX] != -1) {   // found by K7 when the packer supplied the ends (K6 did not walk the CIGARs)
+      ctx->set_error("ERROR: unknown opcode in CIGAR of record %lld (tiecov supports only M,I,D,N,S; n_cigar<256)", h_status[ST_ERRIDX]);
+      return 2;
+    }
     const int64_t K = h_status[ST_NCHANGE];
     // output staging
     int64_t cap = runs->capacity;

@@ -149,6 +149,7 @@ static tc_soa_in sub_window(const tc_soa_in& in, int64_t w0, int64_t len, int64_
   tc_soa_in s = in;
   s.n = len;
   s.tid = in.tid + w0; s.pos = in.pos + w0; s.yc = in.yc + w0; s.strand = in.strand + w0; s.cig_off = in.cig_off + w0;
+  s.end = in.end ? in.end + w0 : nullptr;
   s.n_cig = words;
   return s;
 }

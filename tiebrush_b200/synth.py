@@ -328,6 +328,26 @@ def m_bases(cols):
 
 
 # ---- whole-genome collapsed stream for BASELINE config C4 (tiecov on 2e9 records), shardable by record index -------------
+def end_column(cols, chunk=20_000_000):
+    """0-based exclusive end (pos + reference length of the CIGAR: M D N = X) of every record of a torch column dict, int32,
+    computed in chunks on the columns' device: GSamRecord::end as a host packer has it for free (GSam.cpp:351-417)."""
+    n = int(cols["pos"].shape[0])
+    dev = cols["pos"].device
+    out = torch.empty(n, dtype=torch.int32, device=dev)
+    off = cols["cig_off"]
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        o = off[a:b + 1].to(torch.int64) & 0xFFFFFFFF
+        c0, c1 = int(o[0]), int(o[-1])
+        cig = cols["cigar"][c0:c1].to(torch.int64) & 0xFFFFFFFF
+        op = cig & 0xF
+        ref = torch.where((op == 0) | (op == 2) | (op == 3) | (op == 7) | (op == 8), cig >> 4, torch.zeros_like(cig))
+        cs = torch.zeros(c1 - c0 + 1, dtype=torch.int64, device=dev)
+        cs[1:] = torch.cumsum(ref, 0)
+        out[a:b] = (cols["pos"][a:b].to(torch.int64) + cs[o[1:] - c0] - cs[o[:-1] - c0]).to(torch.int32)
+    return out
+
+
 def genome_layout(n_total, split=4):
     """Contigs of the synthetic genome: every GRCh38 chromosome cut into `split` references (generation stays chunked:
     the largest holds 2 % of the records), records per contig proportional to its length. Returns (lengths, counts, starts)."""
@@ -339,7 +359,7 @@ def genome_layout(n_total, split=4):
     return lens, cnt, start
 
 
-def genome_slice(n_total, a, b, seed=0, n_tx=200000, device="cpu", seg_max=1_000_000_000, split=4):
+def genome_slice(n_total, a, b, seed=0, n_tx=200000, device="cpu", seg_max=1_000_000_000, split=4, with_end=False):
     """Records [a, b) (global stream order) of the synthetic whole-genome collapsed stream of `n_total` records, as a list
     of device-resident segments (own CIGAR arena each, cut only at contig boundaries). The stream is the same whatever the
     slicing: contig c holds sample_reads(TranscriptModel(seed 42+c), counts[c], seed 5000+7919*seed+c) with Zipf YC."""
@@ -374,4 +394,6 @@ def genome_slice(n_total, a, b, seed=0, n_tx=200000, device="cpu", seg_max=1_000
     flush()
     for s in segs:
         mb += m_bases(s)
+        if with_end:
+            s["end"] = end_column(s)
     return segs, mb
