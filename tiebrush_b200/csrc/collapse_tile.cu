@@ -28,7 +28,7 @@ namespace {
 constexpr unsigned long long EMPTY64 = ~0ULL;
 
 struct TileParams {
-  uint32_t T, M, ecap, W, cap_records;
+  uint32_t T, M, ecap, W, cap_records, heavy_records;
   const uint32_t* P; const uint32_t* slotpos; const uint32_t* off;
   uint32_t* gcount; uint32_t* st_rep; float* st_yc; uint32_t* st_yx; uint32_t* st_bits;
   long long* status; unsigned int* slot_counter; uint64_t seed;
@@ -522,6 +522,13 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) col_tile_kernel(ColIn
       __syncthreads();
       const uint32_t pbig = s_pbig;
       const uint32_t rb = tp.P[pbig];
+      // A very deep pile-up (tens of thousands of alignments at one start) almost always holds more distinct alignments than
+      // this launch's small table: streaming it until the table overflows is wasted work. Send the slot straight to the
+      // full-size launch (a performance shortcut only: that launch computes the same groups).
+      if (tp.heavy_list && tp.heavy_records && rank1 - rb > tp.heavy_records) {   // block-uniform
+        if (tid == 0) { tp.gcount[m] = 0; tp.heavy_list[atomicAdd((unsigned long long*)&tp.status[CS_NHEAVY], 1ULL)] = m; }
+        continue;
+      }
       const int big_pos = (int)pbig + in.pos_lo;
       for (uint32_t f = tid; f < k; f += THREADS) {  // first record of the slice at the pile-up position
         uint32_t lo = sm.a[f], hi = sm.b[f];
@@ -682,6 +689,8 @@ int col_front_tile(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups& ou
   tp.gcount = B[XB_GCOUNT].as<uint32_t>(); tp.st_rep = B[XB_ST_REP].as<uint32_t>(); tp.st_yc = B[XB_ST_YC].as<float>();
   tp.st_yx = B[XB_ST_YX].as<uint32_t>(); tp.st_bits = B[XB_ST_BITS].as<uint32_t>(); tp.status = g.d_status; tp.seed = 0x243F6A8885A308D3ULL;
   tp.slot_counter = B[XB_WORK].as<unsigned int>();
+  tp.heavy_records = 24u * E;   // TB_TILE_HEAVY_RECORDS overrides (0 = never shortcut)
+  if (const char* e = getenv("TB_TILE_HEAVY_RECORDS")) tp.heavy_records = (uint32_t)atol(e);
   auto launch = [&](int thr, const TileParams& t, unsigned nslots) -> cudaError_t {
     const size_t smem = tile_smem_bytes((uint32_t)k, t.ecap, W);
     const unsigned want = (unsigned)ctx->sm_count * (1024u / (unsigned)thr);
