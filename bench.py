@@ -582,10 +582,29 @@ def main():
     n = k * reads
     # ---- synthetic cohort straight into HBM; rank r owns an independent coordinate shard (weak scaling) ----
     t_gen = time.perf_counter()
-    cols, run_off, pr = synth.cohort_window(k, reads, seed=rank, device=dev, with_md=(args.mode == 1), paired=(args.flag_mask != 0))
+    # ONE cohort whatever the number of GPUs (strong scaling): every rank draws the same window and keeps its coordinate shard,
+    # cut where no read of any sample covers the cut (groups never span a start position, YD lists are empty after a gap:
+    # the shards are independent and their outputs concatenate to the window's); the groups are gathered on rank 0 over NCCL
+    # inside the timed region. -L keeps independent per-rank windows (the MD arena is not re-cut here).
+    strong = world > 1 and args.mode != 1
+    cols, run_off, pr = synth.cohort_window(k, reads, seed=0 if strong else rank, device=dev, with_md=(args.mode == 1), paired=(args.flag_mask != 0))
     if args.mode == 1:
         cols["md_off"], cols["md"], cols["n_md"] = synth.md_columns_torch(cols)
         del cols["md_mm"], cols["md_a"]
+    n_total = n if (strong or world == 1) else world * n
+    if strong:
+        subs = gap_cut_subwindows(cols, run_off, pr, world, dev)
+        del cols
+        if rank < len(subs):
+            cols, run_off, pr = subs[rank]
+        else:   # fewer gaps than ranks (tiny inputs): this rank idles
+            cols, run_off, pr = subs[-1]
+            cols = {kk: (v[:0] if hasattr(v, "shape") and kk != "cig_off" else v) for kk, v in cols.items()}
+            cols["cig_off"] = torch.zeros(1, dtype=torch.int32, device=dev); cols["n_cig"] = 0
+            run_off = np.zeros(k + 1, np.int64)
+        del subs
+        torch.cuda.empty_cache()
+        n = int(cols["pos"].shape[0])
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
     n_cig = cols["n_cig"]
@@ -595,8 +614,41 @@ def main():
     out = dict(rep_index=torch.empty(n, dtype=torch.int32, device=dev), yc=torch.empty(n, dtype=torch.float32, device=dev),
                yx=torch.empty(n, dtype=torch.int32, device=dev), yd=torch.empty(n, dtype=torch.int32, device=dev))
 
+    gat = None
+    if strong:   # rank 0's arrays for the ordered gather of the groups (rep_index | yc | yx | yd), sized from the first run
+        cnt_t = torch.zeros(world, dtype=torch.int64, device=dev)
+
+    def gather_groups(g_local):
+        """ordered gather of this step's groups on rank 0: all_gather of the counts, one batch of NCCL send / recv"""
+        nonlocal gat
+        mine = torch.tensor([g_local], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(cnt_t, mine)
+        counts = [int(x) for x in cnt_t.tolist()]
+        ops = []
+        if rank == 0:
+            tot = sum(counts)
+            if gat is None or gat["rep_index"].shape[0] < tot:
+                gat = {kk: torch.empty(tot + 1024, dtype=v.dtype, device=dev) for kk, v in out.items()}
+            off = 0
+            for r_, c_ in enumerate(counts):
+                if r_ == 0:
+                    for kk in out:
+                        gat[kk][:c_].copy_(out[kk][:c_], non_blocking=True)
+                elif c_ > 0:
+                    ops += [dist.P2POp(dist.irecv, gat[kk][off:off + c_], r_) for kk in ("rep_index", "yc", "yx", "yd")]
+                off += c_
+        elif g_local > 0:
+            ops = [dist.P2POp(dist.isend, out[kk][:g_local], 0) for kk in ("rep_index", "yc", "yx", "yd")]
+        if ops:
+            for w_ in dist.batch_isend_irecv(ops):
+                w_.wait()
+        return sum(counts)
+
     def step_dev():
-        return ctx.collapse_window(cols, run_off, pos_range=pr, out=out)
+        r_ = ctx.collapse_window(cols, run_off, pos_range=pr, out=out) if n > 0 else {"n_groups": 0, "n_kept": 0}
+        if strong:
+            r_["groups_all_ranks"] = gather_groups(r_["n_groups"])
+        return r_
 
     for _ in range(args.warmup):
         res = step_dev()
@@ -622,7 +674,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = world * n / (ms_step / 1000.0)
+    value = n_total / (ms_step / 1000.0)
     clocks = sampler
     # ---- roofline of the dominant kernel (collapse tile kernel) ----
     cbar = n_cig / n
@@ -639,15 +691,15 @@ def main():
                 "peak_source": peak_src, "kernel_ms": kernel_ms, "algorithmic_bytes": a_col,
                 "layout_bytes": n * (14 + 4 * cbar) + 16 * G}
     line = {"metric": "alignments_collapsed_per_sec", "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if (strong or world == 1) else "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{'C2' if (args.mode == 0 and args.flag_mask == 0 and args.min_qual < 0 and args.max_nh == 0x7fffffff) else 'C3'}: {k} RNA-seq samples x {reads} spliced 150bp reads on chr1, tiebrush mode {args.mode} (0=default CIGAR, 1=-L, 2=-P, 3=-E)"
                                    + (f", -N {args.max_nh}" if args.max_nh != 0x7fffffff else "") + (f", -Q {args.min_qual}" if args.min_qual >= 0 else "")
-                                   + (f", -F {args.flag_mask}" if args.flag_mask else "") + ", one window per GPU",
+                                   + (f", -F {args.flag_mask}" if args.flag_mask else "") + (f"; the ONE cohort sharded by coordinate (cuts at coverage gaps) over {world} GPUs, groups gathered on rank 0 over NCCL" if strong else ", one window per GPU"),
                        "front_end_path": int(ctx.last_path()) if hasattr(ctx, "last_path") else None,
                        "tile_gen": int(ctx.last_tile_gen()), "heavy_slots": int(ctx.last_heavy_slots()), "tile_stats": ctx.last_tile_stats(),
-                       "records_per_step_per_gpu": n, "groups_out": G, "mean_cigar_ops": cbar, "l2": "inputs (>=20 GB at full size) exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"coordinate shards x{world}, no data-path collective", "gen_seconds": t_gen, "host_affinity": numa},
+                       "records_per_step": n_total, "records_per_step_per_gpu": n, "groups_out": int(res.get("groups_all_ranks", G)), "groups_this_rank": G, "mean_cigar_ops": cbar, "l2": "inputs (>=20 GB at full size) exceed the 126 MB L2; no flush needed",
+                       "parallelism": (f"one cohort, coordinate shards x{world} cut at coverage gaps; all_gather of the group counts + batched NCCL send/recv of the groups to rank 0 per step" if strong else f"coordinate shards x{world}, no data-path collective"), "gen_seconds": t_gen, "host_affinity": numa},
             "roofline": roofline, "gpu_launches": int(launches),
             "stage_ms": dict(zip(("hist_scan", "slots_offsets", "tile", "compaction", "yd"), [float(x) for x in np.mean(np.asarray(stages), 0)]))}
     if tiecov_line is not None:
@@ -736,7 +788,7 @@ def main():
                 t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 e2e_ms = float(t.item())
-            single = {"ms_per_step": e2e_ms, "value": world * n / (e2e_ms / 1000.0), "h2d_bytes_per_step": int(h2d), "what": "ONE tb_collapse_window call on the whole 1e9-alignment window: every copy before the first kernel"}
+            single = {"ms_per_step": e2e_ms, "value": n_total / (e2e_ms / 1000.0), "h2d_bytes_per_step": int(h2d), "what": "ONE tb_collapse_window call on the whole window of this rank: every copy before the first kernel"}
             g_tot = r2["n_groups"]
             n_sw = 1
             if subs_host:
@@ -786,7 +838,12 @@ def main():
                 g_tot = sum(r_["n_groups"] for r_ in res_sw)
                 assert g_tot == r2["n_groups"], f"sub-windows gave {g_tot} groups, the one window {r2['n_groups']}"
                 ctx2.close()
-            line["e2e"] = {"value": world * n / (e2e_ms / 1000.0), "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(16 * g_tot + 128 * n_sw),
+            d2h = 16 * g_tot + 128 * n_sw
+            if world > 1:   # whole-job byte counts
+                t = torch.tensor([float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                h2d, d2h = int(t[0].item()), int(t[1].item())
+            line["e2e"] = {"value": n_total / (e2e_ms / 1000.0), "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                            "ms_per_step": e2e_ms, "steps": es, "wall_ms_per_step": 1000.0 * (time.perf_counter() - t0) / es,
                            "windows": n_sw, "hand_over": ("%d coordinate sub-windows cut at coverage gaps, two in flight on two contexts / streams (copies of one overlap the kernels of the other)" % n_sw) if n_sw > 1 else "one call",
                            "single_call": single,
