@@ -328,18 +328,38 @@ def gap_cut_subwindows(cols, run_off, pr, S, dev):
         del cig, op, ref, cs, rl, p, ones
     depth = torch.cumsum(cover, 0, dtype=torch.int32)
     del cover
-    pos0 = cols["pos"][int(run_off[0]):int(run_off[1])]
-    cuts = []
+    # records that start before every coordinate (for balancing the cuts by records, not by coordinate)
+    starts = torch.zeros(span + 2, dtype=torch.int32, device=dev)
+    for f in range(k):
+        a, b = int(run_off[f]), int(run_off[f + 1])
+        starts.index_add_(0, cols["pos"][a:b].to(torch.int64) - lo, torch.ones(b - a, dtype=torch.int32, device=dev))
+    cum = torch.cumsum(starts, 0, dtype=torch.int64)     # cum[x] = records with pos - lo <= x
+    del starts
+    n_all = int(cum[-1].item())
+    cuts, prev_cnt, prev_x = [], 0, 0
+    W_ = 20_000_000
     for s_ in range(1, S):
-        x = int(pos0[len(pos0) * s_ // S].item()) - lo
-        z = (depth[x:x + 20_000_000] == 0).nonzero()
-        if len(z) == 0:
+        target = prev_cnt + (n_all - prev_cnt) // (S - s_ + 1)      # re-balanced after a stretch that could not be cut
+        x = int(torch.searchsorted(cum, torch.tensor([target], device=dev, dtype=torch.int64))[0].item())
+        x = min(max(x, prev_x + 1), span)
+        cand = []
+        zf = (depth[x:x + W_] == 0).nonzero()
+        if len(zf):
+            cand.append(x + int(zf[0].item()))
+        a0 = max(prev_x + 1, x - W_)
+        zb = (depth[a0:x + 1] == 0).nonzero()
+        if len(zb):
+            cand.append(a0 + int(zb[-1].item()))
+        cand = [c for c in cand if prev_x < c < span]
+        if not cand:
             continue
-        c = lo + x + int(z[0].item())
-        if (not cuts or c > cuts[-1]) and c < int(pr[1]):
-            cuts.append(c)
-    del depth
-    bounds = [lo] + cuts + [int(pr[1])]
+        best = min(cand, key=lambda c: abs(int(cum[c - 1].item()) - target))
+        cnt = int(cum[best - 1].item())           # records with pos - lo < best
+        if cnt <= prev_cnt or cnt >= n_all:
+            continue
+        cuts.append(lo + best); prev_cnt, prev_x = cnt, best
+    del depth, cum
+    bounds = [lo] + [c for c in cuts if c < int(pr[1])] + [int(pr[1])]
     subs = []
     for s_ in range(len(bounds) - 1):
         b0 = torch.tensor([bounds[s_], bounds[s_ + 1]], device=dev, dtype=cols["pos"].dtype)
@@ -673,6 +693,13 @@ def main():
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
+    per_rank = None
+    if world > 1:   # who is the slowest: records, groups and device time of the collapse call alone, per rank
+        mine = torch.tensor([float(n), float(G), float(np.mean([sum(x) for x in stages]))], device=dev, dtype=torch.float64)
+        allr = torch.zeros(3 * world, device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        a_ = allr.cpu().numpy().reshape(world, 3)
+        per_rank = {"records": [int(x) for x in a_[:, 0]], "groups": [int(x) for x in a_[:, 1]], "kernel_ms": [round(float(x), 3) for x in a_[:, 2]]}
     ms_step = ms_total / args.steps
     value = n_total / (ms_step / 1000.0)
     clocks = sampler
@@ -700,7 +727,7 @@ def main():
                        "tile_gen": int(ctx.last_tile_gen()), "heavy_slots": int(ctx.last_heavy_slots()), "tile_stats": ctx.last_tile_stats(),
                        "records_per_step": n_total, "records_per_step_per_gpu": n, "groups_out": int(res.get("groups_all_ranks", G)), "groups_this_rank": G, "mean_cigar_ops": cbar, "l2": "inputs (>=20 GB at full size) exceed the 126 MB L2; no flush needed",
                        "parallelism": (f"one cohort, coordinate shards x{world} cut at coverage gaps; all_gather of the group counts + batched NCCL send/recv of the groups to rank 0 per step" if strong else f"coordinate shards x{world}, no data-path collective"), "gen_seconds": t_gen, "host_affinity": numa},
-            "roofline": roofline, "gpu_launches": int(launches),
+            "roofline": roofline, "gpu_launches": int(launches), **({"per_rank": per_rank} if per_rank else {}),
             "stage_ms": dict(zip(("hist_scan", "slots_offsets", "tile", "compaction", "yd"), [float(x) for x in np.mean(np.asarray(stages), 0)]))}
     if tiecov_line is not None:
         line["tiecov"] = tiecov_line
