@@ -52,6 +52,9 @@ enum {  // workspace slots in ctx->buf
   CB_TIDKEYS2,
   CB_PMEND,       // u32 [n]  -s: inclusive prefix maximum of the record ends (1-based), monotone inside a tid
   CB_RFIRST,      // u32 [n]  -s: first record of every bundle
+  CB_IOFF,        // u32 [n+1] ordered walks: first item of every record
+  CB_IKEY, CB_IKEY2, CB_IVAL, CB_IVAL2,   // u64 / u32 [items] tile id | item index (radix sort ping-pong)
+  CB_ILO, CB_IHI, CB_IREC,                // u32 [items] first / last cell of the item, its record
   CB_COUNT_
 };
 
@@ -471,6 +474,88 @@ __global__ void __launch_bounds__(256) cov_sample_cell_kernel(CovIn in, const in
   }
   ival[x] = (long long)(unsigned long long)ceilf(mean);
 }
+
+// ---- ordered per-cell walks in O(covered bases): tile item lists (tiecov -s and the exact path of fractional weights) ----
+// The straightforward kernels above let every cell visit every record that MIGHT cover it (all records of the bundle whose
+// running maximum end reaches the cell: a spliced read "covers" its whole intron this way), 0.6 s per 1e7 records. Here every
+// M block of every record becomes one ITEM per 256-cell tile it touches (first cell, last cell, record), emitted in stream
+// order; a stable radix sort by tile keeps that order inside a tile; one CTA per tile then folds its items in order, each
+// thread one cell — a cell only ever sees records that cover its tile. Same arithmetic, same order, same bits.
+constexpr int OW_TILE = 256;
+template <bool EMIT>
+__global__ void __launch_bounds__(256) ow_items_kernel(CovIn in, const uint32_t* __restrict__ bid, const int32_t* __restrict__ bstart,
+                                                       const long long* __restrict__ bbase, uint32_t* __restrict__ cnt_or_off,
+                                                       unsigned long long* __restrict__ ikey, uint32_t* __restrict__ ival, uint32_t* __restrict__ ilo,
+                                                       uint32_t* __restrict__ ihi, uint32_t* __restrict__ irec) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= in.n) return;
+  const uint32_t b = bid[i];
+  const long long shift = bbase[b] - (long long)bstart[b];   // compact cell of 1-based coordinate g is g + shift
+  int p = in.pos[i] + 1;
+  uint32_t items = 0, w = EMIT ? cnt_or_off[i] : 0u;
+  const uint32_t c1 = in.cig_off[i + 1];
+  for (uint32_t c = in.cig_off[i]; c < c1; ++c) {
+    const uint32_t cw = in.cigar[c];
+    const uint32_t op = cw & 0xf; const int len = (int)(cw >> 4);
+    if (op == TB_OP_M) {
+      if (len > 0) {
+        const long long x0 = (long long)p + shift, x1 = x0 + len - 1;
+        for (long long t = x0 / OW_TILE; t <= x1 / OW_TILE; ++t) {
+          if (EMIT) {
+            const long long lo = t * OW_TILE > x0 ? t * OW_TILE : x0, hi = (t + 1) * OW_TILE - 1 < x1 ? (t + 1) * OW_TILE - 1 : x1;
+            ikey[w] = (unsigned long long)t; ival[w] = w; ilo[w] = (uint32_t)lo; ihi[w] = (uint32_t)hi; irec[w] = (uint32_t)i;
+            ++w;
+          }
+          ++items;
+        }
+      }
+      p += len;
+    } else if (op == TB_OP_D || op == TB_OP_N) p += len;
+  }
+  if (!EMIT) cnt_or_off[i] = items;
+}
+struct IcntIn { const uint32_t* c; __device__ uint32_t operator()(int64_t i) const { return c[i]; } };
+struct IoffOut { uint32_t* o; int64_t n; __device__ void operator()(int64_t i, uint32_t exc, uint32_t inc) const { o[i] = exc; if (i == n - 1) o[n] = inc; } };
+
+// MEAN = true: tiecov -s, float32 running mean of YX then ceil (addMean, tiecov.cpp:155-185); false: double sum of yc (addCov)
+template <bool MEAN>
+__global__ void __launch_bounds__(OW_TILE) ow_cells_kernel(const unsigned long long* __restrict__ skey, const uint32_t* __restrict__ sval, int64_t n_items,
+                                                           const uint32_t* __restrict__ ilo, const uint32_t* __restrict__ ihi, const uint32_t* __restrict__ irec,
+                                                           const int32_t* __restrict__ yx, const float* __restrict__ yc, long long* __restrict__ cell, int64_t L) {
+  __shared__ uint32_t s_lo[OW_TILE], s_hi[OW_TILE];
+  __shared__ float s_w[OW_TILE];
+  __shared__ long long s_range[2];
+  const long long t = blockIdx.x;
+  if (threadIdx.x < 2) {   // [first, last) item of this tile in the sorted list
+    const unsigned long long want = (unsigned long long)t + threadIdx.x;
+    long long lo = 0, hi = n_items;
+    while (lo < hi) { const long long mid = lo + ((hi - lo) >> 1); if (skey[mid] >= want) hi = mid; else lo = mid + 1; }
+    s_range[threadIdx.x] = lo;
+  }
+  __syncthreads();
+  const long long j0 = s_range[0], j1 = s_range[1];
+  const long long x = t * OW_TILE + threadIdx.x;
+  float mean = 0.f; unsigned long long cnt = 1; double sum = 0.0;
+  for (long long base = j0; base < j1; base += OW_TILE) {
+    const long long j = base + threadIdx.x;
+    __syncthreads();
+    if (j < j1) {
+      const uint32_t it = sval[j];
+      s_lo[threadIdx.x] = ilo[it]; s_hi[threadIdx.x] = ihi[it];
+      const uint32_t r = irec[it];
+      s_w[threadIdx.x] = MEAN ? (float)yx[r] : yc[r];
+    }
+    __syncthreads();
+    const int m = (int)((j1 - base) < OW_TILE ? (j1 - base) : OW_TILE);
+    for (int q = 0; q < m; ++q) {
+      if ((uint32_t)x >= s_lo[q] && (uint32_t)x <= s_hi[q]) {
+        if (MEAN) { mean += (s_w[q] - mean) / (float)cnt; ++cnt; }
+        else sum += (double)s_w[q];
+      }
+    }
+  }
+  if (x < L) cell[x] = MEAN ? (long long)(unsigned long long)ceilf(mean) : __double_as_longlong(sum);
+}
 struct ChgIn {
   const long long* v;
   __device__ uint32_t operator()(int64_t x) const { return v[x] != (x ? v[x - 1] : 0) ? 1u : 0u; }
@@ -801,12 +886,51 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
   if (cells) {
     TB_CUDA(B[CB_DIFF].ensure(sizeof(int64_t) * (L + 1)));
     if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[0], st));
-    if (sample)
-      cov_sample_cell_kernel<<<grid_for(L, 256), 256, 0, st>>>(in, d_yx, NB, B[CB_BBASE].as<long long>(), B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(),
-                                                              d_rfirst, d_pmend, B[CB_DIFF].as<long long>(), L);
-    else
-      cov_exact_cell_kernel<<<grid_for(L, 256), 256, 0, st>>>(in, NB, B[CB_BBASE].as<long long>(), B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(),
-                                                             d_rfirst, d_pmend, B[CB_DIFF].as<long long>(), L);
+    const bool brute = getenv("TB_COV_WALK") && !strcmp(getenv("TB_COV_WALK"), "brute");   // the simple kernels, kept as a cross-check
+    if (brute) {
+      if (!d_pmend) { ctx->set_error("tc_coverage_window: TB_COV_WALK=brute needs the running maximum (internal)"); return 1; }
+      if (sample)
+        cov_sample_cell_kernel<<<grid_for(L, 256), 256, 0, st>>>(in, d_yx, NB, B[CB_BBASE].as<long long>(), B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(),
+                                                                d_rfirst, d_pmend, B[CB_DIFF].as<long long>(), L);
+      else
+        cov_exact_cell_kernel<<<grid_for(L, 256), 256, 0, st>>>(in, NB, B[CB_BBASE].as<long long>(), B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(),
+                                                               d_rfirst, d_pmend, B[CB_DIFF].as<long long>(), L);
+    } else {
+      if (L >= (1LL << 32)) { ctx->set_error("tc_coverage_window: %lld cells do not fit the 32-bit item lists (smaller windows)", (long long)L); return 1; }
+      TB_CUDA(B[CB_IOFF].ensure(sizeof(uint32_t) * (n + 2)));
+      uint32_t* ioff = B[CB_IOFF].as<uint32_t>();
+      ow_items_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(in, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(), B[CB_BBASE].as<long long>(), ioff,
+                                                              nullptr, nullptr, nullptr, nullptr, nullptr);
+      TB_CUDA(B[CB_AGG].ensure((size_t)(tb_scan_blocks(n) + 8) * sizeof(SumNz)));
+      TB_CUDA((tb_device_scan<OpSumU32>(ctx, IcntIn{ioff}, n, B[CB_AGG].as<uint32_t>(), IoffOut{ioff, n})));
+      uint32_t n_items_u = 0;
+      TB_CUDA(cudaMemcpyAsync(&n_items_u, ioff + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      TB_CUDA(cudaStreamSynchronize(st));
+      const int64_t NI = n_items_u;
+      const int64_t nalloc = NI > 0 ? NI : 1;
+      TB_CUDA(B[CB_IKEY].ensure(sizeof(uint64_t) * nalloc)); TB_CUDA(B[CB_IKEY2].ensure(sizeof(uint64_t) * nalloc));
+      TB_CUDA(B[CB_IVAL].ensure(sizeof(uint32_t) * nalloc)); TB_CUDA(B[CB_IVAL2].ensure(sizeof(uint32_t) * nalloc));
+      TB_CUDA(B[CB_ILO].ensure(sizeof(uint32_t) * nalloc)); TB_CUDA(B[CB_IHI].ensure(sizeof(uint32_t) * nalloc)); TB_CUDA(B[CB_IREC].ensure(sizeof(uint32_t) * nalloc));
+      ow_items_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(in, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(), B[CB_BBASE].as<long long>(), ioff,
+                                                             B[CB_IKEY].as<unsigned long long>(), B[CB_IVAL].as<uint32_t>(), B[CB_ILO].as<uint32_t>(),
+                                                             B[CB_IHI].as<uint32_t>(), B[CB_IREC].as<uint32_t>());
+      ctx->launches += 2;
+      const int64_t ntile = (L + OW_TILE - 1) / OW_TILE;
+      int bits = 1; while ((1LL << bits) < ntile + 1) ++bits;
+      uint64_t* rk = B[CB_IKEY].as<uint64_t>(); uint32_t* rv = B[CB_IVAL].as<uint32_t>();
+      if (NI > 0) {
+        TB_CUDA(B[CB_RSTABLE].ensure(sizeof(uint32_t) * tb_radix_table_elems(NI)));
+        TB_CUDA(B[CB_RSAGG].ensure(sizeof(uint32_t) * tb_radix_agg_elems(NI)));
+        TB_CUDA(tb_radix_sort(ctx, B[CB_IKEY].as<uint64_t>(), B[CB_IVAL].as<uint32_t>(), B[CB_IKEY2].as<uint64_t>(), B[CB_IVAL2].as<uint32_t>(), NI, 0, bits,
+                              B[CB_RSTABLE].as<uint32_t>(), B[CB_RSAGG].as<uint32_t>(), &rk, &rv));
+      }
+      if (sample)
+        ow_cells_kernel<true><<<(unsigned)ntile, OW_TILE, 0, st>>>((const unsigned long long*)rk, rv, NI, B[CB_ILO].as<uint32_t>(), B[CB_IHI].as<uint32_t>(), B[CB_IREC].as<uint32_t>(),
+                                                                  d_yx, in.yc, B[CB_DIFF].as<long long>(), L);
+      else
+        ow_cells_kernel<false><<<(unsigned)ntile, OW_TILE, 0, st>>>((const unsigned long long*)rk, rv, NI, B[CB_ILO].as<uint32_t>(), B[CB_IHI].as<uint32_t>(), B[CB_IREC].as<uint32_t>(),
+                                                                   d_yx, in.yc, B[CB_DIFF].as<long long>(), L);
+    }
     ctx->launches++;
     if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[1], st));
   }
