@@ -82,15 +82,82 @@ __device__ int ord_compare(const ColIn& in, const OrdParams& op, uint32_t x, uin
 }
 __device__ __forceinline__ int ord_pair_order(uint16_t fl) { return (fl & 0x40) ? 1 : ((fl & 0x80) ? 2 : 0); }  // GSam.h:315-321
 
-__global__ void __launch_bounds__(128) ord_emulate_kernel(ColIn in, OrdParams op) {
+// GList::Found (GList.hh:567-604) of record i in the sorted list L[0..nl) of position slots based at b: first, last, then bisection
+__device__ __forceinline__ bool ord_found(const ColIn& in, const OrdParams& op, uint32_t b, const uint32_t* L, uint32_t nl, uint32_t i, uint32_t& idx) {
+  idx = 0;
+  if (nl == 0) return false;
+  if (ord_compare(in, op, op.g_rep[b + L[0]], i) > 0) { idx = 0; return false; }
+  if (ord_compare(in, op, i, op.g_rep[b + L[nl - 1]]) > 0) { idx = nl; return false; }
+  int l = 0, h = (int)nl - 1;
+  while (l <= h) {
+    const int mid = l + ((h - l) >> 1);
+    const int c = ord_compare(in, op, op.g_rep[b + L[mid]], i);
+    if (c < 0) l = mid + 1;
+    else { h = mid - 1; if (c == 0) { idx = (uint32_t)mid; return true; } }
+  }
+  idx = (uint32_t)l;
+  return false;
+}
+// dupAdd (tiebrush.cpp:408-436) of record i (file f) into group slot s
+__device__ __forceinline__ void ord_dup_add(const ColIn& in, const OrdParams& op, uint32_t s, uint32_t i, int f, bool merged, uint16_t fl) {
+  const uint32_t W = op.W;
+  if (merged) {
+    double v = (double)in.yc_in[i]; if (v == 0.0) v = 1.0;
+    op.g_yc[s] += v;
+    op.g_yx[s] += in.yx_in[i];
+    const int32_t yd = in.yd_in[i];
+    if (yd > op.g_yd[s]) op.g_yd[s] = yd;
+  } else {
+    const uint32_t bw = op.g_bits[(uint64_t)s * W + ((uint32_t)f >> 5)], bit = 1u << (f & 31);
+    const uint32_t rep = op.g_rep[s];
+    if (!in.collapse_same || !(bw & bit) || ord_pair_order(fl) != ord_pair_order(in.flag[rep]) || in.qhash[i] != in.qhash[rep]) {
+      if (in.keep_bits & TB_STORE_FRAC) { const int nh = in.nh[i] ? in.nh[i] : 1; op.g_yc[s] += 1.0 / nh; }
+      else op.g_yc[s] += 1.0;
+      op.g_bits[(uint64_t)s * W + ((uint32_t)f >> 5)] = bw | bit;
+    }
+  }
+}
+// settle (tiebrush.cpp:378-406) + sortInsert of record i as new group j at list index idx
+__device__ __forceinline__ void ord_settle(const ColIn& in, const OrdParams& op, uint32_t b, uint32_t* L, uint32_t& nl, uint32_t idx, uint32_t i, int f, bool merged) {
+  const uint32_t W = op.W;
+  const uint32_t j = nl;            // slots are handed out in arrival order
+  const uint32_t s = b + j;
+  op.g_rep[s] = i;
+  for (uint32_t w = 0; w < W; ++w) op.g_bits[(uint64_t)s * W + w] = 0;
+  if (merged) {
+    double v = (double)in.yc_in[i]; if (v == 0.0) v = 1.0;
+    op.g_yc[s] = v; op.g_yx[s] = in.yx_in[i]; op.g_yd[s] = in.yd_in[i];
+  } else {
+    if (in.keep_bits & TB_STORE_FRAC) { const int nh = in.nh[i] ? in.nh[i] : 1; op.g_yc[s] = 1.0 / nh; }
+    else op.g_yc[s] = 1.0;
+    op.g_yx[s] = 0; op.g_yd[s] = 0;
+    op.g_bits[(uint64_t)s * W + ((uint32_t)f >> 5)] = 1u << (f & 31);
+  }
+  for (uint32_t q = nl; q > idx; --q) L[q] = L[q - 1];
+  L[idx] = j; ++nl;
+}
+// flushPData order (tiebrush.cpp:501-530): the list order
+__device__ __forceinline__ void ord_flush_one(const OrdParams& op, uint32_t b, const uint32_t* L, uint32_t x) {
+  const uint32_t W = op.W;
+  const uint32_t s = b + L[x], o = b + x;
+  uint32_t pc = 0;
+  for (uint32_t w = 0; w < W; ++w) { const uint32_t bw = op.g_bits[(uint64_t)s * W + w]; pc += __popc(bw); op.st_bits[(uint64_t)o * W + w] = bw; }
+  op.st_rep[o] = op.g_rep[s];
+  op.st_yc[o] = (float)op.g_yc[s];
+  op.st_yx[o] = (uint32_t)((long long)pc + op.g_yx[s]);
+  op.st_yd[o] = op.g_yd[s] > 0 ? op.g_yd[s] : 0;
+  op.valid[o] = 1u;
+}
+
+// one THREAD per start position (positions of at least `deep` records are left to the warp kernel below)
+__global__ void __launch_bounds__(128) ord_emulate_kernel(ColIn in, OrdParams op, uint32_t deep) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= in.span) return;
   const uint32_t b = op.P[p], e = op.P[p + 1];
-  if (e == b) return;
+  if (e == b || e - b >= deep) return;
   uint32_t* L = op.list + b;
   uint32_t nl = 0;
   long long kept = 0;
-  const uint32_t W = op.W;
   for (uint32_t r = b; r < e; ++r) {
     const uint32_t i = op.order[r];
     const uint16_t fl = in.flag[i];
@@ -98,70 +165,75 @@ __global__ void __launch_bounds__(128) ord_emulate_kernel(ColIn in, OrdParams op
     ++kept;
     const int f = ord_file_of(op.run_off, in.k, (int64_t)i);
     const bool merged = op.merged && op.merged[f];
-    // GList::Found (GList.hh:567-604)
-    bool found = false; uint32_t idx = 0;
-    if (nl > 0) {
-      if (ord_compare(in, op, op.g_rep[b + L[0]], i) > 0) { idx = 0; }
-      else if (ord_compare(in, op, i, op.g_rep[b + L[nl - 1]]) > 0) { idx = nl; }
-      else {
-        int l = 0, h = (int)nl - 1;
-        idx = 0xffffffffu;
-        while (l <= h) {
-          const int mid = l + ((h - l) >> 1);
-          const int c = ord_compare(in, op, op.g_rep[b + L[mid]], i);
-          if (c < 0) l = mid + 1;
-          else { h = mid - 1; if (c == 0) { found = true; idx = (uint32_t)mid; break; } }
-        }
-        if (!found) idx = (uint32_t)l;
-      }
-    }
-    if (found) {  // dupAdd (tiebrush.cpp:408-436)
-      const uint32_t s = b + L[idx];
-      if (merged) {
-        double v = (double)in.yc_in[i]; if (v == 0.0) v = 1.0;
-        op.g_yc[s] += v;
-        op.g_yx[s] += in.yx_in[i];
-        const int32_t yd = in.yd_in[i];
-        if (yd > op.g_yd[s]) op.g_yd[s] = yd;
-      } else {
-        const uint32_t bw = op.g_bits[(uint64_t)s * W + ((uint32_t)f >> 5)], bit = 1u << (f & 31);
-        const uint32_t rep = op.g_rep[s];
-        if (!in.collapse_same || !(bw & bit) || ord_pair_order(fl) != ord_pair_order(in.flag[rep]) || in.qhash[i] != in.qhash[rep]) {
-          if (in.keep_bits & TB_STORE_FRAC) { const int nh = in.nh[i] ? in.nh[i] : 1; op.g_yc[s] += 1.0 / nh; }
-          else op.g_yc[s] += 1.0;
-          op.g_bits[(uint64_t)s * W + ((uint32_t)f >> 5)] = bw | bit;
-        }
-      }
-    } else {      // settle (tiebrush.cpp:378-406) + sortInsert
-      const uint32_t j = nl;            // slots are handed out in arrival order
-      const uint32_t s = b + j;
-      op.g_rep[s] = i;
-      for (uint32_t w = 0; w < W; ++w) op.g_bits[(uint64_t)s * W + w] = 0;
-      if (merged) {
-        double v = (double)in.yc_in[i]; if (v == 0.0) v = 1.0;
-        op.g_yc[s] = v; op.g_yx[s] = in.yx_in[i]; op.g_yd[s] = in.yd_in[i];
-      } else {
-        if (in.keep_bits & TB_STORE_FRAC) { const int nh = in.nh[i] ? in.nh[i] : 1; op.g_yc[s] = 1.0 / nh; }
-        else op.g_yc[s] = 1.0;
-        op.g_yx[s] = 0; op.g_yd[s] = 0;
-        op.g_bits[(uint64_t)s * W + ((uint32_t)f >> 5)] = 1u << (f & 31);
-      }
-      for (uint32_t q = nl; q > idx; --q) L[q] = L[q - 1];
-      L[idx] = j; ++nl;
-    }
+    uint32_t idx;
+    if (ord_found(in, op, b, L, nl, i, idx)) ord_dup_add(in, op, b + L[idx], i, f, merged, fl);
+    else ord_settle(in, op, b, L, nl, idx, i, f, merged);
   }
-  // flushPData order (tiebrush.cpp:501-530): the list order
-  for (uint32_t x = 0; x < nl; ++x) {
-    const uint32_t s = b + L[x], o = b + x;
-    uint32_t pc = 0;
-    for (uint32_t w = 0; w < W; ++w) { const uint32_t bw = op.g_bits[(uint64_t)s * W + w]; pc += __popc(bw); op.st_bits[(uint64_t)o * W + w] = bw; }
-    op.st_rep[o] = op.g_rep[s];
-    op.st_yc[o] = (float)op.g_yc[s];
-    op.st_yx[o] = (uint32_t)((long long)pc + op.g_yx[s]);
-    op.st_yd[o] = op.g_yd[s] > 0 ? op.g_yd[s] : 0;
-    op.valid[o] = 1u;
-  }
+  for (uint32_t x = 0; x < nl; ++x) ord_flush_one(op, b, L, x);
   if (kept) atomicAdd((unsigned long long*)&op.status[CS_NKEPT], (unsigned long long)kept);
+}
+
+// deep positions (pile-ups): their list of start positions
+__global__ void __launch_bounds__(256) ord_deep_list_kernel(const uint32_t* __restrict__ P, uint32_t span, uint32_t deep, uint32_t* __restrict__ list, unsigned int* __restrict__ count) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= span) return;
+  if (P[p + 1] - P[p] >= deep) list[atomicAdd(count, 1u)] = p;
+}
+
+// one WARP per deep position. The reference's loop is sequential because every record meets the list its predecessors
+// left behind — but only an INSERT changes the list: the 32 lanes search 32 consecutive records of the merge order against
+// the current list at once (the expensive part: ~log2(groups) comparator calls with global loads each); the records in
+// front of the first one that is not found are then applied one after the other in merge order (dupAdd reads and writes
+// group state, so -A / --store-frac / TieBrush-made inputs keep their order), that record is inserted, and the search
+// restarts behind it. Exactly the sequence of list states of the one-thread loop.
+__global__ void __launch_bounds__(128) ord_emulate_warp_kernel(ColIn in, OrdParams op, const uint32_t* __restrict__ deep_list, const unsigned int* __restrict__ deep_count) {
+  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= *deep_count) return;
+  const uint32_t p = deep_list[wid];
+  const uint32_t b = op.P[p], e = op.P[p + 1];
+  uint32_t* L = op.list + b;
+  uint32_t nl = 0;
+  long long kept = 0;
+  uint32_t r0 = b;
+  while (r0 < e) {
+    const uint32_t r = r0 + lane;
+    const bool have = r < e;
+    uint32_t i = 0, idx = 0; uint16_t fl = 0; bool pass = false, found = false;
+    if (have) {
+      i = op.order[r]; fl = in.flag[i];
+      pass = tb_passes_options(in, fl, in.mapq[i], in.nh[i]);
+      if (pass) found = ord_found(in, op, b, L, nl, i, idx);
+    }
+    const unsigned need_insert = __ballot_sync(0xffffffffu, have && pass && !found);
+    const unsigned in_range = __ballot_sync(0xffffffffu, have);
+    const int stop = need_insert ? __ffs(need_insert) - 1 : 32;      // first lane whose record opens a new group
+    // apply the found records in front of it, in merge order
+    for (int q = 0; q < stop && ((in_range >> q) & 1u); ++q) {
+      if ((int)lane == q && pass) {
+        const int f = ord_file_of(op.run_off, in.k, (int64_t)i);
+        ord_dup_add(in, op, b + L[idx], i, f, op.merged && op.merged[f], fl);
+        ++kept;
+      }
+      __syncwarp();
+    }
+    if (stop < 32) {
+      if ((int)lane == stop) {
+        const int f = ord_file_of(op.run_off, in.k, (int64_t)i);
+        ord_settle(in, op, b, L, nl, idx, i, f, op.merged && op.merged[f]);
+        ++kept;
+      }
+      __threadfence_block();
+      nl = __shfl_sync(0xffffffffu, nl, stop);
+      r0 += (uint32_t)stop + 1u;
+    } else {
+      r0 += 32u;
+    }
+    __syncwarp();
+  }
+  for (uint32_t x = lane; x < nl; x += 32) ord_flush_one(op, b, L, x);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, d);
+  if (lane == 0 && kept) atomicAdd((unsigned long long*)&op.status[CS_NKEPT], (unsigned long long)kept);
 }
 
 struct ValidIn { const uint32_t* v; __device__ uint32_t operator()(int64_t i) const { return v[i]; } };
@@ -219,8 +291,23 @@ int col_front_ordered(tb_ctx* ctx, const ColIn& in, const ColGeom& g, ColGroups&
   TB_CUDA(B[XB_ORD_GBITS].ensure(sizeof(uint32_t) * (size_t)n * W));
   op.g_bits = B[XB_ORD_GBITS].as<uint32_t>();
   TB_CUDA(cudaMemsetAsync(op.valid, 0, sizeof(uint32_t) * n, st));
-  ord_emulate_kernel<<<tb_grid_for((int64_t)g.S, 128), 128, 0, st>>>(in, op);
-  ctx->launches++;
+  // positions of at least `deep` records (pile-ups) get a warp each, the others a thread each
+  uint32_t deep = 96;
+  if (const char* e = getenv("TB_ORD_DEEP")) { const long v = atol(e); deep = v > 0 ? (uint32_t)v : 0xffffffffu; }
+  TB_CUDA(B[XB_ORD_DEEP].ensure(sizeof(uint32_t) * ((size_t)(n / (deep ? deep : 1)) + 64)));
+  unsigned int* d_deep_count = B[XB_ORD_DEEP].as<unsigned int>();
+  uint32_t* d_deep_list = B[XB_ORD_DEEP].as<uint32_t>() + 16;
+  TB_CUDA(cudaMemsetAsync(d_deep_count, 0, 64, st));
+  ord_deep_list_kernel<<<tb_grid_for((int64_t)g.S, 256), 256, 0, st>>>(g.P, g.S, deep, d_deep_list, d_deep_count);
+  ord_emulate_kernel<<<tb_grid_for((int64_t)g.S, 128), 128, 0, st>>>(in, op, deep);
+  {
+    unsigned int h_deep = 0;
+    TB_CUDA(cudaMemcpyAsync(&h_deep, d_deep_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    if (h_deep > 0) { ord_emulate_warp_kernel<<<tb_grid_for((int64_t)h_deep * 32, 128), 128, 0, st>>>(in, op, d_deep_list, d_deep_count); ctx->launches++; }
+    ctx->last_ord_deep = (int64_t)h_deep;
+  }
+  ctx->launches += 2;
   // ---- O4 ----
   TB_CUDA(B[XB_BITS].ensure(sizeof(uint32_t) * (size_t)n * W));   // dense bitsets; G <= n is only known after the scan
   out.bits = B[XB_BITS].as<uint32_t>();

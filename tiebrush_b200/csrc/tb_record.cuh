@@ -203,6 +203,7 @@ enum {
   XB_ORD_KEY, XB_ORD_KEY2, XB_ORD_VAL, XB_ORD_VAL2, XB_ORD_REFLEN, XB_ORD_TABLE, XB_ORD_AGG,   // ordered path: merge-order sort
   XB_ORD_LIST, XB_ORD_GREP, XB_ORD_GYC, XB_ORD_GYX, XB_ORD_GYD, XB_ORD_VALID, XB_ORD_GBITS,                // ordered path: per-position group lists
   XB_META_DICT,   // u64 [256] dictionary of the packed wire format
+  XB_ORD_DEEP,    // ordered path: counter + list of the deep start positions
   XB_COUNT_
 };
 static_assert(XB_COUNT_ <= TB_NBUF, "raise TB_NBUF");
