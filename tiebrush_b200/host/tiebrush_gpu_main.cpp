@@ -34,6 +34,11 @@
 #include <memory>
 #include <functional>
 #include "tiebrush_b200.h"
+#include <unistd.h>
+
+// error exit from a worker thread: the reference's convention (message on stderr, exit code 1) without running exit handlers
+// while the other threads of the pipeline are still alive
+static void tb_die(const char* msg) { fputs(msg, stderr); fputc('\n', stderr); fflush(stderr); _exit(1); }
 
 namespace {
 
@@ -213,7 +218,7 @@ struct TbWindowPacker {
     tb_groups_out out; memset(&out, 0, sizeof(out));
     out.capacity = (int64_t)n; out.rep_index = o_rep.data(); out.yc = o_yc.data(); out.yx = o_yx.data(); out.yd = o_yd.data();
     auto t1 = clk::now();
-    if (tb_collapse_window(ctx, &in, &out)) GError("%s\n", tb_last_error(ctx));
+    if (tb_collapse_window(ctx, &in, &out)) tb_die(tb_last_error(ctx));
     auto t2 = clk::now();
     inCounter += (uint64_t)out.n_kept;                               // tiebrush.cpp:573
     {   // flushPData, tiebrush.cpp:506-527: the tags of the representatives are patched on the pack threads (records are
@@ -330,7 +335,7 @@ int main(int argc, char* argv[]) {
     const char* dev_env = getenv("TB_DEVICE");
     tb_ctx* ctx = tb_create(dev_env ? atoi(dev_env) : 0, numSamples, mode, options.flags, options.max_nh, options.min_qual, keep,
                             options.collapse_same ? 1 : 0);
-    if (!ctx) GError("%s\n", tb_last_error(NULL));
+    if (!ctx) tb_die(tb_last_error(NULL));
     t_create = std::chrono::duration<double>(clk::now() - c0).count();
     while (std::unique_ptr<TbWindow> w = queue.pop()) packer.flush(ctx, *w);
     tb_destroy(ctx);

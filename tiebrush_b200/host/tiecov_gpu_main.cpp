@@ -24,6 +24,11 @@
 #include <deque>
 #include <memory>
 #include "tiebrush_b200.h"
+#include <unistd.h>
+
+// error exit from a worker thread: the reference's convention (message on stderr, exit code 1) without running exit handlers
+// while the other threads of the pipeline are still alive
+static void tb_die(const char* msg) { fputs(msg, stderr); fputc('\n', stderr); fflush(stderr); _exit(1); }
 
 namespace {
 
@@ -102,13 +107,13 @@ struct TcWindowPacker {
     }
     if (coutf || joutf) {
       const int rc = tc_coverage_window(ctx, &in, coutf ? &runs : NULL, joutf ? &js : NULL);
-      if (rc) GError("%s\n", tb_last_error(ctx));                    // incl. the "unknown opcode" abort of tiecov.cpp:219-220
+      if (rc) tb_die(tb_last_error(ctx));                             // incl. the "unknown opcode" abort of tiecov.cpp:219-220
     }
     tc_runs_out rows; memset(&rows, 0, sizeof(rows));
     if (soutf) {
       s_tid.resize(cap_r); s_start.resize(cap_r); s_end.resize(cap_r); s_val.resize(cap_r);
       rows.capacity = cap_r; rows.tid = s_tid.data(); rows.start0 = s_start.data(); rows.end0 = s_end.data(); rows.value = s_val.data();
-      if (tc_sample_window(ctx, &in, yx.data(), &rows)) GError("%s\n", tb_last_error(ctx));
+      if (tc_sample_window(ctx, &in, yx.data(), &rows)) tb_die(tb_last_error(ctx));
     }
     auto t1 = clk::now();
     if (coutf)                                                        // flushCoverage, tiecov.cpp:237
