@@ -14,9 +14,11 @@
  *
  * Everything crossing the boundary is a plain pointer + size. No torch / STL types.
  * Arrays are struct-of-arrays; `on_device` says whether the per-record arrays are host pointers
- * (the library stages them through pinned memory and copies on its stream) or device pointers
- * (already resident in HBM; no copy). Small descriptor arrays (run_off, file_merged) are always
- * host memory.
+ * (the library copies them from the caller's buffers on its stream with cudaMemcpyAsync: page-locked
+ * buffers travel at PCIe rate, pageable ones at what the driver's bounce buffers give; a caller that wants
+ * copies to overlap kernels hands over smaller windows on two contexts, as bench.py's e2e leg does) or
+ * device pointers (already resident in HBM; no copy). Small descriptor arrays (run_off, file_merged,
+ * meta_dict) are always host memory.
  *
  * Error convention mirrors the reference's GError (gclib/GBase.cpp:31-53): a call returns non-zero,
  * tb_last_error() gives the message, the caller prints it to stderr and exits 1.
