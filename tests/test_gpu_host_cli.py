@@ -194,3 +194,24 @@ def test_store_frac_then_tiecov_cli_is_exact(sams):
     _run([os.path.join(HOST, "tiecov_gpu"), "-c", gc, "-j", gj, frac], env={"TB_WINDOW_RECORDS": "800"})
     assert open(gc + ".bedgraph").read() == open(rc + ".bedgraph").read()
     assert open(gj + ".bed").read() == open(rj + ".bed").read()
+
+
+def test_tiecov_cli_on_several_gpus_matches_reference(sams):
+    """TB_DEVICES: tiecov_gpu shards every round of the stream over the GPUs of the box (tc_shard_coverage: NCCL halo exchange)
+    and prints the reference's bytes, with rounds small enough that cuts fall inside bundles. Needs >= 2 GPUs."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    _need(os.path.join(REF, "tiecov"), os.path.join(REF, "tiebrush"), os.path.join(HOST, "tiecov_gpu"))
+    tmp, paths, _ = sams
+    merged = os.path.join(tmp, "multi_in.bam")
+    _run([os.path.join(REF, "tiebrush"), "-o", merged] + paths)
+    rc, rj = os.path.join(tmp, "ref_multi_cov"), os.path.join(tmp, "ref_multi_j")
+    _run([os.path.join(REF, "tiecov"), "-c", rc, "-j", rj, merged])
+    for devs, wr in ((f"0-{min(ngpu, 8) - 1}", "150"), ("0,1", "40")):
+        gc, gj = os.path.join(tmp, "gpu_multi_cov" + wr), os.path.join(tmp, "gpu_multi_j" + wr)
+        msg = _run([os.path.join(HOST, "tiecov_gpu"), "-c", gc, "-j", gj, merged], env={"TB_DEVICES": devs, "TB_WINDOW_RECORDS": wr, "TB_TIMING": "1"})
+        assert "GPUs" in msg and "rounds" in msg
+        assert open(gc + ".bedgraph").read() == open(rc + ".bedgraph").read()
+        assert open(gj + ".bed").read() == open(rj + ".bed").read()

@@ -369,10 +369,36 @@ int tc_coverage_stream(tb_ctx* ctx, const tc_soa_in* in, int64_t window, const i
 static int shard_coverage_impl(tb_ctx* ctx, const tc_soa_in* segs, int n_segs, int64_t window, tc_runs_out* runs, tc_juncs_out* juncs, GatherState* gs) {
   if (!ctx) return 1;
   if (!segs || n_segs < 1 || (!runs && !juncs)) { ctx->set_error("tc_shard_coverage: segments and one of runs / juncs are required"); return 1; }
-  for (int s = 0; s < n_segs; ++s) if (!segs[s].on_device) { ctx->set_error("tc_shard_coverage: segments must be device resident"); return 1; }
   ctx->err.clear();
   TB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  // ONE host-resident segment (the command-line tool's case) is copied to the device first; several segments must be resident
+  tc_soa_in dseg;
+  if (!segs[0].on_device) {
+    if (n_segs != 1) { ctx->set_error("tc_shard_coverage: host arrays are accepted as ONE segment; several segments must be device resident"); return 1; }
+    const tc_soa_in& h = segs[0];
+    dseg = h; dseg.on_device = 1;
+    if (h.n > 0) {
+      const uint32_t c0 = h.cig_off[0], c1 = h.cig_off[h.n];
+      DevBuf* IS = ctx->in_stage;
+      auto up = [&](DevBuf& b, const void* src, size_t bytes, const void** out) -> cudaError_t {
+        cudaError_t e = b.ensure(bytes + 16); if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st); *out = b.p; return e;
+      };
+      const void* q;
+      TB_CUDA(up(IS[8], h.tid, sizeof(int32_t) * h.n, &q)); dseg.tid = (const int32_t*)q;
+      TB_CUDA(up(IS[9], h.pos, sizeof(int32_t) * h.n, &q)); dseg.pos = (const int32_t*)q;
+      TB_CUDA(up(IS[10], h.yc, sizeof(float) * h.n, &q)); dseg.yc = (const float*)q;
+      TB_CUDA(up(IS[11], h.strand, (size_t)h.n, &q)); dseg.strand = (const uint8_t*)q;
+      TB_CUDA(up(IS[12], h.cig_off, sizeof(uint32_t) * (h.n + 1), &q)); dseg.cig_off = (const uint32_t*)q;
+      TB_CUDA(up(IS[13], h.cigar + c0, sizeof(uint32_t) * (size_t)(c1 - c0), &q)); dseg.cigar = (const uint32_t*)q - c0;   // offsets stay absolute
+      if (h.end) { TB_CUDA(up(IS[14], h.end, sizeof(int32_t) * h.n, &q)); dseg.end = (const int32_t*)q; }
+      dseg.n_cig = (int64_t)(c1 - c0);
+      TB_CUDA(cudaStreamSynchronize(st));
+    }
+    segs = &dseg;
+  }
+  for (int s = 0; s < n_segs; ++s) if (!segs[s].on_device) { ctx->set_error("tc_shard_coverage: segments must be all host (one) or all device resident"); return 1; }
   if (runs) runs->n_runs = 0;
   if (juncs) juncs->n_juncs = 0;
   ctx->stream_windows = 0;

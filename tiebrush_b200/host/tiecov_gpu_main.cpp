@@ -162,6 +162,129 @@ int main(int argc, char* argv[]) {
   if (!jfname.is_empty()) joutf = open_track(jfname, ".bed", "track name=junctions\n");
   if (!sfname.is_empty())
     soutf = open_track(sfname, ".bedgraph", "track type=bedGraph name=\"Sample Count Heatmap\" description=\"Sample Count Heatmap\" visibility=full graphType=\"heatmap\" color=200,100,0 altColor=0,100,200\n");
+  // ---- TB_DEVICES=0,1,... or 0-7: the stream sharded over several GPUs of the box (-c / -j). One thread per GPU, each with its
+  // own context and NCCL rank; the reader hands over ROUNDS of whole bundles, a round is split by record count into one
+  // slice per GPU (the cuts fall anywhere: tc_shard_coverage moves the records of a bundle that a cut separated from its
+  // head to the GPU that holds the head), the rows are printed in GPU order with one running JUNC counter. ----
+  std::vector<int> devs;
+  if (const char* de = getenv("TB_DEVICES")) {
+    for (const char* q = de; *q;) {
+      char* endp; long a = strtol(q, &endp, 10);
+      if (endp == q) break;
+      long b = a;
+      if (*endp == '-') { q = endp + 1; b = strtol(q, &endp, 10); }
+      for (long d = a; d <= b; ++d) devs.push_back((int)d);
+      q = *endp ? endp + 1 : endp;
+    }
+  }
+  if (devs.size() > 1) {
+    if (soutf) GError("Error: -s is not available with TB_DEVICES (one GPU computes the sample heat-map)\n");
+    const int W = (int)devs.size();
+    unsigned char nccl_id[128];
+    if (tb_comm_unique_id(nccl_id)) GError("%s\n", tb_last_error(NULL));
+    size_t round_min = (size_t)W * (2u << 20);   // records per round (TB_WINDOW_RECORDS = per GPU)
+    if (const char* e = getenv("TB_WINDOW_RECORDS")) { long v = atol(e); if (v > 0) round_min = (size_t)v * W; }
+    struct RankOut { std::vector<int32_t> r_tid, r_start, r_end, j_tid, j_start, j_end; std::vector<double> r_val, j_val; std::vector<uint8_t> j_strand; int64_t nr = 0, nj = 0; };
+    std::vector<RankOut> outs(W);
+    std::mutex qm; std::condition_variable qcv; std::deque<std::unique_ptr<TcWindow>> q; bool q_done = false;
+    // a reusable barrier over the W device threads
+    std::mutex bm; std::condition_variable bcv; int b_wait = 0; long b_gen = 0;
+    auto barrier = [&] {
+      std::unique_lock<std::mutex> lk(bm);
+      const long g = b_gen;
+      if (++b_wait == W) { b_wait = 0; ++b_gen; bcv.notify_all(); }
+      else bcv.wait(lk, [&] { return b_gen != g; });
+    };
+    std::unique_ptr<TcWindow> cur; bool all_done = false;
+    double t_device = 0, t_print = 0; long n_rounds = 0;
+    sam_hdr_t* hdr = samreader.header();
+    auto device_main = [&](int r) {
+      tb_ctx* ctx = tb_create(devs[r], 1, TB_MODE_CIGAR, 0, TB_NO_MAX_NH, -1, 0, 0);
+      if (!ctx) tb_die(tb_last_error(NULL));
+      if (tb_comm_init(ctx, r, W, nccl_id)) tb_die(tb_last_error(ctx));
+      for (;;) {
+        if (r == 0) {   // take the next round
+          std::unique_lock<std::mutex> lk(qm);
+          qcv.wait(lk, [&] { return !q.empty() || q_done; });
+          if (q.empty()) all_done = true;
+          else { cur = std::move(q.front()); q.pop_front(); qcv.notify_all(); }
+        }
+        barrier();
+        if (all_done) break;
+        auto t0 = clk::now();
+        TcWindow& w = *cur;
+        const int64_t n = (int64_t)w.n(), a = n * r / W, b = n * (r + 1) / W;
+        tc_soa_in in; memset(&in, 0, sizeof(in));
+        in.n = b - a; in.tid = w.tid.data() + a; in.pos = w.pos.data() + a; in.yc = w.yc.data() + a; in.strand = w.strand.data() + a;
+        in.cig_off = w.cig_off.data() + a; in.cigar = w.cigar.data(); in.on_device = 0;
+        in.n_cig = (int64_t)(w.cig_off[b] - w.cig_off[a]);
+        RankOut& o = outs[r];
+        // rows of this GPU: its own records' worth plus what the lead exchange may bring in from the right
+        const int64_t cap_r = 2 * (int64_t)w.cigar.size() + 16, cap_j = (int64_t)w.cigar.size() + 16;
+        tc_runs_out runs; memset(&runs, 0, sizeof(runs)); tc_juncs_out js; memset(&js, 0, sizeof(js));
+        o.r_tid.resize(cap_r); o.r_start.resize(cap_r); o.r_end.resize(cap_r); o.r_val.resize(cap_r);
+        runs.capacity = cap_r; runs.tid = o.r_tid.data(); runs.start0 = o.r_start.data(); runs.end0 = o.r_end.data(); runs.value = o.r_val.data();
+        o.j_tid.resize(cap_j); o.j_start.resize(cap_j); o.j_end.resize(cap_j); o.j_val.resize(cap_j); o.j_strand.resize(cap_j);
+        js.capacity = cap_j; js.tid = o.j_tid.data(); js.start = o.j_start.data(); js.end = o.j_end.data(); js.strand = o.j_strand.data(); js.value = o.j_val.data();
+        const int rc = tc_shard_coverage(ctx, &in, 1, 1 << 26, coutf ? &runs : NULL, joutf ? &js : NULL);   // collective: every GPU thread is here
+        if (rc) tb_die(tb_last_error(ctx));
+        o.nr = coutf ? runs.n_runs : 0; o.nj = joutf ? js.n_juncs : 0;
+        barrier();
+        if (r == 0) {
+          auto t1 = clk::now();
+          for (int g = 0; g < W; ++g) {
+            RankOut& og = outs[g];
+            if (coutf) print_rows(coutf, og.nr, [&](int64_t i, char* buf, size_t cap) {
+              return snprintf(buf, cap, "%s\t%d\t%d\t%.3f\n", hdr->target_name[og.r_tid[i]], og.r_start[i], og.r_end[i], og.r_val[i]); });
+            if (joutf) {
+              const int base = juncCount;
+              print_rows(joutf, og.nj, [&](int64_t i, char* buf, size_t cap) {
+                return snprintf(buf, cap, "%s\t%d\t%d\tJUNC%08d\t%.3f\t%c\n", hdr->target_name[og.j_tid[i]], og.j_start[i] - 1, og.j_end[i], base + (int)i + 1, og.j_val[i], (char)og.j_strand[i]); });
+              juncCount += (int)og.nj;
+            }
+          }
+          cur.reset();
+          ++n_rounds;
+          t_device += std::chrono::duration<double>(t1 - t0).count();
+          t_print += std::chrono::duration<double>(clk::now() - t1).count();
+        }
+        barrier();
+      }
+      tb_destroy(ctx);
+    };
+    std::vector<std::thread> dth;
+    for (int r = 0; r < W; ++r) dth.emplace_back(device_main, r);
+    auto hand_over = [&](std::unique_ptr<TcWindow>& w) {
+      if (w->n() == 0) return;
+      w->cig_off.push_back((uint32_t)w->cigar.size());
+      if (w->cigar.empty()) w->cigar.push_back(0);
+      std::unique_lock<std::mutex> lk(qm);
+      qcv.wait(lk, [&] { return q.size() < 2; });
+      q.push_back(std::move(w)); qcv.notify_all();
+      w.reset(new TcWindow());
+    };
+    std::unique_ptr<TcWindow> win(new TcWindow());
+    int prev_tid = -1, b_end = 0;
+    GSamRecord brec;
+    while (samreader.next(brec)) {
+      if (brec.isUnmapped()) continue;                                 // tiecov.cpp:436-438
+      const bool new_bundle = brec.refId() != prev_tid || (int)brec.start > b_end;   // tiecov.cpp:443
+      if (new_bundle) {
+        if (win->n() >= round_min) hand_over(win);
+        b_end = brec.end; prev_tid = brec.refId();
+      } else if (b_end < (int)brec.end) b_end = brec.end;
+      win->add(brec);
+    }
+    hand_over(win);
+    { std::lock_guard<std::mutex> lk(qm); q_done = true; qcv.notify_all(); }
+    for (auto& t : dth) t.join();
+    if (coutf && coutf != stdout) fclose(coutf);
+    if (joutf) fclose(joutf);
+    if (getenv("TB_TIMING"))
+      fprintf(stderr, "tb_b200 timing: total %.3f s | %d GPUs | device (H2D+halo exchange+kernels+D2H) %.3f | print %.3f | rounds %ld\n",
+              std::chrono::duration<double>(clk::now() - t_begin).count(), W, t_device, t_print, n_rounds);
+    return 0;
+  }
   const char* dev_env = getenv("TB_DEVICE");
   tb_ctx* ctx = tb_create(dev_env ? atoi(dev_env) : 0, 1, TB_MODE_CIGAR, 0, TB_NO_MAX_NH, -1, 0, 0);
   if (!ctx) GError("%s\n", tb_last_error(NULL));
