@@ -215,3 +215,21 @@ def test_tiecov_cli_on_several_gpus_matches_reference(sams):
         assert "GPUs" in msg and "rounds" in msg
         assert open(gc + ".bedgraph").read() == open(rc + ".bedgraph").read()
         assert open(gj + ".bed").read() == open(rj + ".bed").read()
+
+
+def test_tiebrush_cli_on_several_gpus_matches_reference(sams):
+    """TB_DEVICES: tiebrush_gpu computes its windows on several GPUs at once and writes them in hand-over order. Needs >= 2 GPUs."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    _need(os.path.join(REF, "tiebrush"), os.path.join(REF, "htsfile"), os.path.join(HOST, "tiebrush_gpu"))
+    tmp, paths, _ = sams
+    for opts in ([], ["-E", "-N", "2"]):
+        tag = "multi" + "_".join(o.strip("-") for o in opts)
+        ref_out, our_out = os.path.join(tmp, f"ref_{tag}.bam"), os.path.join(tmp, f"gpu_{tag}.bam")
+        ref_msg = _run([os.path.join(REF, "tiebrush")] + opts + ["-o", ref_out] + paths)
+        our_msg = _run([os.path.join(HOST, "tiebrush_gpu")] + opts + ["-o", our_out] + paths,
+                       env={"TB_DEVICES": f"0-{min(ngpu, 8) - 1}", "TB_WINDOW_RECORDS": "250", "TB_WINDOW_SPAN": "2000", "TB_TIMING": "1"})
+        assert _records(our_out) == _records(ref_out)
+        assert "GPU(s)" in our_msg and ref_msg.strip().split("\n")[-1] in our_msg

@@ -44,6 +44,7 @@ namespace {
 
 struct TbWindow {   // what the reader thread hands to the device thread
   int tid = -1;
+  long seq = 0;   // hand-over order: the windows are written in this order whichever GPU computed them
   size_t n = 0;
   std::vector<std::vector<GSamRecord*>> per_file;   // records of the window, per input file, in file order
   std::vector<uint8_t> file_merged;
@@ -76,8 +77,16 @@ struct Reaper {
   void finish() { { std::lock_guard<std::mutex> lk(m); done = true; } cv.notify_all(); th.join(); }
 };
 
+// windows may be computed on several GPUs at once (TB_DEVICES) but are tagged and written strictly in hand-over order
+struct WriteGate {
+  std::mutex m; std::condition_variable cv; long next = 0;
+  void wait_turn(long seq) { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return next == seq; }); }
+  void done() { { std::lock_guard<std::mutex> lk(m); ++next; } cv.notify_all(); }
+};
+
 struct TbWindowPacker {
   int k = 0;
+  WriteGate* gate = NULL;
   htsFile* out_fp = NULL; sam_hdr_t* out_hdr = NULL;
   // SoA staging (reused between windows)
   std::vector<int64_t> run_off;
@@ -220,6 +229,8 @@ struct TbWindowPacker {
     auto t1 = clk::now();
     if (tb_collapse_window(ctx, &in, &out)) tb_die(tb_last_error(ctx));
     auto t2 = clk::now();
+    if (gate) gate->wait_turn(w.seq);
+    auto t2w = clk::now();
     inCounter += (uint64_t)out.n_kept;                               // tiebrush.cpp:573
     {   // flushPData, tiebrush.cpp:506-527: the tags of the representatives are patched on the pack threads (records are
         // independent), the BAM records are then written in output order (BGZF compression on the htslib worker threads)
@@ -247,12 +258,13 @@ struct TbWindowPacker {
     if (reaper) reaper->push(std::move(held));
     else for (GSamRecord* r : held) delete r;
     held = std::vector<GSamRecord*>();
+    if (gate) gate->done();
     t_tagwrite_only += std::chrono::duration<double>(t2b - t2).count();
     ++n_windows;
     auto t3 = clk::now();
     t_pack += std::chrono::duration<double>(t1 - t0).count();
     t_device += std::chrono::duration<double>(t2 - t1).count();
-    t_write += std::chrono::duration<double>(t3 - t2).count();
+    t_write += std::chrono::duration<double>(t3 - t2w).count();
   }
 };
 
@@ -260,18 +272,19 @@ struct TbWindowPacker {
 
 // bounded hand-off queue between the reader thread and the device thread
 struct TbQueue {
+  size_t max_queued = 2;
   std::mutex m; std::condition_variable cv;
-  std::deque<std::unique_ptr<TbWindow>> q; bool done = false;
+  std::deque<std::unique_ptr<TbWindow>> q; bool done = false; long n_popped = 0;
   void push(std::unique_ptr<TbWindow> w) {
     std::unique_lock<std::mutex> lk(m);
-    cv.wait(lk, [&] { return q.size() < 2; });
+    cv.wait(lk, [&] { return q.size() < max_queued; });
     q.push_back(std::move(w)); cv.notify_all();
   }
   std::unique_ptr<TbWindow> pop() {
     std::unique_lock<std::mutex> lk(m);
     cv.wait(lk, [&] { return !q.empty() || done; });
     if (q.empty()) return nullptr;
-    std::unique_ptr<TbWindow> w = std::move(q.front()); q.pop_front(); cv.notify_all();
+    std::unique_ptr<TbWindow> w = std::move(q.front()); q.pop_front(); w->seq = n_popped++; cv.notify_all();
     return w;
   }
   void finish() { std::lock_guard<std::mutex> lk(m); done = true; cv.notify_all(); }
@@ -310,7 +323,7 @@ int main(int argc, char* argv[]) {
   TbWindowPacker packer; packer.init(numSamples); packer.out_fp = out_fp; packer.out_hdr = out_hdr;
   Reaper reaper; packer.reaper = &reaper;
   TbQueue queue;
-  double t_create = 0;
+  double t_create = 0; int n_devices = 1;
   std::thread device_thread([&] {   // owns the CUDA context: one submitting host thread per context
     if (dry_run) {   // checks the reader's contract: file order kept, windows separated by coverage gaps, nothing lost
       long nwin = 0, nrec = 0, bad_order = 0, bad_gap = 0; int last_tid = -1; uint64_t last_end = 0;
@@ -331,14 +344,42 @@ int main(int argc, char* argv[]) {
       fprintf(stderr, "tb_b200 dry run: %ld windows, %ld records, %ld order violations, %ld gap violations\n", nwin, nrec, bad_order, bad_gap);
       return;
     }
-    auto c0 = clk::now();
-    const char* dev_env = getenv("TB_DEVICE");
-    tb_ctx* ctx = tb_create(dev_env ? atoi(dev_env) : 0, numSamples, mode, options.flags, options.max_nh, options.min_qual, keep,
-                            options.collapse_same ? 1 : 0);
-    if (!ctx) tb_die(tb_last_error(NULL));
-    t_create = std::chrono::duration<double>(clk::now() - c0).count();
-    while (std::unique_ptr<TbWindow> w = queue.pop()) packer.flush(ctx, *w);
-    tb_destroy(ctx);
+    // TB_DEVICES=0,1 / 0-3: one worker thread, context and packer per GPU; the windows (independent by construction) are
+    // computed wherever a GPU is free and written in hand-over order. Default: TB_DEVICE (or 0) alone.
+    std::vector<int> devs;
+    if (const char* de = getenv("TB_DEVICES")) {
+      for (const char* q = de; *q;) {
+        char* endp; long a = strtol(q, &endp, 10);
+        if (endp == q) break;
+        long b = a;
+        if (*endp == '-') { q = endp + 1; b = strtol(q, &endp, 10); }
+        for (long d = a; d <= b; ++d) devs.push_back((int)d);
+        q = *endp ? endp + 1 : endp;
+      }
+    }
+    if (devs.empty()) { const char* dev_env = getenv("TB_DEVICE"); devs.push_back(dev_env ? atoi(dev_env) : 0); }
+    const int nd = (int)devs.size();
+    queue.max_queued = (size_t)nd + 1;
+    WriteGate gate;
+    std::vector<TbWindowPacker> packers(nd, packer);
+    std::vector<std::thread> workers;
+    std::vector<double> creates(nd, 0.0);
+    for (int d = 0; d < nd; ++d)
+      workers.emplace_back([&, d] {
+        auto c0 = clk::now();
+        tb_ctx* ctx = tb_create(devs[d], numSamples, mode, options.flags, options.max_nh, options.min_qual, keep, options.collapse_same ? 1 : 0);
+        if (!ctx) tb_die(tb_last_error(NULL));
+        creates[d] = std::chrono::duration<double>(clk::now() - c0).count();
+        packers[d].gate = &gate;
+        while (std::unique_ptr<TbWindow> w = queue.pop()) packers[d].flush(ctx, *w);
+        tb_destroy(ctx);
+      });
+    for (auto& t : workers) t.join();
+    for (int d = 0; d < nd; ++d) {
+      packer.t_pack += packers[d].t_pack; packer.t_device += packers[d].t_device; packer.t_write += packers[d].t_write; packer.n_windows += packers[d].n_windows;
+      if (creates[d] > t_create) t_create = creates[d];
+    }
+    n_devices = nd;
   });
 
   // ---- parallel decode: the files are read independently (the device does the k-way merge), TB_DECODE_THREADS readers
@@ -457,7 +498,7 @@ int main(int argc, char* argv[]) {
   double p = 100.00 - (double)(outCounter * 100.00) / (double)inCounter;
   GMessage("%ld input records written as %ld (%.2f%% reduction)\n", inCounter, outCounter, p);
   if (getenv("TB_TIMING"))
-    fprintf(stderr, "tb_b200 timing: total %.3f s | decode+merge %.3f | pack %.3f | device (H2D+kernels+D2H) %.3f | tag+write %.3f | windows %ld | cuda init %.3f (overlapped) | reader thread includes waiting for the device thread | all windows written at %.3f s, records freed on a background thread\n",
-            std::chrono::duration<double>(clk::now() - t_begin).count(), t_read, packer.t_pack, packer.t_device, packer.t_write, (long)packer.n_windows, t_create, t_before_reap);
+    fprintf(stderr, "tb_b200 timing: total %.3f s | decode+merge %.3f | pack %.3f | device (H2D+kernels+D2H) %.3f | tag+write %.3f | windows %ld on %d GPU(s) | cuda init %.3f (overlapped) | reader thread includes waiting for the device thread | all windows written at %.3f s, records freed on a background thread\n",
+            std::chrono::duration<double>(clk::now() - t_begin).count(), t_read, packer.t_pack, packer.t_device, packer.t_write, (long)packer.n_windows, n_devices, t_create, t_before_reap);
   return 0;
 }
