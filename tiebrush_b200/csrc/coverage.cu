@@ -80,13 +80,13 @@ struct CovIn {
 // its exclusive prefix maximum IS that bundle's end (a bundle starts beyond every earlier end of its tid).
 // Reads every input field once (27 B per record) and writes the bundle id (4 B); no key / prefix arrays.
 #ifndef TB_CBK_ITEMS
-#define TB_CBK_ITEMS 8
+#define TB_CBK_ITEMS 16
 #endif
 #ifndef TB_CBK_MINB
-#define TB_CBK_MINB 4
+#define TB_CBK_MINB 2
 #endif
 constexpr int CBK_THREADS = 256, CBK_ITEMS = TB_CBK_ITEMS, CBK_TILE = CBK_THREADS * CBK_ITEMS;
-// VEC: the per-record columns are 16-byte aligned, so a thread fetches its 8 consecutive records with 128-bit loads
+// VEC: the per-record columns are 16-byte aligned, so a thread fetches its CBK_ITEMS consecutive records with 128-bit loads
 // (a warp request then covers 512 contiguous bytes instead of 32 scattered sectors)
 template <bool VEC, bool HAS_END>
 __global__ void __launch_bounds__(CBK_THREADS, TB_CBK_MINB) cov_bundle_kernel(CovIn in, int check_ops, unsigned long long* __restrict__ st_max,
@@ -276,9 +276,11 @@ __device__ __forceinline__ long long cov_seg_prefix(bool head_in, long long val)
 // words: native 32-bit shared atomics on the low word, the carry / borrow it reports folded into the high word (64-bit
 // shared atomicAdd is a CAS loop on sm_100). Junction weights are pre-aggregated the same way in a small shared hash
 // table. The flush issues one global RED per NON-ZERO cell / occupied junction slot: an order of magnitude fewer global
-// atomics than one per update, and none of them contended inside the CTA.
+// atomics than one per update, and none of them contended inside the CTA. The kernel waits on memory more than it
+// issues, so the geometry buys occupancy: 2048 cells (28 KB of shared memory per CTA with the lists) and a 40-register
+// cap keep 6 CTAs = 48 warps per SM; 4096 cells / 5 CTAs measured 13 % slower on the C4 stream, 7 or 8 CTAs spill.
 #ifndef TB_COV_TILE
-#define TB_COV_TILE 4096
+#define TB_COV_TILE 2048
 #endif
 #ifndef TB_COV_RPT
 #define TB_COV_RPT 16
@@ -287,6 +289,14 @@ constexpr int COV_THREADS = 256;
 constexpr int COV_RPT = TB_COV_RPT;
 constexpr int COV_TILE = TB_COV_TILE;
 constexpr int COV_JSLOTS = 256;
+#ifndef TB_COV_MINB
+#define TB_COV_MINB 6
+#endif
+#ifndef TB_COV_BATCH
+#define TB_COV_BATCH 4
+#endif
+constexpr int COV_BATCH = TB_COV_BATCH;
+static_assert(COV_RPT % COV_BATCH == 0, "COV_RPT must be a multiple of COV_BATCH");
 
 __device__ __forceinline__ void cov_cell_add(uint32_t* lo, uint32_t* hi, uint32_t c, long long w) {   // cell c += w
   const uint32_t wl = (uint32_t)(unsigned long long)w, wh = (uint32_t)((unsigned long long)w >> 32);
@@ -298,122 +308,210 @@ __device__ __forceinline__ void cov_cell_add(uint32_t* lo, uint32_t* hi, uint32_
 struct CovSmem {
   uint32_t lo[COV_TILE], hi[COV_TILE];
   unsigned long long jkey[COV_JSLOTS]; uint32_t jlo[COV_JSLOTS], jhi[COV_JSLOTS];
+  uint16_t list[COV_THREADS * COV_RPT];   // per warp: its records, grouped by CIGAR length class
 };
 
-// One thread per record and round (COV_RPT rounds, records strided by the CTA size so loads coalesce), each thread
-// walking its own CIGAR: a warp costs the instructions of its records, not 32 x the longest CIGAR. Before the walk,
-// adjacent records that are the same alignment (pile-ups of an uncollapsed input) are summed in registers by one
-// segmented prefix sum and only the last record of the run issues updates (warp-uniform branch, skipped on collapsed
-// input); and the -w closing an M block cancels against the +w opening the next when the blocks touch (M I M).
-__global__ void __launch_bounds__(COV_THREADS) cov_accumulate_kernel(CovIn in, const uint32_t* __restrict__ bid, const int32_t* __restrict__ bstart,
-                                                                     const long long* __restrict__ bbase, long long* __restrict__ diff,
-                                                                     int do_cov, int do_junc, JTable jt, long long* __restrict__ status, int check_ops) {
-  __shared__ CovSmem sm;
-  const int64_t rec0 = (int64_t)blockIdx.x * (COV_THREADS * COV_RPT);
-  for (int c = threadIdx.x; c < COV_TILE; c += COV_THREADS) { sm.lo[c] = 0; sm.hi[c] = 0; }
-  for (int c = threadIdx.x; c < COV_JSLOTS; c += COV_THREADS) { sm.jkey[c] = J_EMPTY; sm.jlo[c] = 0; sm.jhi[c] = 0; }
-  long long cell0; int tid0;
-  {
-    const uint32_t b0 = bid[rec0];
-    cell0 = (long long)in.pos[rec0] + 1 + bbase[b0] - (long long)bstart[b0];
-    tid0 = in.tid[rec0];
+// What a record's updates go through: the CTA's shared tile of difference cells and its small junction table, global
+// memory for whatever falls outside.
+struct CovTile {
+  CovSmem* sm; long long cell0; int tid0; long long* diff; JTable jt; long long* status;
+  __device__ __forceinline__ void cell(long long c, long long w) const {
+    const unsigned long long rel = (unsigned long long)(c - cell0);
+    if (rel < (unsigned long long)COV_TILE) cov_cell_add(sm->lo, sm->hi, (uint32_t)rel, w);
+    else atomicAdd((unsigned long long*)&diff[c], (unsigned long long)w);
   }
-  __syncthreads();
-  auto cell_update = [&](long long cell, long long w) {
-    const unsigned long long rel = (unsigned long long)(cell - cell0);
-    if (rel < (unsigned long long)COV_TILE) cov_cell_add(sm.lo, sm.hi, (uint32_t)rel, w);
-    else atomicAdd((unsigned long long*)&diff[cell], (unsigned long long)w);
-  };
-  auto junc_update = [&](int tid, unsigned long long k64, long long w) {
+  __device__ __forceinline__ void junction(int tid, unsigned long long k64, long long w) const {
     if (tid == tid0) {
       uint32_t s = (uint32_t)(tb_mix64(k64) >> 40) & (COV_JSLOTS - 1);
+#pragma unroll 1
       for (int probe = 0; probe < 8; ++probe) {
-        unsigned long long cur = sm.jkey[s];
-        if (cur == J_EMPTY) { cur = atomicCAS(&sm.jkey[s], J_EMPTY, k64); if (cur == J_EMPTY) cur = k64; }
-        if (cur == k64) { cov_cell_add(sm.jlo, sm.jhi, s, w); return; }
+        unsigned long long cur = sm->jkey[s];
+        if (cur == J_EMPTY) { cur = atomicCAS(&sm->jkey[s], J_EMPTY, k64); if (cur == J_EMPTY) cur = k64; }
+        if (cur == k64) { cov_cell_add(sm->jlo, sm->jhi, s, w); return; }
         s = (s + 1) & (COV_JSLOTS - 1);
       }
     }
     junc_insert(jt, tid, k64, w, status);
-  };
-#pragma unroll 1
-  for (int r = 0; r < COV_RPT; ++r) {
-    const int64_t i = rec0 + (int64_t)r * COV_THREADS + threadIdx.x;
-    bool valid = i < in.n;
-    uint32_t c0 = 0, nc = 0; int pos = 0, tid = 0; long long w = 0; uint8_t st = 0;
-    bool dup = false;   // same alignment as record i-1
-    if (valid) {
-      c0 = in.cig_off[i]; nc = in.cig_off[i + 1] - c0;
-      pos = in.pos[i]; tid = in.tid[i]; st = in.strand[i];
-      w = (long long)rintf(in.yc[i] * (float)COV_FX_SCALE);
-      if (i > 0 && in.pos[i - 1] == pos && in.tid[i - 1] == tid && in.strand[i - 1] == st) {
-        const uint32_t p0 = in.cig_off[i - 1];
-        if (c0 - p0 == nc) {
-          dup = true;
-          for (uint32_t q = 0; q < nc; ++q) if (in.cigar[p0 + q] != in.cigar[c0 + q]) { dup = false; break; }
+  }
+};
+
+// setupCoordinates' state (GSam.cpp:351-417) plus the pending -w of the coverage walk, advanced one CIGAR word at a time.
+struct CovWalk {
+  int l = 0, exstart, nclosed = 0, last_end = 0;
+  bool intron = false, ins = false;
+  long long pend = -1;   // difference cell of the pending -w (one past the last M block), -1 = none
+  // the switch of setupCoordinates / addCov as predicated arithmetic (lanes of a warp sit on different ops):
+  //   M,=,X,D : l += len, intron = ins = false      N : close the exon (unless ins && intron), l += len, intron = true
+  //   S,H     : intron = ins = false                I : ins = true                  M alone adds coverage
+  __device__ __forceinline__ void step(const CovTile& t, uint32_t cw, int pos, int tid, unsigned sc, long long shift, long long w,
+                                       int do_cov, int do_junc, int check_ops, int64_t i) {
+    const uint32_t op = cw & 0xf; const int len = (int)(cw >> 4);
+    if (check_ops && !((0x1Fu >> op) & 1u)) atomicMin((unsigned long long*)&t.status[ST_ERRIDX], (unsigned long long)i);   // M I D N S only (tiecov.cpp:219-220)
+    if (op == TB_OP_M) {
+      if (do_cov && len > 0 && w != 0) {
+        const long long a = (long long)(pos + l + 1) + shift;
+        if (pend != a) {       // the -w closing an M block cancels against the +w opening the next when they touch (M I M)
+          if (pend >= 0) t.cell(pend, -w);
+          t.cell(a, w);
         }
+        pend = a + len;
       }
+    } else if (op == TB_OP_N) {
+      if (!ins || !intron) {
+        if (do_junc && nclosed > 0)
+          t.junction(tid, ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc, w);
+        last_end = pos + l; nclosed++;
+      }
+      exstart = pos + l + len;
+    }
+    const bool refc = (0x18Du >> op) & 1u;            // M(0) D(2) N(3) =(7) X(8) consume the reference
+    const bool known = (0x1BFu >> op) & 1u;           // M I D N S H = X: the ops the reference's switch names
+    l += refc ? len : 0;
+    if (known) {
+      ins = (op == TB_OP_I) || (op == TB_OP_N && ins);
+      intron = (op == TB_OP_N) || (op == TB_OP_I && intron);
+    }
+  }
+  __device__ __forceinline__ void finish(const CovTile& t, int tid, unsigned sc, long long w, int do_junc) {
+    if (pend >= 0) t.cell(pend, -w);
+    if (do_junc && nclosed > 0)   // the junction that ends at the last exon
+      t.junction(tid, ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc, w);
+  }
+};
+
+// One warp walks its list: 32 entries per step, neighbours in the list being neighbours in the stream with the same
+// CIGAR length, so the lanes of a step run the same number of words (a step that straddles two classes aside). The fixed
+// columns are loaded together, then the first three CIGAR words and the bundle base together; longer CIGARs load the
+// rest word by word. One loop for every length: the code stays small enough for the instruction cache.
+__device__ __forceinline__ void cov_walk_list(const CovIn& in, const uint32_t* __restrict__ bid, const int32_t* __restrict__ bstart,
+                                              const long long* __restrict__ bbase, const uint16_t* list, unsigned cnt, unsigned lane,
+                                              int64_t wrec0, const CovTile& t, int do_cov, int do_junc, int check_ops) {
+#pragma unroll 1
+  for (unsigned e0 = 0; e0 < cnt; e0 += 32) {
+    const unsigned e = e0 + lane;
+    bool on = e < cnt;
+    int64_t i = 0; uint32_t c0 = 0, nc = 0, b = 0; int pos = 0, tid = 0; float yc = 0.f; unsigned st = 0;
+    if (on) {
+      const unsigned slot = list[e];
+      i = wrec0 + (int64_t)(slot >> 5) * COV_THREADS + (slot & 31);
+      c0 = in.cig_off[i]; nc = in.cig_off[i + 1] - c0;
+      pos = in.pos[i]; tid = in.tid[i]; yc = in.yc[i]; st = in.strand[i]; b = bid[i];
+    }
+    uint32_t cw0 = 0, cw1 = 0, cw2 = 0; long long shift = 0;
+    if (on) {
+      shift = bbase[b] - (long long)bstart[b];   // compact index of 1-based coordinate x is x + shift
+      cw0 = in.cigar[c0];
+      if (nc > 1u) cw1 = in.cigar[c0 + 1];
+      if (nc > 2u) cw2 = in.cigar[c0 + 2];
+    }
+    long long w = on ? (long long)rintf(yc * (float)COV_FX_SCALE) : 0;
+    // Adjacent list entries that are the same alignment (pile-ups of an uncollapsed or synthetic stream) would all hit the
+    // same shared cells: sum their weights in registers by one segmented prefix sum and let the last of the run issue the
+    // updates. The comparison is on registers (neighbour lane by shuffle); skipped when the step has no such pair.
+    bool dup;
+    {
+      const int ppos = __shfl_up_sync(0xffffffffu, pos, 1), ptid = __shfl_up_sync(0xffffffffu, tid, 1);
+      const unsigned pst = __shfl_up_sync(0xffffffffu, st, 1), pnc = __shfl_up_sync(0xffffffffu, nc, 1);
+      const uint32_t pc0 = __shfl_up_sync(0xffffffffu, c0, 1);
+      const uint32_t pw0 = __shfl_up_sync(0xffffffffu, cw0, 1), pw1 = __shfl_up_sync(0xffffffffu, cw1, 1), pw2 = __shfl_up_sync(0xffffffffu, cw2, 1);
+      dup = on && lane > 0 && ppos == pos && ptid == tid && pst == st && pnc == nc && pw0 == cw0 && pw1 == cw1 && pw2 == cw2;   // (an idle lane has nc 0)
+      if (dup)
+        for (uint32_t q = 3; q < nc; ++q) if (in.cigar[pc0 + q] != in.cigar[c0 + q]) { dup = false; break; }
     }
     if (__any_sync(0xffffffffu, dup)) {
       w = cov_seg_prefix(!dup, w);
       const int next_dup = __shfl_down_sync(0xffffffffu, (int)dup, 1);
-      if ((threadIdx.x & 31) != 31 && next_dup) valid = false;   // not the last record of its run inside this warp
+      if (lane != 31 && next_dup) on = false;   // not the last record of its run inside this step
     }
-    if (!valid) continue;
-    const uint32_t b = bid[i];
-    const long long shift = bbase[b] - (long long)bstart[b];  // compact index of 1-based coordinate x is x + shift
-    const unsigned sc = strand_code(st);
-    // setupCoordinates state (GSam.cpp:351-417) for the junctions
-    int l = 0, exstart = pos, nclosed = 0, last_end = 0;
-    bool intron = false, ins = false;
-    long long pend = -1;   // difference cell of the pending -w (one past the last M block), -1 = none
-    if (check_ops && nc >= 256u) atomicMin((unsigned long long*)&status[ST_ERRIDX], (unsigned long long)i);   // tiecov.cpp:198
+    if (!on) continue;
+    const unsigned sc = strand_code((uint8_t)st);
+    CovWalk wk; wk.exstart = pos;
+    if (check_ops && nc >= 256u) atomicMin((unsigned long long*)&t.status[ST_ERRIDX], (unsigned long long)i);   // tiecov.cpp:198
+#pragma unroll 1
     for (uint32_t q = 0; q < nc; ++q) {
-      const uint32_t cw = in.cigar[c0 + q];
-      const uint32_t op = cw & 0xf; const int len = (int)(cw >> 4);
-      if (check_ops && !((0x1Fu >> op) & 1u)) atomicMin((unsigned long long*)&status[ST_ERRIDX], (unsigned long long)i);   // M I D N S only (tiecov.cpp:219-220)
-      // the switch of setupCoordinates / addCov as predicated arithmetic (lanes of a warp sit on different ops):
-      //   M,=,X,D : l += len, intron = ins = false      N : close the exon (unless ins && intron), l += len, intron = true
-      //   S,H     : intron = ins = false                I : ins = true                  M alone adds coverage
-      if (op == TB_OP_M) {
-        if (do_cov && len > 0 && w != 0) {
-          const long long a = (long long)(pos + l + 1) + shift;
-          if (pend != a) {
-            if (pend >= 0) cell_update(pend, -w);
-            cell_update(a, w);
-          }
-          pend = a + len;
-        }
-      } else if (op == TB_OP_N) {
-        if (!ins || !intron) {
-          if (do_junc && nclosed > 0)
-            junc_update(tid, ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc, w);
-          last_end = pos + l; nclosed++;
-        }
-        exstart = pos + l + len;
-      }
-      const bool refc = (0x18Du >> op) & 1u;            // M(0) D(2) N(3) =(7) X(8) consume the reference
-      const bool known = (0x1BFu >> op) & 1u;           // M I D N S H = X: the ops the reference's switch names
-      l += refc ? len : 0;
-      if (known) {
-        ins = (op == TB_OP_I) || (op == TB_OP_N && ins);
-        intron = (op == TB_OP_N) || (op == TB_OP_I && intron);
-      }
+      const uint32_t cw = q == 0 ? cw0 : (q == 1 ? cw1 : (q == 2 ? cw2 : in.cigar[c0 + q]));
+      wk.step(t, cw, pos, tid, sc, shift, w, do_cov, do_junc, check_ops, i);
     }
-    if (pend >= 0) cell_update(pend, -w);
-    if (do_junc && nclosed > 0)   // the junction that ends at the last exon
-      junc_update(tid, ((unsigned long long)(uint32_t)(last_end + 1) << 33) | ((unsigned long long)(uint32_t)exstart << 2) | sc, w);
+    wk.finish(t, tid, sc, w, do_junc);
   }
+}
+
+// K7. A CTA owns COV_RPT*256 consecutive records, a warp every eighth group of 32 of them. A lane's warp pays for the
+// longest CIGAR among its 32 records, and the C4 stream mixes 1-, 3- and 5-word CIGARs evenly, so each warp first SORTS
+// its 512 records by CIGAR length class (1, 3, 2, 4, 5 words, longer) into its own shared list — classes counted and
+// ranked with match / redux warp primitives on six 10-bit counters packed in two registers, no atomics, no CTA barrier —
+// and then walks the classes one after another (cov_walk_list).
+__global__ void __launch_bounds__(COV_THREADS, TB_COV_MINB) cov_accumulate_kernel(CovIn in, const uint32_t* __restrict__ bid, const int32_t* __restrict__ bstart,
+                                                                     const long long* __restrict__ bbase, long long* __restrict__ diff,
+                                                                     int do_cov, int do_junc, JTable jt, long long* __restrict__ status, int check_ops) {
+  __shared__ CovSmem sm;
+  static_assert(COV_RPT * 3 <= 64 && COV_RPT * 32 < 1024, "class word / packed counters sized for <= 21 rounds");
+  const int64_t rec0 = (int64_t)blockIdx.x * (COV_THREADS * COV_RPT);
+  for (int c = threadIdx.x; c < COV_TILE; c += COV_THREADS) { sm.lo[c] = 0; sm.hi[c] = 0; }
+  for (int c = threadIdx.x; c < COV_JSLOTS; c += COV_THREADS) { sm.jkey[c] = J_EMPTY; sm.jlo[c] = 0; sm.jhi[c] = 0; }
+  CovTile t; t.sm = &sm; t.diff = diff; t.jt = jt; t.status = status;
+  {
+    const uint32_t b0 = bid[rec0];
+    t.cell0 = (long long)in.pos[rec0] + 1 + bbase[b0] - (long long)bstart[b0];
+    t.tid0 = in.tid[rec0];
+  }
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint16_t* list = sm.list + warp * (32 * COV_RPT);
+  // ---- classes, in list order: 0 = 1 CIGAR word, 1 = 3 words, then 2 / 4 / 5 words and longer; 7 = nothing to do
+  // (past the end, or an empty CIGAR) ----
+  unsigned long long cls = 0;
+  uint32_t tot_lo = 0, tot_hi = 0;           // packed 10-bit counters: classes 0-2 | classes 3-5 (warp-uniform)
+  auto packed = [](unsigned c, uint32_t& lo, uint32_t& hi) { lo = c < 3 ? 1u << (10 * c) : 0u; hi = (c >= 3 && c < 6) ? 1u << (10 * (c - 3)) : 0u; };
+#pragma unroll 1
+  for (int r0 = 0; r0 < COV_RPT; r0 += COV_BATCH) {
+    uint32_t a0[COV_BATCH], a1[COV_BATCH];
+#pragma unroll
+    for (int k = 0; k < COV_BATCH; ++k) {
+      const int64_t i = rec0 + (int64_t)(r0 + k) * COV_THREADS + threadIdx.x;
+      a0[k] = 0; a1[k] = 0;
+      if (i < in.n) { a0[k] = in.cig_off[i]; a1[k] = in.cig_off[i + 1]; }
+    }
+#pragma unroll
+    for (int k = 0; k < COV_BATCH; ++k) {
+      const uint32_t nc = a1[k] - a0[k];
+      const unsigned c = nc == 0 ? 7u : (nc <= 5u ? (0x43120u >> (4 * (nc - 1u))) & 0xfu : 5u);
+      cls |= (unsigned long long)c << (3 * (r0 + k));
+      uint32_t lo, hi; packed(c, lo, hi);
+      tot_lo += __reduce_add_sync(0xffffffffu, lo); tot_hi += __reduce_add_sync(0xffffffffu, hi);
+    }
+  }
+  unsigned cnt[6], base[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) cnt[k] = ((k < 3 ? tot_lo : tot_hi) >> (10 * (k % 3))) & 1023u;
+  base[0] = 0;
+#pragma unroll
+  for (int k = 1; k < 6; ++k) base[k] = base[k - 1] + cnt[k - 1];
+  uint32_t run_lo = base[0] | (base[1] << 10) | (base[2] << 20), run_hi = base[3] | (base[4] << 10) | (base[5] << 20);   // next free entry of every class
+#pragma unroll 4
+  for (int r = 0; r < COV_RPT; ++r) {
+    const unsigned c = (unsigned)(cls >> (3 * r)) & 7u;
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    if (c < 6u) {
+      const unsigned at = ((c < 3u ? run_lo : run_hi) >> (10 * (c < 3u ? c : c - 3u))) & 1023u;
+      list[at + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)((r << 5) | lane);
+    }
+    uint32_t lo, hi; packed(c, lo, hi);
+    run_lo += __reduce_add_sync(0xffffffffu, lo); run_hi += __reduce_add_sync(0xffffffffu, hi);
+  }
+  __syncwarp();
+  const int64_t wrec0 = rec0 + warp * 32;
+  cov_walk_list(in, bid, bstart, bbase, list, base[5] + cnt[5], lane, wrec0, t, do_cov, do_junc, check_ops);
   __syncthreads();
   if (do_cov)
     for (int c = threadIdx.x; c < COV_TILE; c += COV_THREADS) {
       const unsigned long long v = ((unsigned long long)sm.hi[c] << 32) | sm.lo[c];
-      if (v) atomicAdd((unsigned long long*)&diff[cell0 + c], v);
+      if (v) atomicAdd((unsigned long long*)&diff[t.cell0 + c], v);
     }
   if (do_junc)
     for (int c = threadIdx.x; c < COV_JSLOTS; c += COV_THREADS) {
       const unsigned long long k64 = sm.jkey[c];
-      if (k64 != J_EMPTY) junc_insert(jt, tid0, k64, (long long)(((unsigned long long)sm.jhi[c] << 32) | sm.jlo[c]), status);
+      if (k64 != J_EMPTY) junc_insert(jt, t.tid0, k64, (long long)(((unsigned long long)sm.jhi[c] << 32) | sm.jlo[c]), status);
     }
 }
 
