@@ -205,6 +205,157 @@ __global__ void __launch_bounds__(CBK_THREADS, TB_CBK_MINB) cov_bundle_kernel(Co
   }
 }
 
+// ---- K6 with the end column: three streaming passes instead of two look-back chains -------------------------------
+// With GSamRecord::end supplied there is no CIGAR walk in K6 and the single pass above spends its time waiting on the
+// look-back chains (16 % issue slots, 18 % of the DRAM peak in ncu). Reading the small columns again is cheaper:
+//   P1  maximum key of every tile of 4096 records (tid, end: 8 B per record)            -> device scan: tile prefixes
+//   P2  heads from the exclusive prefix maximum (pos, tid, end, yc: 16 B per record): per thread a 16-bit head mask,
+//       per tile the head count; a head parks the end of the bundle it closes in its own bid slot  -> device scan
+//   P3  bundle ids from the masks alone (0.125 B per record read, 4 B written as 128-bit stores); only the heads touch
+//       pos / tid / the parked end to write bstart, btid, bend and rfirst.
+// 28 B per record in three coalesced passes, no inter-CTA waiting. Same outputs as cov_bundle_kernel (which stays for
+// inputs without the end column and for the pmend pass of the exact path).
+struct TileU64In { const unsigned long long* p; __device__ unsigned long long operator()(int64_t i) const { return p[i]; } };
+struct TileU64Exc { unsigned long long* p; __device__ void operator()(int64_t i, unsigned long long exc, unsigned long long) const { p[i] = exc; } };
+struct TileU32In { const uint32_t* p; __device__ uint32_t operator()(int64_t i) const { return p[i]; } };
+struct TileU32Exc { uint32_t* p; __device__ void operator()(int64_t i, uint32_t exc, uint32_t) const { p[i] = exc; } };
+
+template <bool VEC>
+__global__ void __launch_bounds__(CBK_THREADS) cbk_tilemax_kernel(CovIn in, unsigned long long* __restrict__ tmax) {
+  __shared__ unsigned long long s_red[CBK_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * CBK_TILE + (int64_t)threadIdx.x * CBK_ITEMS;
+  unsigned long long tm = 0;
+  if (VEC && base + CBK_ITEMS <= in.n) {
+#pragma unroll
+    for (int q = 0; q < CBK_ITEMS / 4; ++q) {
+      const int4 t = *reinterpret_cast<const int4*>(in.tid + base + 4 * q);
+      const uint4 e = *reinterpret_cast<const uint4*>(in.end + base + 4 * q);
+      const unsigned long long k0 = ((unsigned long long)(uint32_t)t.x << 32) | e.x, k1 = ((unsigned long long)(uint32_t)t.y << 32) | e.y,
+                               k2 = ((unsigned long long)(uint32_t)t.z << 32) | e.z, k3 = ((unsigned long long)(uint32_t)t.w << 32) | e.w;
+      const unsigned long long a = k0 > k1 ? k0 : k1, b = k2 > k3 ? k2 : k3, c = a > b ? a : b;
+      tm = c > tm ? c : tm;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < CBK_ITEMS; ++k)
+      if (base + k < in.n) {
+        const unsigned long long key = ((unsigned long long)(uint32_t)in.tid[base + k] << 32) | (uint32_t)in.end[base + k];
+        tm = key > tm ? key : tm;
+      }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, tm, d); tm = o > tm ? o : tm; }
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = tm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < CBK_THREADS / 32; ++w) tm = s_red[w] > tm ? s_red[w] : tm;
+    tmax[blockIdx.x] = tm;
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(CBK_THREADS) cbk_heads_kernel(CovIn in, const unsigned long long* __restrict__ tpre, uint16_t* __restrict__ masks,
+                                                                uint32_t* __restrict__ theads, uint32_t* bid, long long* __restrict__ status) {
+  static_assert(CBK_ITEMS <= 16, "16-bit head masks");
+  __shared__ unsigned long long s_scan64[33];
+  __shared__ uint32_t s_red[CBK_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * CBK_TILE + (int64_t)threadIdx.x * CBK_ITEMS;
+  int pos[CBK_ITEMS], tidv[CBK_ITEMS]; uint32_t endv[CBK_ITEMS]; float ycv[CBK_ITEMS];
+  if (VEC && base + CBK_ITEMS <= in.n) {
+#pragma unroll
+    for (int q = 0; q < CBK_ITEMS / 4; ++q) {
+      const int4 p = *reinterpret_cast<const int4*>(in.pos + base + 4 * q), t = *reinterpret_cast<const int4*>(in.tid + base + 4 * q);
+      const uint4 e = *reinterpret_cast<const uint4*>(in.end + base + 4 * q);
+      const float4 y = *reinterpret_cast<const float4*>(in.yc + base + 4 * q);
+      pos[4 * q] = p.x; pos[4 * q + 1] = p.y; pos[4 * q + 2] = p.z; pos[4 * q + 3] = p.w;
+      tidv[4 * q] = t.x; tidv[4 * q + 1] = t.y; tidv[4 * q + 2] = t.z; tidv[4 * q + 3] = t.w;
+      endv[4 * q] = e.x; endv[4 * q + 1] = e.y; endv[4 * q + 2] = e.z; endv[4 * q + 3] = e.w;
+      ycv[4 * q] = y.x; ycv[4 * q + 1] = y.y; ycv[4 * q + 2] = y.z; ycv[4 * q + 3] = y.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < CBK_ITEMS; ++k) {
+      const int64_t i = base + k;
+      pos[k] = 0; tidv[k] = 0; endv[k] = 0; ycv[k] = 0.f;
+      if (i < in.n) { pos[k] = in.pos[i]; tidv[k] = in.tid[i]; endv[k] = (uint32_t)in.end[i]; ycv[k] = in.yc[i]; }
+    }
+  }
+  unsigned long long tm = 0; bool inexact = false;
+#pragma unroll
+  for (int k = 0; k < CBK_ITEMS; ++k)
+    if (base + k < in.n) {
+      const unsigned long long key = ((unsigned long long)(uint32_t)tidv[k] << 32) | endv[k];
+      tm = key > tm ? key : tm;
+      const float sc = ycv[k] * (float)COV_FX_SCALE;
+      inexact |= sc != truncf(sc);
+    }
+  if (inexact) status[ST_INEXACT] = 1;  // benign race: any writer stores 1
+  const unsigned long long texc = tb_block_exscan<OpMaxU64>(tm, s_scan64, (unsigned long long*)nullptr);
+  const unsigned long long tp = tpre[blockIdx.x];
+  unsigned long long run = tp > texc ? tp : texc;   // exclusive prefix maximum at this thread's first record
+  uint32_t headm = 0;
+#pragma unroll
+  for (int k = 0; k < CBK_ITEMS; ++k) {
+    const int64_t i = base + k;
+    if (i < in.n) {
+      const bool h = i == 0 || tidv[k] != (int)(run >> 32) || (pos[k] + 1) > (int)(uint32_t)run;   // tiecov.cpp:443
+      if (h) { headm |= 1u << k; bid[i] = (uint32_t)run; }   // parked for P3: the end of the bundle this head closes
+      const unsigned long long key = ((unsigned long long)(uint32_t)tidv[k] << 32) | endv[k];
+      run = key > run ? key : run;
+    }
+  }
+  masks[(int64_t)blockIdx.x * CBK_THREADS + threadIdx.x] = (uint16_t)headm;
+  uint32_t hc = __popc(headm);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) hc += __shfl_xor_sync(0xffffffffu, hc, d);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = hc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < CBK_THREADS / 32; ++w) hc += s_red[w];
+    theads[blockIdx.x] = hc;
+  }
+}
+
+__global__ void __launch_bounds__(CBK_THREADS) cbk_write_kernel(CovIn in, const uint16_t* __restrict__ masks, const uint32_t* __restrict__ thbase,
+                                                                const unsigned long long* __restrict__ tpre, const unsigned long long* __restrict__ tmax,
+                                                                uint32_t* bid, int32_t* __restrict__ bstart, int32_t* __restrict__ bend,
+                                                                int32_t* __restrict__ btid, uint32_t* __restrict__ rfirst, long long* __restrict__ status) {
+  __shared__ uint32_t s_scan32[33];
+  const int64_t base = (int64_t)blockIdx.x * CBK_TILE + (int64_t)threadIdx.x * CBK_ITEMS;
+  const uint32_t headm = masks[(int64_t)blockIdx.x * CBK_THREADS + threadIdx.x];
+  const uint32_t hexc = tb_block_exscan<OpSumU32>((uint32_t)__popc(headm), s_scan32, (uint32_t*)nullptr);
+  uint32_t cnt = thbase[blockIdx.x] + hexc;   // heads before this thread's first record
+  uint32_t ids[CBK_ITEMS];
+#pragma unroll
+  for (int k = 0; k < CBK_ITEMS; ++k) {
+    const int64_t i = base + k;
+    if (headm & (1u << k)) {
+      const uint32_t b = cnt++;
+      bstart[b] = in.pos[i] + 1; btid[b] = in.tid[i];
+      if (b > 0) bend[b - 1] = (int)bid[i];   // parked by P2; this head closes the previous bundle
+      if (rfirst) rfirst[b] = (uint32_t)i;
+    }
+    ids[k] = cnt - 1;
+  }
+  if (base + CBK_ITEMS <= in.n) {
+#pragma unroll
+    for (int q = 0; q < CBK_ITEMS / 4; ++q)
+      *reinterpret_cast<uint4*>(bid + base + 4 * q) = make_uint4(ids[4 * q], ids[4 * q + 1], ids[4 * q + 2], ids[4 * q + 3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < CBK_ITEMS; ++k) if (base + k < in.n) bid[base + k] = ids[k];
+  }
+  if (base < in.n && in.n - 1 < base + CBK_ITEMS) {   // the thread of the last record: close the last bundle
+    const unsigned long long a = tpre[blockIdx.x], b = tmax[blockIdx.x], fin = a > b ? a : b;
+    uint32_t last = 0;
+#pragma unroll
+    for (int k = 0; k < CBK_ITEMS; ++k) if (base + k == in.n - 1) last = ids[k];
+    bend[last] = (int)(uint32_t)fin; status[ST_NBUNDLES] = (long long)last + 1;
+  }
+}
+
 struct BLenIn {
   const int32_t* bstart; const int32_t* bend; const long long* status;
   __device__ long long operator()(int64_t b) const {
@@ -902,11 +1053,31 @@ int tc_coverage_impl(tb_ctx* ctx, const tc_soa_in* hin, tc_runs_out* runs, tc_ju
   if (ctx->profiling) TB_CUDA(cudaEventRecord(ctx->ev[8], st));
   auto launch_k6 = [&](bool use_end) -> int {
     const int64_t ntiles = (n + CBK_TILE - 1) / CBK_TILE;
+    const bool vec = (((uintptr_t)in.pos | (uintptr_t)in.tid | (uintptr_t)in.cig_off | (uintptr_t)in.yc | (uintptr_t)in.end) & 15u) == 0 && !getenv("TB_COV_NOVEC");
+    if (use_end && !d_pmend && !getenv("TB_COV_LOOKBACK")) {   // three streaming passes (see cbk_tilemax_kernel)
+      const int64_t sb = tb_scan_blocks(ntiles) + 8;
+      TB_CUDA(B[CB_KEY].ensure(sizeof(uint64_t) * ((size_t)ntiles * (3 + CBK_THREADS / 4) + (size_t)sb + 16)));
+      unsigned long long* tmax = B[CB_KEY].as<unsigned long long>();
+      unsigned long long* tpre = tmax + ntiles;
+      unsigned long long* agg = tpre + ntiles;
+      uint32_t* theads = reinterpret_cast<uint32_t*>(agg + sb);
+      uint32_t* thbase = theads + ntiles;
+      uint16_t* masks = reinterpret_cast<uint16_t*>(thbase + ntiles);
+      if (vec) cbk_tilemax_kernel<true><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, tmax);
+      else cbk_tilemax_kernel<false><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, tmax);
+      TB_CUDA((tb_device_scan<OpMaxU64>(ctx, TileU64In{tmax}, ntiles, agg, TileU64Exc{tpre})));
+      if (vec) cbk_heads_kernel<true><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, tpre, masks, theads, B[CB_BID].as<uint32_t>(), d_status);
+      else cbk_heads_kernel<false><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, tpre, masks, theads, B[CB_BID].as<uint32_t>(), d_status);
+      TB_CUDA((tb_device_scan<OpSumU32>(ctx, TileU32In{theads}, ntiles, reinterpret_cast<uint32_t*>(agg), TileU32Exc{thbase})));
+      cbk_write_kernel<<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, masks, thbase, tpre, tmax, B[CB_BID].as<uint32_t>(), B[CB_BSTART].as<int32_t>(),
+                                                              B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_rfirst, d_status);
+      ctx->launches += 3;
+      return 0;
+    }
     unsigned long long* st_max = B[CB_KEY].as<unsigned long long>();
     unsigned long long* st_cnt = st_max + ntiles;
     unsigned long long* ticket = st_cnt + ntiles;
     TB_CUDA(cudaMemsetAsync(st_max, 0, sizeof(uint64_t) * (2 * (size_t)ntiles + 8), st));
-    const bool vec = (((uintptr_t)in.pos | (uintptr_t)in.tid | (uintptr_t)in.cig_off | (uintptr_t)in.yc | (uintptr_t)in.end) & 15u) == 0 && !getenv("TB_COV_NOVEC");
 #define TB_K6(V, E) cov_bundle_kernel<V, E><<<(unsigned)ntiles, CBK_THREADS, 0, st>>>(in, do_cov, st_max, st_cnt, ticket, B[CB_BID].as<uint32_t>(), \
       B[CB_BSTART].as<int32_t>(), B[CB_BEND].as<int32_t>(), B[CB_BTID].as<int32_t>(), d_pmend, d_rfirst, d_status)
     if (use_end) { if (vec) TB_K6(true, true); else TB_K6(false, true); }
