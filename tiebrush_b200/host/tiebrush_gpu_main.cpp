@@ -15,10 +15,11 @@
 // merge itself); the raw GSamRecords of a window stay alive until rep_index[] comes back, then the representatives
 // get their tags and are written, the rest are freed.
 //
-// Host pipeline (first step): the main thread decodes + merges (the reference's TInputFiles) and cuts
-// windows; a second thread owns the CUDA context and does pack -> tb_collapse_window -> tag patching -> BAM write (BGZF
-// compression on TB_IO_THREADS htslib worker threads) -> free, so decode of window w+1 overlaps device + write of window w,
-// and CUDA start-up overlaps the first window's decode.
+// Host pipeline: three stages on their own threads. The main thread decodes (TB_DECODE_THREADS readers)
+// and cuts windows; a device thread per GPU owns a CUDA context and does pack -> tb_collapse_window; a writer thread patches
+// the tags of the representatives and writes the BAM records strictly in hand-over order (BGZF compression on TB_IO_THREADS
+// htslib worker threads) and hands the records to a background deleter. Decode of window w+2, pack + device of window w+1
+// and tag + write of window w overlap, and CUDA start-up overlaps the first window's decode.
 //
 // No CPU fallback: without a CUDA device tb_create() fails and the tool exits 1 like any other GError.
 #define main tb_reference_main_unused
@@ -31,6 +32,7 @@
 #include <mutex>
 #include <condition_variable>
 #include <deque>
+#include <map>
 #include <memory>
 #include <functional>
 #include "tiebrush_b200.h"
@@ -77,17 +79,77 @@ struct Reaper {
   void finish() { { std::lock_guard<std::mutex> lk(m); done = true; } cv.notify_all(); th.join(); }
 };
 
-// windows may be computed on several GPUs at once (TB_DEVICES) but are tagged and written strictly in hand-over order
-struct WriteGate {
-  std::mutex m; std::condition_variable cv; long next = 0;
-  void wait_turn(long seq) { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return next == seq; }); }
-  void done() { { std::lock_guard<std::mutex> lk(m); ++next; } cv.notify_all(); }
+// What the device thread hands to the writer: the window's records and the groups tb_collapse_window returned for them.
+struct WriteJob {
+  long seq = 0; int64_t n_kept = 0, n_groups = 0;
+  std::vector<GSamRecord*> held;
+  std::vector<uint32_t> rep, yx; std::vector<float> yc; std::vector<int32_t> yd;
+};
+
+// The writer thread: windows may be computed on several GPUs at once (TB_DEVICES) and finish in any order, but they are tagged
+// and written strictly in hand-over order (flushPData, tiebrush.cpp:506-527). A job is admitted when it is the next one to
+// write or fewer than `cap` are waiting, so a slow output throttles the device threads without ever blocking the job the
+// writer is waiting for.
+struct Writer {
+  htsFile* fp = NULL; sam_hdr_t* hdr = NULL; Reaper* reaper = NULL; int nt = 1; size_t cap = 2;
+  std::mutex m; std::condition_variable cv; std::map<long, WriteJob> pend; long next = 0; bool done = false;
+  double t_write = 0; std::thread th;
+  void start() { th = std::thread([this] { run(); }); }
+  void push(WriteJob&& j) {
+    std::unique_lock<std::mutex> lk(m);
+    const long seq = j.seq;
+    cv.wait(lk, [&] { return seq == next || pend.size() < cap; });
+    pend.emplace(seq, std::move(j));
+    cv.notify_all();
+  }
+  void finish() { { std::lock_guard<std::mutex> lk(m); done = true; } cv.notify_all(); if (th.joinable()) th.join(); }
+  void run() {
+    for (;;) {
+      WriteJob j;
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return pend.count(next) != 0 || (done && pend.empty()); });
+        auto it = pend.find(next);
+        if (it == pend.end()) return;
+        j = std::move(it->second); pend.erase(it);
+      }
+      auto t0 = std::chrono::steady_clock::now();
+      emit(j);
+      t_write += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      { std::lock_guard<std::mutex> lk(m); ++next; }
+      cv.notify_all();
+    }
+  }
+  void emit(WriteJob& j) {
+    inCounter += (uint64_t)j.n_kept;                                 // tiebrush.cpp:573
+    // the tags of the representatives are patched on `nt` threads (records are independent), the BAM records are then written
+    // in output order (BGZF compression on the htslib worker threads)
+    const int64_t G = j.n_groups;
+    auto patch = [&](int64_t g) {
+      GSamRecord* r = j.held[j.rep[g]];
+      r->add_double_tag("YC", (double)j.yc[g]);
+      r->add_int_tag("YX", (int64_t)j.yx[g]);
+      if (j.yd[g] > 0) r->add_int_tag("YD", j.yd[g]); else r->remove_tag("YD");
+    };
+    if (nt == 1 || G < 20000) { for (int64_t g = 0; g < G; ++g) patch(g); }
+    else {
+      std::vector<std::thread> w;
+      for (int t = 0; t < nt; ++t) w.emplace_back([&, t] { for (int64_t g = G * t / nt; g < G * (t + 1) / nt; ++g) patch(g); });
+      for (auto& x : w) x.join();
+    }
+    for (int64_t g = 0; g < G; ++g) {
+      if (sam_write1(fp, hdr, j.held[j.rep[g]]->get_b()) < 0) GError("Error writing SAM record!\n");   // GSamWriter::write, GSam.h:648-653
+      outCounter++;
+    }
+    // the window's records (millions of bam1_t + exon vectors) go back to the allocator on a background thread
+    if (reaper) reaper->push(std::move(j.held));
+    else for (GSamRecord* r : j.held) delete r;
+  }
 };
 
 struct TbWindowPacker {
   int k = 0;
-  WriteGate* gate = NULL;
-  htsFile* out_fp = NULL; sam_hdr_t* out_hdr = NULL;
+  Writer* writer = NULL;
   // SoA staging (reused between windows)
   std::vector<int64_t> run_off;
   std::vector<int32_t> pos, yx_in, yd_in;
@@ -99,8 +161,7 @@ struct TbWindowPacker {
   std::vector<float> yc_in;
   std::vector<GSamRecord*> held;                    // window index -> record
   std::vector<uint32_t> o_rep, o_yx; std::vector<float> o_yc; std::vector<int32_t> o_yd;
-  double t_pack = 0, t_device = 0, t_write = 0, t_tagwrite_only = 0;
-  struct Reaper* reaper = NULL;
+  double t_pack = 0, t_device = 0;
   int64_t n_windows = 0;
 
   void init(int nfiles) { k = nfiles; }
@@ -115,7 +176,7 @@ struct TbWindowPacker {
     const size_t n = w.n; const int tid = w.tid;
     std::vector<std::vector<GSamRecord*>>& per_file = w.per_file;
     std::vector<uint8_t>& file_merged = w.file_merged;
-    if (n == 0) return;
+    if (n == 0) { WriteJob e; e.seq = w.seq; writer->push(std::move(e)); return; }
     using clk = std::chrono::steady_clock;
     auto t0 = clk::now();
     const bool want_md = mrgStrategy == tMrgStratFull;
@@ -229,42 +290,14 @@ struct TbWindowPacker {
     auto t1 = clk::now();
     if (tb_collapse_window(ctx, &in, &out)) tb_die(tb_last_error(ctx));
     auto t2 = clk::now();
-    if (gate) gate->wait_turn(w.seq);
-    auto t2w = clk::now();
-    inCounter += (uint64_t)out.n_kept;                               // tiebrush.cpp:573
-    {   // flushPData, tiebrush.cpp:506-527: the tags of the representatives are patched on the pack threads (records are
-        // independent), the BAM records are then written in output order (BGZF compression on the htslib worker threads)
-      const int64_t G = out.n_groups;
-      auto patch = [&](int64_t g) {
-        GSamRecord* r = held[o_rep[g]];
-        r->add_double_tag("YC", (double)o_yc[g]);
-        r->add_int_tag("YX", (int64_t)o_yx[g]);
-        if (o_yd[g] > 0) r->add_int_tag("YD", o_yd[g]); else r->remove_tag("YD");
-      };
-      if (nt == 1 || G < 20000) { for (int64_t g = 0; g < G; ++g) patch(g); }
-      else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; ++t) th.emplace_back([&, t] { for (int64_t g = G * t / nt; g < G * (t + 1) / nt; ++g) patch(g); });
-        for (auto& x : th) x.join();
-      }
-      for (int64_t g = 0; g < G; ++g) {
-        if (sam_write1(out_fp, out_hdr, held[o_rep[g]]->get_b()) < 0) GError("Error writing SAM record!\n");   // GSamWriter::write, GSam.h:648-653
-        outCounter++;
-      }
-    }
-    auto t2b = clk::now();
-    // the window's records (millions of bam1_t + exon vectors) go back to the allocator on a background thread: off the
-    // device thread's critical path, overlapping the next window
-    if (reaper) reaper->push(std::move(held));
-    else for (GSamRecord* r : held) delete r;
-    held = std::vector<GSamRecord*>();
-    if (gate) gate->done();
-    t_tagwrite_only += std::chrono::duration<double>(t2b - t2).count();
+    WriteJob job;
+    job.seq = w.seq; job.n_kept = out.n_kept; job.n_groups = out.n_groups;
+    job.held = std::move(held); job.rep = std::move(o_rep); job.yc = std::move(o_yc); job.yx = std::move(o_yx); job.yd = std::move(o_yd);
+    held = std::vector<GSamRecord*>(); o_rep = std::vector<uint32_t>(); o_yc = std::vector<float>(); o_yx = std::vector<uint32_t>(); o_yd = std::vector<int32_t>();
+    writer->push(std::move(job));   // blocks while the writer is more than a window behind
     ++n_windows;
-    auto t3 = clk::now();
     t_pack += std::chrono::duration<double>(t1 - t0).count();
     t_device += std::chrono::duration<double>(t2 - t1).count();
-    t_write += std::chrono::duration<double>(t3 - t2w).count();
   }
 };
 
@@ -310,7 +343,7 @@ int main(int argc, char* argv[]) {
   const int mode = mrgStrategy == tMrgStratFull ? TB_MODE_FULL : mrgStrategy == tMrgStratClip ? TB_MODE_CLIP :
                    mrgStrategy == tMrgStratExon ? TB_MODE_EXON : TB_MODE_CIGAR;
   // records buffered before a coverage gap closes the window (TB_WINDOW_RECORDS; host memory ~ 400 B per record)
-  size_t window_min = 1u << 20;
+  size_t window_min = 1u << 19;   // 512 K: with three pipeline stages the last window's pack + device + write is the exposed tail
   if (const char* e = getenv("TB_WINDOW_RECORDS")) { long v = atol(e); if (v > 0) window_min = (size_t)v; }
 
   // The window is cut only at a coordinate no read covers; an input without such a gap (a deep locus, DNA-seq) would buffer a
@@ -320,8 +353,15 @@ int main(int argc, char* argv[]) {
   if (const char* e = getenv("TB_WINDOW_MAX_RECORDS")) { long long v = atoll(e); if (v > 0) window_max = (size_t)v; }
   if (window_max > 2000000000u) window_max = 2000000000u;
   const bool dry_run = getenv("TB_DRYRUN") != NULL;   // reader self-check: no device, no output records, window statistics only
-  TbWindowPacker packer; packer.init(numSamples); packer.out_fp = out_fp; packer.out_hdr = out_hdr;
-  Reaper reaper; packer.reaper = &reaper;
+  TbWindowPacker packer; packer.init(numSamples);
+  Reaper reaper;
+  Writer writer; writer.fp = out_fp; writer.hdr = out_hdr; writer.reaper = &reaper;
+  {
+    int nt = (int)std::thread::hardware_concurrency(); if (nt > 16) nt = 16;
+    if (const char* e = getenv("TB_PACK_THREADS")) nt = atoi(e);
+    writer.nt = nt < 1 ? 1 : nt;
+  }
+  packer.writer = &writer;
   TbQueue queue;
   double t_create = 0; int n_devices = 1;
   std::thread device_thread([&] {   // owns the CUDA context: one submitting host thread per context
@@ -360,7 +400,8 @@ int main(int argc, char* argv[]) {
     if (devs.empty()) { const char* dev_env = getenv("TB_DEVICE"); devs.push_back(dev_env ? atoi(dev_env) : 0); }
     const int nd = (int)devs.size();
     queue.max_queued = (size_t)nd + 1;
-    WriteGate gate;
+    writer.cap = (size_t)nd + 1;
+    writer.start();
     std::vector<TbWindowPacker> packers(nd, packer);
     std::vector<std::thread> workers;
     std::vector<double> creates(nd, 0.0);
@@ -370,13 +411,13 @@ int main(int argc, char* argv[]) {
         tb_ctx* ctx = tb_create(devs[d], numSamples, mode, options.flags, options.max_nh, options.min_qual, keep, options.collapse_same ? 1 : 0);
         if (!ctx) tb_die(tb_last_error(NULL));
         creates[d] = std::chrono::duration<double>(clk::now() - c0).count();
-        packers[d].gate = &gate;
         while (std::unique_ptr<TbWindow> w = queue.pop()) packers[d].flush(ctx, *w);
         tb_destroy(ctx);
       });
     for (auto& t : workers) t.join();
+    writer.finish();
     for (int d = 0; d < nd; ++d) {
-      packer.t_pack += packers[d].t_pack; packer.t_device += packers[d].t_device; packer.t_write += packers[d].t_write; packer.n_windows += packers[d].n_windows;
+      packer.t_pack += packers[d].t_pack; packer.t_device += packers[d].t_device; packer.n_windows += packers[d].n_windows;
       if (creates[d] > t_create) t_create = creates[d];
     }
     n_devices = nd;
@@ -499,6 +540,6 @@ int main(int argc, char* argv[]) {
   GMessage("%ld input records written as %ld (%.2f%% reduction)\n", inCounter, outCounter, p);
   if (getenv("TB_TIMING"))
     fprintf(stderr, "tb_b200 timing: total %.3f s | decode+merge %.3f | pack %.3f | device (H2D+kernels+D2H) %.3f | tag+write %.3f | windows %ld on %d GPU(s) | cuda init %.3f (overlapped) | reader thread includes waiting for the device thread | all windows written at %.3f s, records freed on a background thread\n",
-            std::chrono::duration<double>(clk::now() - t_begin).count(), t_read, packer.t_pack, packer.t_device, packer.t_write, (long)packer.n_windows, n_devices, t_create, t_before_reap);
+            std::chrono::duration<double>(clk::now() - t_begin).count(), t_read, packer.t_pack, packer.t_device, writer.t_write, (long)packer.n_windows, n_devices, t_create, t_before_reap);
   return 0;
 }
